@@ -1,0 +1,75 @@
+// Shared device helpers: error checks, storage-type traits (fp32 | bf16), epilogue evaluation.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+#include "graph.h"
+
+namespace b200ocr {
+
+#define B200_CUDA_CHECK(expr)                                                                        \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + \
+                                     __FILE__ + ":" + std::to_string(__LINE__) + " (" #expr ")");    \
+    } while (0)
+
+inline int cpad_of(int c) { return c == 1 ? 1 : (c <= 4 ? 4 : (c + 7) / 8 * 8); }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+typedef __nv_bfloat16 bf16;
+
+template <typename T> struct ST;   // storage traits
+template <> struct ST<float> {
+    static __device__ __forceinline__ float ld(const float* p) { return *p; }
+    static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+    static __device__ __forceinline__ void ld4(const float* p, float* v) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void st4(float* p, const float* v) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct ST<bf16> {
+    static __device__ __forceinline__ float ld(const bf16* p) { return __bfloat162float(*p); }
+    static __device__ __forceinline__ void st(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+    static __device__ __forceinline__ void ld4(const bf16* p, float* v) {
+        uint2 t = *reinterpret_cast<const uint2*>(p);
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void st4(bf16* p, const float* v) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 t;
+        t.x = *reinterpret_cast<uint32_t*>(&a);
+        t.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(p) = t;
+    }
+};
+
+__device__ __forceinline__ float epi_apply(float v, const Epilogue& e) {
+#pragma unroll 1
+    for (int i = 0; i < e.n; ++i) {
+        const EpiStep s = e.s[i];
+        switch (s.type) {
+            case EPI_AFFINE: v = fmaf(v, s.a, s.b); break;
+            case EPI_RELU: v = fmaxf(v, 0.f); break;
+            case EPI_HSWISH: v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) / 6.f; break;
+            case EPI_SIGMOID: v = 1.f / (1.f + expf(-v)); break;
+            case EPI_SWISH: v = v * (1.f / (1.f + expf(-v))); break;
+            case EPI_HSIGMOID: v = fminf(fmaxf(fmaf(v, s.a, s.b), 0.f), 1.f); break;
+            case EPI_CLIP: v = fminf(fmaxf(v, s.a), s.b); break;
+            default: break;
+        }
+    }
+    return v;
+}
+
+}  // namespace b200ocr

@@ -1,0 +1,867 @@
+#include "engine.h"
+
+#include <algorithm>
+#include <cstring>
+#include <sstream>
+
+#include "net_kernels.cuh"
+
+namespace b200ocr {
+
+std::vector<int64_t> PVal::logical() const {
+    switch (form) {
+        case F_NCHW: return {n, c, h, w};
+        case F_NCS: return {n, c, (int64_t)h * w};
+        case F_NSC: return {n, (int64_t)h * w, c};
+        case F_NHWC: return {n, h, w, c};
+        case F_NC: return {n, c};
+        default: return host.empty() ? std::vector<int64_t>{} : std::vector<int64_t>{(int64_t)host.size()};
+    }
+}
+
+Plan::~Plan() {
+    if (out_dense) cudaFree(out_dense);
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+}
+
+static int grid_for(int64_t total, int block = 256) {
+    int64_t g = (total + block - 1) / block;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, 148 * 32));
+}
+
+static float* upload(const std::vector<float>& v) {
+    float* d = nullptr;
+    B200_CUDA_CHECK(cudaMalloc(&d, std::max<size_t>(1, v.size()) * sizeof(float)));
+    if (!v.empty()) B200_CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return d;
+}
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ------------------------------------------------------------------------------------ load
+Model::Model(const std::string& path, int precision) : prec_(precision) {
+    OnnxModel m = load_onnx(path);
+    g_ = build_cgraph(m);
+    if (g_->input_shape.size() == 4 && g_->input_shape[1] > 0) in_c_ = (int)g_->input_shape[1];
+    dw_.resize(g_->weights.size());
+    auto pack_dense = [&](int wid, bool convt) {
+        const ConvWeights& cw = g_->weights[wid];
+        DevWeights& d = dw_[wid];
+        int cinp = cpad_of(cw.cin), coutp = cpad_of(cw.cout);
+        int taps = cw.kh * cw.kw;
+        int cols = convt ? 4 * coutp : coutp;
+        d.K = convt ? cinp : taps * cinp;
+        d.Kpad = round_up(d.K, IG_BK);
+        d.ColsW = round_up(cols, 64);
+        std::vector<float> w((size_t)d.Kpad * d.ColsW, 0.f), bias(d.ColsW, 0.f);
+        for (int t = 0; t < taps; ++t)
+            for (int ci = 0; ci < cw.cin; ++ci)
+                for (int co = 0; co < cw.cout; ++co) {
+                    float v = cw.w[((size_t)t * cw.cin + ci) * cw.cout + co];
+                    if (convt) w[(size_t)ci * d.ColsW + t * coutp + co] = v;
+                    else w[((size_t)t * cinp + ci) * d.ColsW + co] = v;
+                }
+        for (int co = 0; co < cw.cout; ++co) bias[co] = cw.bias[co];
+        d.w = upload(w);
+        d.bias = upload(bias);
+    };
+    for (auto& c : g_->nodes) {
+        if (c.kind == C_CONV) pack_dense(c.weight_id, false);
+        else if (c.kind == C_CONVT) pack_dense(c.weight_id, true);
+        else if (c.kind == C_SE) {
+            pack_dense(c.se_w1, false);
+            pack_dense(c.se_w2, false);
+        } else if (c.kind == C_DWCONV) {
+            const ConvWeights& cw = g_->weights[c.weight_id];
+            DevWeights& d = dw_[c.weight_id];
+            int cp = cpad_of(cw.cout), taps = cw.kh * cw.kw;
+            std::vector<float> w((size_t)taps * cp, 0.f), bias(cp, 0.f);
+            for (int t = 0; t < taps; ++t)
+                for (int ch = 0; ch < cw.cout; ++ch) w[(size_t)t * cp + ch] = cw.w[(size_t)t * cw.cout + ch];
+            for (int ch = 0; ch < cw.cout; ++ch) bias[ch] = cw.bias[ch];
+            d.w = upload(w);
+            d.bias = upload(bias);
+            d.ColsW = cp;
+        }
+    }
+    for (auto& v : g_->vecs) {
+        std::vector<float> a = v.a, b = v.b;
+        a.resize(round_up((int)a.size(), 8), 0.f);
+        b.resize(a.size(), 0.f);
+        dvec_.push_back({upload(a), upload(b)});
+    }
+}
+
+Model::~Model() {
+    plans_.clear();
+    for (auto& d : dw_) {
+        if (d.w) cudaFree(d.w);
+        if (d.bias) cudaFree(d.bias);
+        if (d.w_bf16) cudaFree(d.w_bf16);
+    }
+    for (auto& v : dvec_) {
+        cudaFree(v.first);
+        cudaFree(v.second);
+    }
+    if (stage_in_) cudaFree(stage_in_);
+    if (arena_) cudaFree(arena_);
+}
+
+std::string Model::describe() const { return dump_cgraph(*g_); }
+
+// ------------------------------------------------------------------------------------ host shape math
+static std::vector<int64_t> host_eval(const OnnxNode& n, const std::vector<std::vector<int64_t>>& in) {
+    const std::string& op = n.op_type;
+    if (op == "Cast" || op == "Unsqueeze" || op == "Squeeze") return in.at(0);
+    if (op == "Concat") {
+        std::vector<int64_t> r;
+        for (auto& v : in) r.insert(r.end(), v.begin(), v.end());
+        return r;
+    }
+    if (op == "Slice") {
+        const auto& x = in.at(0);
+        int64_t st, en, step = 1;
+        if (in.size() >= 3) {
+            st = in[1].at(0);
+            en = in[2].at(0);
+            if (in.size() >= 5 && !in[4].empty()) step = in[4][0];
+        } else {
+            st = n.attr_ints("starts").at(0);
+            en = n.attr_ints("ends").at(0);
+        }
+        int64_t d = (int64_t)x.size();
+        if (st < 0) st += d;
+        if (en < 0) en += d;
+        st = std::max<int64_t>(0, std::min(st, d));
+        en = std::max<int64_t>(0, std::min(en, d));
+        std::vector<int64_t> r;
+        for (int64_t i = st; i < en; i += step) r.push_back(x[i]);
+        return r;
+    }
+    if (op == "Gather") {
+        std::vector<int64_t> r;
+        for (auto i : in.at(1)) r.push_back(in[0].at(i < 0 ? i + in[0].size() : i));
+        return r;
+    }
+    if (op == "Add" || op == "Sub" || op == "Mul" || op == "Div") {
+        const auto &a = in.at(0), &b = in.at(1);
+        size_t len = std::max(a.size(), b.size());
+        std::vector<int64_t> r(len);
+        for (size_t i = 0; i < len; ++i) {
+            int64_t x = a[a.size() == 1 ? 0 : i], y = b[b.size() == 1 ? 0 : i];
+            r[i] = op == "Add" ? x + y : op == "Sub" ? x - y : op == "Mul" ? x * y : (y ? x / y : 0);
+        }
+        return r;
+    }
+    throw std::runtime_error("host op not supported: " + op);
+}
+
+// ------------------------------------------------------------------------------------ plan
+namespace {
+struct Arena {
+    struct Blk { size_t off, size; };
+    std::vector<Blk> free_;
+    size_t end = 0;
+    size_t alloc(size_t bytes) {
+        bytes = (bytes + 255) / 256 * 256;
+        for (size_t i = 0; i < free_.size(); ++i) {
+            if (free_[i].size >= bytes) {
+                size_t off = free_[i].off;
+                if (free_[i].size == bytes) free_.erase(free_.begin() + i);
+                else { free_[i].off += bytes; free_[i].size -= bytes; }
+                return off;
+            }
+        }
+        // extend: reuse a trailing free block if it touches the end
+        if (!free_.empty() && free_.back().off + free_.back().size == end) {
+            size_t off = free_.back().off;
+            end = off + bytes;
+            free_.pop_back();
+            return off;
+        }
+        size_t off = end;
+        end += bytes;
+        return off;
+    }
+    void release(size_t off, size_t bytes) {
+        bytes = (bytes + 255) / 256 * 256;
+        Blk b{off, bytes};
+        auto it = std::lower_bound(free_.begin(), free_.end(), b, [](const Blk& x, const Blk& y) { return x.off < y.off; });
+        it = free_.insert(it, b);
+        size_t i = it - free_.begin();
+        if (i + 1 < free_.size() && free_[i].off + free_[i].size == free_[i + 1].off) {
+            free_[i].size += free_[i + 1].size;
+            free_.erase(free_.begin() + i + 1);
+        }
+        if (i > 0 && free_[i - 1].off + free_[i - 1].size == free_[i].off) {
+            free_[i - 1].size += free_[i].size;
+            free_.erase(free_.begin() + i);
+        }
+    }
+};
+}  // namespace
+
+Plan* Model::plan_for(int n, int h, int w) {
+    std::vector<int> key{n, h, w};
+    auto it = plans_.find(key);
+    if (it != plans_.end()) return it->second.get();
+    if (plans_.size() >= 96) plans_.clear();            // bounded cache (dynamic rec widths)
+    std::unique_ptr<Plan> p = build_plan(n, h, w);
+    Plan* raw = p.get();
+    plans_[key] = std::move(p);
+    return raw;
+}
+
+std::unique_ptr<Plan> Model::build_plan(int n, int h, int w) {
+    std::unique_ptr<Plan> p(new Plan());
+    p->model_arena = &arena_;
+    p->n = n;
+    p->h = h;
+    p->w = w;
+    if (prec_ == PREC_BF16) build_steps<bf16>(*p);
+    else build_steps<float>(*p);
+    if (p->arena_bytes > arena_cap_) {
+        B200_CUDA_CHECK(cudaDeviceSynchronize());
+        if (arena_) cudaFree(arena_);
+        arena_ = nullptr;
+        arena_cap_ = p->arena_bytes + p->arena_bytes / 8;
+        B200_CUDA_CHECK(cudaMalloc(&arena_, arena_cap_));
+        // pad lanes of every buffer are written by the producing kernels; no memset needed
+    }
+    return p;
+}
+
+template <typename T>
+void Model::build_steps(Plan& p) {
+    const CGraph& g = *g_;
+    std::map<std::string, int> vid;
+    std::vector<int> buf_first, buf_last;
+    std::vector<size_t>& buf_bytes = p.buf_bytes;
+    int cur = 0;   // node index being planned
+
+    auto new_buf = [&](size_t bytes) {
+        buf_bytes.push_back(std::max<size_t>(bytes, 16));
+        buf_first.push_back(cur);
+        buf_last.push_back(cur);
+        return (int)buf_bytes.size() - 1;
+    };
+    auto new_val = [&](int form, int vn, int vh, int vw, int vc) {
+        PVal v;
+        v.form = form; v.n = vn; v.h = vh; v.w = vw; v.c = vc; v.cp = cpad_of(vc);
+        v.root = new_buf((size_t)v.elems() * sizeof(T));
+        p.vals.push_back(v);
+        return (int)p.vals.size() - 1;
+    };
+    auto alias_val = [&](int src, int form, int vh, int vw) {
+        PVal v = p.vals[src];
+        v.form = form; v.h = vh; v.w = vw;
+        p.vals.push_back(v);
+        return (int)p.vals.size() - 1;
+    };
+    std::function<void(int)> use = [&](int v) {
+        const PVal& pv = p.vals[v];
+        if (pv.up_src >= 0) { use(pv.up_src); return; }
+        if (pv.root >= 0) buf_last[pv.root] = std::max(buf_last[pv.root], cur);
+    };
+    auto get = [&](const std::string& name, const CNode& c) -> int {
+        auto it = vid.find(name);
+        if (it == vid.end()) throw std::runtime_error("plan: value '" + name + "' used before definition at " + c.name);
+        return it->second;
+    };
+    Plan* pp = &p;
+    auto emit = [&](const std::string& name, std::function<void(cudaStream_t)> fn) {
+        p.steps.push_back(std::move(fn));
+        p.step_names.push_back(name);
+    };
+    // materialise a virtual upsample
+    auto materialize = [&](int v) -> int {
+        if (p.vals[v].up_src < 0) return v;
+        PVal pv = p.vals[v];
+        int src = pv.up_src;
+        int out = new_val(pv.form, pv.n, pv.h, pv.w, pv.c);
+        use(src);
+        int cp = pv.cp, fh = pv.fh, fw = pv.fw, N = pv.n, H = pv.h, W = pv.w;
+        emit("upsample", [=](cudaStream_t st) {
+            concat_slice_kernel<T><<<grid_for((int64_t)N * H * W * cp), 256, 0, st>>>(
+                (const T*)pp->ptr(src), (T*)pp->ptr(out), N, H, W, cp, cp, cp, 0, fh, fw);
+        });
+        return out;
+    };
+    std::map<std::string, int> nuse;
+    for (auto& c : g.nodes)
+        for (auto& in : c.in) nuse[in]++;
+    nuse[g.output_name]++;
+
+    // graph input
+    cur = -1;
+    p.in_val = new_val(F_NCHW, p.n, p.h, p.w, in_c_);
+    vid[g.input_name] = p.in_val;
+    std::vector<char> skip(g.nodes.size(), 0);
+
+    for (size_t ni = 0; ni < g.nodes.size(); ++ni) {
+        if (skip[ni]) continue;
+        const CNode& c = g.nodes[ni];
+        cur = (int)ni;
+        switch (c.kind) {
+            case C_HOST: {
+                std::vector<std::vector<int64_t>> ins;
+                if (c.host.op_type == "Shape") {
+                    ins.push_back(p.vals[get(c.in[0], c)].logical());
+                    PVal v;
+                    v.form = F_HOST;
+                    v.host = ins[0];
+                    p.vals.push_back(v);
+                } else {
+                    for (auto& in : c.in) {
+                        if (in.empty()) { ins.push_back({}); continue; }
+                        auto hc = g.host_consts.find(in);
+                        if (hc != g.host_consts.end()) {
+                            std::vector<int64_t> t;
+                            if (hc->second.is_float()) for (float f : hc->second.f) t.push_back((int64_t)f);
+                            else t = hc->second.i;
+                            ins.push_back(t);
+                        } else {
+                            ins.push_back(p.vals[get(in, c)].host);
+                        }
+                    }
+                    PVal v;
+                    v.form = F_HOST;
+                    v.host = host_eval(c.host, ins);
+                    p.vals.push_back(v);
+                }
+                vid[c.out] = (int)p.vals.size() - 1;
+                break;
+            }
+            case C_CONV:
+            case C_CONVT: {
+                int in = materialize(get(c.in[0], c));
+                const PVal iv = p.vals[in];
+                bool convt = c.kind == C_CONVT;
+                if (c.is_linear) {
+                    if (iv.form != F_NSC && iv.form != F_NC && iv.form != F_NHWC)
+                        throw std::runtime_error("MatMul on a tensor whose last axis is not the channel axis: " + c.name);
+                } else if (iv.form != F_NCHW) {
+                    throw std::runtime_error("Conv input is not NCHW-shaped: " + c.name);
+                }
+                if (iv.c != c.cin)
+                    throw std::runtime_error("channel mismatch at " + c.name + ": got " + std::to_string(iv.c) +
+                                             " expected " + std::to_string(c.cin));
+                int Ho, Wo;
+                if (convt) { Ho = iv.h; Wo = iv.w; }
+                else {
+                    Ho = (iv.h + c.pt + c.pb - c.kh) / c.sh + 1;
+                    Wo = (iv.w + c.pl + c.pr - c.kw) / c.sw + 1;
+                }
+                if (Ho <= 0 || Wo <= 0) throw std::runtime_error("empty conv output at " + c.name);
+                int out = new_val(iv.form, iv.n, convt ? 2 * Ho : Ho, convt ? 2 * Wo : Wo, c.cout);
+                use(in);
+                const DevWeights& dw = dw_[c.weight_id];
+                ConvP cp;
+                cp.N = iv.n; cp.H = iv.h; cp.W = iv.w; cp.CinP = iv.cp;
+                cp.Ho = Ho; cp.Wo = Wo; cp.Cout = c.cout; cp.CoutP = cpad_of(c.cout);
+                cp.kh = convt ? 1 : c.kh; cp.kw = convt ? 1 : c.kw;
+                cp.sh = convt ? 1 : c.sh; cp.sw = convt ? 1 : c.sw;
+                cp.pt = convt ? 0 : c.pt; cp.pl = convt ? 0 : c.pl;
+                cp.K = dw.K; cp.ColsW = dw.ColsW;
+                cp.Cols = convt ? 4 * cp.CoutP : cp.CoutP;
+                cp.convT = convt ? 1 : 0;
+                cp.M = iv.n * Ho * Wo;
+                cp.epi = c.epi;
+                p.flops += 2.0 * cp.M * (double)c.cout * c.cin * (convt ? 4 : c.kh * c.kw);
+                const float* wptr = dw.w;
+                const float* bptr = dw.bias;
+                int cols = cp.Cols;
+                emit(std::string(convt ? "convT " : c.is_linear ? "linear " : "conv ") + c.name, [=](cudaStream_t st) {
+                    const T* x = (const T*)pp->ptr(in);
+                    T* y = (T*)pp->ptr(out);
+                    if (cols <= 16) {
+                        dim3 grid((unsigned)ceil_div(cp.M, 256), (unsigned)ceil_div(cols, 16));
+                        conv_igemm_kernel<T, 256, 16><<<grid, 256, 0, st>>>(x, wptr, bptr, y, cp);
+                    } else if (cols <= 32) {
+                        dim3 grid((unsigned)ceil_div(cp.M, 128), (unsigned)ceil_div(cols, 32));
+                        conv_igemm_kernel<T, 128, 32><<<grid, 256, 0, st>>>(x, wptr, bptr, y, cp);
+                    } else {
+                        dim3 grid((unsigned)ceil_div(cp.M, 64), (unsigned)ceil_div(cols, 64));
+                        conv_igemm_kernel<T, 64, 64><<<grid, 256, 0, st>>>(x, wptr, bptr, y, cp);
+                    }
+                });
+                vid[c.out] = out;
+                break;
+            }
+            case C_DWCONV: {
+                int in = materialize(get(c.in[0], c));
+                const PVal iv = p.vals[in];
+                if (iv.form != F_NCHW || iv.c != c.cin) throw std::runtime_error("bad depthwise input at " + c.name);
+                int Ho = (iv.h + c.pt + c.pb - c.kh) / c.sh + 1;
+                int Wo = (iv.w + c.pl + c.pr - c.kw) / c.sw + 1;
+                int out = new_val(F_NCHW, iv.n, Ho, Wo, c.cout);
+                use(in);
+                DwP dp;
+                dp.N = iv.n; dp.H = iv.h; dp.W = iv.w; dp.CP = iv.cp; dp.C = iv.c; dp.Ho = Ho; dp.Wo = Wo;
+                dp.kh = c.kh; dp.kw = c.kw; dp.sh = c.sh; dp.sw = c.sw; dp.pt = c.pt; dp.pl = c.pl;
+                dp.epi = c.epi;
+                p.flops += 2.0 * iv.n * Ho * Wo * (double)c.cout * c.kh * c.kw;
+                const float* wptr = dw_[c.weight_id].w;
+                const float* bptr = dw_[c.weight_id].bias;
+                int64_t total = (int64_t)iv.n * Ho * Wo * (iv.cp / 4);
+                emit("dwconv " + c.name, [=](cudaStream_t st) {
+                    dwconv_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)pp->ptr(in), wptr, bptr, (T*)pp->ptr(out), dp);
+                });
+                vid[c.out] = out;
+                break;
+            }
+            case C_SE:
+            case C_GAP: {
+                int in = materialize(get(c.in[0], c));
+                const PVal iv = p.vals[in];
+                if (iv.form != F_NCHW) throw std::runtime_error("GlobalAveragePool input is not NCHW-shaped: " + c.name);
+                if (iv.cp > 1024 || iv.cp < 4) throw std::runtime_error("GlobalAveragePool channel count unsupported: " + c.name);
+                int HW = iv.h * iv.w;
+                int chunks = std::max(1, std::min(64, HW / 2048));
+                int partial = new_buf((size_t)iv.n * chunks * iv.cp * sizeof(float));
+                int rows = std::max(1, 256 / (iv.cp / 4));
+                size_t smem = (size_t)rows * iv.cp * sizeof(float);
+                int N = iv.n, CP = iv.cp, C = iv.c;
+                use(in);
+                emit("gap_partial " + c.name, [=](cudaStream_t st) {
+                    gap_partial_kernel<T><<<dim3(chunks, N), 256, smem, st>>>((const T*)pp->ptr(in), (float*)pp->bufptr(partial),
+                                                                                HW, CP, chunks);
+                });
+                if (c.kind == C_GAP) {
+                    int out = new_val(F_NCHW, iv.n, 1, 1, iv.c);
+                    emit("gap_finish " + c.name, [=](cudaStream_t st) {
+                        gap_finish_kernel<T><<<N, 256, 0, st>>>((const float*)pp->bufptr(partial), (T*)pp->ptr(out), HW, C, CP, chunks);
+                    });
+                    vid[c.out] = out;
+                    break;
+                }
+                if (c.cout != iv.c) throw std::runtime_error("SE channel mismatch at " + c.name);
+                int scale = new_buf((size_t)iv.n * iv.cp * sizeof(float));
+                // y = x + x*s when the very next node adds the SE input back (RSELayer shortcut)
+                int residual = 0;
+                std::string out_name = c.out;
+                Epilogue epi = c.epi;
+                if (ni + 1 < g.nodes.size() && c.epi.n == 0) {
+                    const CNode& nx = g.nodes[ni + 1];
+                    if (nx.kind == C_ADD && nx.epi.n == 0 && nuse[c.out] == 1 &&
+                        ((nx.in[0] == c.in[0] && nx.in[1] == c.out) || (nx.in[1] == c.in[0] && nx.in[0] == c.out))) {
+                        residual = 1;
+                        out_name = nx.out;
+                        skip[ni + 1] = 1;
+                    }
+                }
+                int out = new_val(F_NCHW, iv.n, iv.h, iv.w, iv.c);
+                const DevWeights &w1 = dw_[c.se_w1], &w2 = dw_[c.se_w2];
+                int mid = c.se_mid;
+                float alpha = c.scale, beta = c.eps;
+                size_t smem2 = (size_t)(iv.cp + mid) * sizeof(float);
+                emit("se_fc " + c.name, [=](cudaStream_t st) {
+                    se_fc_kernel<<<N, 256, smem2, st>>>((const float*)pp->bufptr(partial), chunks, HW, C, CP, mid, w1.w, w1.ColsW,
+                                                         w1.bias, w2.w, w2.ColsW, w2.bias, alpha, beta, (float*)pp->bufptr(scale));
+                });
+                int64_t total4 = (int64_t)iv.n * HW * (iv.cp / 4);
+                emit("se_apply " + c.name, [=](cudaStream_t st) {
+                    se_apply_kernel<T><<<grid_for(total4), 256, 0, st>>>((const T*)pp->ptr(in), (const float*)pp->bufptr(scale),
+                                                                          (T*)pp->ptr(out), HW, CP, C, total4, residual, epi);
+                });
+                p.flops += 4.0 * iv.n * (double)iv.c * mid;
+                vid[out_name] = out;
+                break;
+            }
+            case C_MAXPOOL:
+            case C_AVGPOOL: {
+                int in = materialize(get(c.in[0], c));
+                const PVal iv = p.vals[in];
+                if (iv.form != F_NCHW) throw std::runtime_error("pool input is not NCHW-shaped: " + c.name);
+                auto odim = [&](int d, int k, int s, int p0, int p1) {
+                    int num = d + p0 + p1 - k;
+                    return (c.ceil_mode ? (num + s - 1) / s : num / s) + 1;
+                };
+                PoolP pl;
+                pl.N = iv.n; pl.H = iv.h; pl.W = iv.w; pl.CP = iv.cp; pl.C = iv.c;
+                pl.Ho = odim(iv.h, c.kh, c.sh, c.pt, c.pb);
+                pl.Wo = odim(iv.w, c.kw, c.sw, c.pl, c.pr);
+                pl.kh = c.kh; pl.kw = c.kw; pl.sh = c.sh; pl.sw = c.sw; pl.pt = c.pt; pl.pl = c.pl;
+                pl.is_max = c.kind == C_MAXPOOL;
+                pl.count_include_pad = c.count_include_pad;
+                int out = new_val(F_NCHW, iv.n, pl.Ho, pl.Wo, iv.c);
+                use(in);
+                int64_t total = (int64_t)iv.n * pl.Ho * pl.Wo * iv.cp;
+                emit("pool " + c.name, [=](cudaStream_t st) {
+                    pool_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)pp->ptr(in), (T*)pp->ptr(out), pl);
+                });
+                vid[c.out] = out;
+                break;
+            }
+            case C_RESIZE: {
+                int in = materialize(get(c.in[0], c));
+                PVal v = p.vals[in];
+                if (v.form != F_NCHW) throw std::runtime_error("Resize input is not NCHW-shaped: " + c.name);
+                v.up_src = in;
+                v.root = -1;
+                v.fh = c.fh; v.fw = c.fw;
+                v.h *= c.fh; v.w *= c.fw;
+                p.vals.push_back(v);
+                vid[c.out] = (int)p.vals.size() - 1;
+                break;
+            }
+            case C_CONCAT: {
+                std::vector<int> ins;
+                int ctot = 0;
+                for (auto& nm : c.in) ins.push_back(get(nm, c));
+                const PVal v0 = p.vals[ins[0]];
+                int axis = c.axis < 0 ? c.axis + (int)v0.logical().size() : c.axis;
+                bool chan_axis = (v0.form == F_NCHW && axis == 1) || (v0.form == F_NSC && axis == 2) ||
+                                 (v0.form == F_NC && axis == 1) || (v0.form == F_NHWC && axis == 3);
+                if (!chan_axis) throw std::runtime_error("Concat along a non-channel axis: " + c.name);
+                for (int v : ins) {
+                    const PVal& pv = p.vals[v];
+                    if (pv.n != v0.n || pv.h != v0.h || pv.w != v0.w) throw std::runtime_error("Concat shape mismatch: " + c.name);
+                    ctot += pv.c;
+                }
+                int out = new_val(v0.form, v0.n, v0.h, v0.w, ctot);
+                int cdp = p.vals[out].cp;
+                if (cdp != ctot) {
+                    int64_t tot = p.vals[out].elems();
+                    emit("concat_zero " + c.name, [=](cudaStream_t st) {
+                        fill_zero_kernel<T><<<grid_for(tot), 256, 0, st>>>((T*)pp->ptr(out), tot);
+                    });
+                }
+                int off = 0;
+                for (int v : ins) {
+                    const PVal pv = p.vals[v];
+                    int src = pv.up_src >= 0 ? pv.up_src : v;
+                    use(v);
+                    int N = pv.n, H = pv.h, W = pv.w, Cs = pv.c, CsP = pv.cp, fh = pv.fh, fw = pv.fw, coff = off;
+                    emit("concat " + c.name, [=](cudaStream_t st) {
+                        concat_slice_kernel<T><<<grid_for((int64_t)N * H * W * Cs), 256, 0, st>>>(
+                            (const T*)pp->ptr(src), (T*)pp->ptr(out), N, H, W, Cs, CsP, cdp, coff, fh, fw);
+                    });
+                    off += pv.c;
+                }
+                vid[c.out] = out;
+                break;
+            }
+            case C_ADD:
+            case C_MUL: {
+                int a = get(c.in[0], c), b = get(c.in[1], c);
+                auto is_bcast = [&](int big, int small) {
+                    const PVal &x = p.vals[big], &y = p.vals[small];
+                    return y.h == 1 && y.w == 1 && (x.h != 1 || x.w != 1) && x.n == y.n && x.c == y.c;
+                };
+                if (p.vals[a].up_src >= 0 && p.vals[b].up_src < 0) std::swap(a, b);
+                if (is_bcast(b, a)) std::swap(a, b);
+                a = materialize(a);
+                if (p.vals[b].up_src >= 0 && is_bcast(a, b)) b = materialize(b);
+                const PVal av = p.vals[a], bv = p.vals[b];
+                bool bc = is_bcast(a, b);
+                if (!bc && (av.n != bv.n || av.h != bv.h || av.w != bv.w || av.c != bv.c))
+                    throw std::runtime_error("element-wise shape mismatch at " + c.name);
+                int out = new_val(av.form, av.n, av.h, av.w, av.c);
+                int bsrc = bv.up_src >= 0 ? bv.up_src : b;
+                use(a);
+                use(b);
+                EltP ep;
+                ep.N = av.n; ep.H = av.h; ep.W = av.w; ep.CP = av.cp; ep.C = av.c;
+                ep.fh = bv.up_src >= 0 ? bv.fh : 1;
+                ep.fw = bv.up_src >= 0 ? bv.fw : 1;
+                ep.b_bcast = bc;
+                ep.op = c.kind == C_MUL;
+                ep.epi = c.epi;
+                if (av.cp < 4) {
+                    if (bc || bv.up_src >= 0) throw std::runtime_error("scalar-channel element-wise with broadcast: " + c.name);
+                    int64_t tot = av.elems();
+                    emit("eltwise " + c.name, [=](cudaStream_t st) {
+                        eltwise_scalar_kernel<T><<<grid_for(tot), 256, 0, st>>>((const T*)pp->ptr(a), (const T*)pp->ptr(bsrc),
+                                                                                 (T*)pp->ptr(out), tot, ep.op, ep.epi);
+                    });
+                } else {
+                    int64_t tot = (int64_t)av.n * av.h * av.w * (av.cp / 4);
+                    emit("eltwise " + c.name, [=](cudaStream_t st) {
+                        eltwise_kernel<T><<<grid_for(tot), 256, 0, st>>>((const T*)pp->ptr(a), (const T*)pp->ptr(bsrc),
+                                                                          (T*)pp->ptr(out), ep);
+                    });
+                }
+                vid[c.out] = out;
+                break;
+            }
+            case C_UNARY:
+            case C_CHANVEC: {
+                int in = materialize(get(c.in[0], c));
+                const PVal iv = p.vals[in];
+                if (c.kind == C_CHANVEC && c.cout != iv.c) throw std::runtime_error("per-channel vector length mismatch at " + c.name);
+                int out = new_val(iv.form, iv.n, iv.h, iv.w, iv.c);
+                use(in);
+                const float* vec = c.kind == C_CHANVEC ? dvec_[c.vec_id].first : nullptr;
+                int vop = c.kind == C_CHANVEC ? c.vec_op : -1;
+                int64_t tot = iv.elems();
+                int CP = iv.cp, C = iv.c;
+                Epilogue epi = c.epi;
+                emit("unary " + c.name, [=](cudaStream_t st) {
+                    unary_kernel<T><<<grid_for(tot), 256, 0, st>>>((const T*)pp->ptr(in), (T*)pp->ptr(out), tot, CP, C, vec, vop, epi);
+                });
+                vid[c.out] = out;
+                break;
+            }
+            case C_LAYERNORM: {
+                int in = materialize(get(c.in[0], c));
+                const PVal iv = p.vals[in];
+                if (iv.form != F_NSC && iv.form != F_NC && iv.form != F_NHWC)
+                    throw std::runtime_error("LayerNorm over a non-channel axis: " + c.name);
+                if (iv.c != c.cout) throw std::runtime_error("LayerNorm width mismatch at " + c.name);
+                int out = new_val(iv.form, iv.n, iv.h, iv.w, iv.c);
+                use(in);
+                int64_t rows = (int64_t)iv.n * iv.h * iv.w;
+                int C = iv.c, CP = iv.cp;
+                float eps = c.eps;
+                const float* ga = dvec_[c.ln_id].first;
+                const float* be = dvec_[c.ln_id].second;
+                emit("layernorm " + c.name, [=](cudaStream_t st) {
+                    layernorm_kernel<T><<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>((const T*)pp->ptr(in), (T*)pp->ptr(out),
+                                                                                             ga, be, rows, C, CP, eps);
+                });
+                vid[c.out] = out;
+                break;
+            }
+            case C_ATTENTION: {
+                int in = materialize(get(c.in[0], c));
+                const PVal iv = p.vals[in];
+                if (iv.form != F_NSC || iv.c % (3 * c.heads) != 0) throw std::runtime_error("attention input layout unsupported: " + c.name);
+                int dim = iv.c / 3, hd = dim / c.heads, Tn = iv.h * iv.w;
+                int out = new_val(F_NSC, iv.n, iv.h, iv.w, dim);
+                use(in);
+                size_t smem = (size_t)2 * Tn * hd * sizeof(float);
+                if (smem > 200 * 1024) throw std::runtime_error("attention sequence too long for shared memory: " + c.name);
+                int heads = c.heads, B = iv.n, CPin = iv.cp, CPout = p.vals[out].cp;
+                float scale = c.scale;
+                int qblocks = std::max(1, std::min(8, (Tn + 63) / 64));
+                p.flops += 4.0 * B * heads * (double)Tn * Tn * hd;
+                emit("attention " + c.name, [=](cudaStream_t st) {
+                    const T* q = (const T*)pp->ptr(in);
+                    T* o = (T*)pp->ptr(out);
+                    dim3 grid(B * heads, qblocks);
+#define B200_ATTN(HD)                                                                                               \
+    {                                                                                                               \
+        if (smem > 48 * 1024)                                                                                       \
+            cudaFuncSetAttribute(attention_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        attention_kernel<T, HD><<<grid, 64, smem, st>>>(q, o, Tn, heads, CPin, CPout, scale);                       \
+    }
+                    switch (hd) {
+                        case 8: B200_ATTN(8) break;
+                        case 15: B200_ATTN(15) break;
+                        case 16: B200_ATTN(16) break;
+                        case 30: B200_ATTN(30) break;
+                        case 32: B200_ATTN(32) break;
+                        default: break;
+                    }
+#undef B200_ATTN
+                    if (CPout != dim) {
+                        int64_t rows = (int64_t)B * Tn;
+                        zero_pad_lanes_kernel<T><<<grid_for(rows * (CPout - dim)), 256, 0, st>>>(o, rows, dim, CPout);
+                    }
+                });
+                if (hd != 8 && hd != 15 && hd != 16 && hd != 30 && hd != 32)
+                    throw std::runtime_error("attention head dim " + std::to_string(hd) + " unsupported: " + c.name);
+                vid[c.out] = out;
+                break;
+            }
+            case C_SOFTMAX: {
+                int in = materialize(get(c.in[0], c));
+                const PVal iv = p.vals[in];
+                int rank = (int)iv.logical().size();
+                int axis = c.axis < 0 ? c.axis + rank : c.axis;
+                bool last_is_c = iv.form == F_NSC || iv.form == F_NC || iv.form == F_NHWC;
+                if (!last_is_c || axis != rank - 1) throw std::runtime_error("Softmax over a non-channel axis: " + c.name);
+                int64_t rows = (int64_t)iv.n * iv.h * iv.w;
+                int C = iv.c, CP = iv.cp;
+                use(in);
+                if (c.out == g.output_name) {
+                    // graph output: write the dense fp32 logical tensor directly
+                    PVal ov = iv;
+                    ov.root = -1;
+                    p.vals.push_back(ov);
+                    int out = (int)p.vals.size() - 1;
+                    p.out_written_dense = true;
+                    emit("softmax_out " + c.name, [=](cudaStream_t st) {
+                        softmax_kernel<T><<<(unsigned)rows, 256, 0, st>>>((const T*)pp->ptr(in), nullptr, pp->out_dense, C, CP);
+                    });
+                    vid[c.out] = out;
+                } else {
+                    int out = new_val(iv.form, iv.n, iv.h, iv.w, iv.c);
+                    emit("softmax " + c.name, [=](cudaStream_t st) {
+                        softmax_kernel<T><<<(unsigned)rows, 256, 0, st>>>((const T*)pp->ptr(in), (T*)pp->ptr(out), nullptr, C, CP);
+                    });
+                    vid[c.out] = out;
+                }
+                break;
+            }
+            case C_RESHAPE: {
+                int in = materialize(get(c.in[0], c));
+                const PVal iv = p.vals[in];
+                std::vector<int64_t> tgt;
+                auto hc = g.host_consts.find(c.in[1]);
+                if (hc != g.host_consts.end()) tgt = hc->second.i;
+                else tgt = p.vals[get(c.in[1], c)].host;
+                std::vector<int64_t> cur_shape = iv.logical();
+                int64_t total = 1;
+                for (auto d : cur_shape) total *= d;
+                int64_t known = 1;
+                int neg = -1;
+                for (size_t i = 0; i < tgt.size(); ++i) {
+                    if (tgt[i] == 0) tgt[i] = i < cur_shape.size() ? cur_shape[i] : 1;
+                    if (tgt[i] == -1) neg = (int)i;
+                    else known *= tgt[i];
+                }
+                if (neg >= 0) tgt[neg] = known ? total / known : 0;
+                int out = -1;
+                int64_t S = (int64_t)iv.h * iv.w;
+                if (tgt == cur_shape) {
+                    out = alias_val(in, iv.form, iv.h, iv.w);
+                } else if (iv.form == F_NCHW && tgt.size() == 3 && tgt[0] == iv.n && tgt[1] == iv.c && tgt[2] == S) {
+                    out = alias_val(in, F_NCS, iv.h, iv.w);
+                } else if (iv.form == F_NCHW && tgt.size() == 2 && S == 1 && tgt[0] == iv.n && tgt[1] == iv.c) {
+                    out = alias_val(in, F_NC, 1, 1);
+                } else if (iv.form == F_NSC && tgt.size() == 4 && tgt[0] == iv.n && tgt[3] == iv.c && tgt[1] * tgt[2] == S) {
+                    out = alias_val(in, F_NHWC, (int)tgt[1], (int)tgt[2]);
+                } else if (iv.form == F_NHWC && tgt.size() == 3 && tgt[0] == iv.n && tgt[1] == S && tgt[2] == iv.c) {
+                    out = alias_val(in, F_NSC, iv.h, iv.w);
+                } else if (iv.form == F_NCS && tgt.size() == 4 && tgt[0] == iv.n && tgt[1] == iv.c && tgt[2] * tgt[3] == S) {
+                    out = alias_val(in, F_NCHW, (int)tgt[2], (int)tgt[3]);
+                } else if (iv.form == F_NC && tgt.size() == 4 && tgt[0] == iv.n && tgt[1] == iv.c && tgt[2] == 1 && tgt[3] == 1) {
+                    out = alias_val(in, F_NCHW, 1, 1);
+                } else {
+                    std::ostringstream os;
+                    os << "unsupported Reshape at " << c.name << ": [";
+                    for (auto d : cur_shape) os << d << ",";
+                    os << "] -> [";
+                    for (auto d : tgt) os << d << ",";
+                    os << "]";
+                    throw std::runtime_error(os.str());
+                }
+                vid[c.out] = out;
+                break;
+            }
+            case C_TRANSPOSE: {
+                int in = materialize(get(c.in[0], c));
+                const PVal iv = p.vals[in];
+                const auto& pm = c.perm;
+                int out = -1;
+                auto is = [&](std::initializer_list<int64_t> l) { return pm == std::vector<int64_t>(l); };
+                if (iv.form == F_NCS && is({0, 2, 1})) out = alias_val(in, F_NSC, iv.h, iv.w);
+                else if (iv.form == F_NSC && is({0, 2, 1})) out = alias_val(in, F_NCS, iv.h, iv.w);
+                else if (iv.form == F_NHWC && is({0, 3, 1, 2})) out = alias_val(in, F_NCHW, iv.h, iv.w);
+                else if (iv.form == F_NCHW && is({0, 2, 3, 1})) out = alias_val(in, F_NHWC, iv.h, iv.w);
+                else throw std::runtime_error("unsupported Transpose at " + c.name);
+                vid[c.out] = out;
+                break;
+            }
+            case C_SQUEEZE: {
+                int in = materialize(get(c.in[0], c));
+                const PVal iv = p.vals[in];
+                int out = -1;
+                std::vector<int64_t> ax = c.axes;
+                for (auto& a : ax) if (a < 0) a += (int64_t)iv.logical().size();
+                std::sort(ax.begin(), ax.end());
+                if (iv.form == F_NCHW && ax == std::vector<int64_t>{2} && iv.h == 1) out = alias_val(in, F_NCS, 1, iv.w);
+                else if (iv.form == F_NCHW && ax == std::vector<int64_t>{3} && iv.w == 1) out = alias_val(in, F_NCS, iv.h, 1);
+                else if (iv.form == F_NCHW && ax == std::vector<int64_t>{2, 3} && iv.h == 1 && iv.w == 1) out = alias_val(in, F_NC, 1, 1);
+                else throw std::runtime_error("unsupported Squeeze at " + c.name);
+                vid[c.out] = out;
+                break;
+            }
+            case C_FLATTEN: {
+                int in = materialize(get(c.in[0], c));
+                const PVal iv = p.vals[in];
+                if (iv.form == F_NCHW && iv.h == 1 && iv.w == 1 && c.axis == 1) vid[c.out] = alias_val(in, F_NC, 1, 1);
+                else throw std::runtime_error("unsupported Flatten at " + c.name);
+                break;
+            }
+            default:
+                throw std::runtime_error("plan: unhandled node kind at " + c.name);
+        }
+    }
+
+    // graph output
+    cur = (int)g.nodes.size();
+    auto oit = vid.find(g.output_name);
+    if (oit == vid.end()) throw std::runtime_error("graph output '" + g.output_name + "' was never produced");
+    int ov = materialize(oit->second);
+    p.out_val = ov;
+    const PVal out = p.vals[ov];
+    p.out_shape = out.logical();
+    p.out_dense_elems = 1;
+    for (auto d : p.out_shape) p.out_dense_elems *= (size_t)d;
+    if (!p.out_written_dense) {
+        use(ov);
+        int to_nchw = out.form == F_NCHW || out.form == F_NCS;
+        int N = out.n, C = out.c, H = out.h, W = out.w, CP = out.cp;
+        int64_t tot = (int64_t)p.out_dense_elems;
+        emit("to_dense", [=](cudaStream_t st) {
+            to_dense_f32_kernel<T><<<grid_for(tot), 256, 0, st>>>((const T*)pp->ptr(ov), pp->out_dense, N, C, H, W, CP, to_nchw);
+        });
+    }
+    B200_CUDA_CHECK(cudaMalloc(&p.out_dense, std::max<size_t>(1, p.out_dense_elems) * sizeof(float)));
+
+    // ---- liveness-based offsets
+    size_t nb = buf_bytes.size();
+    p.buf_off.assign(nb, 0);
+    std::vector<std::vector<int>> starts(g.nodes.size() + 2), ends(g.nodes.size() + 2);
+    for (size_t b = 0; b < nb; ++b) {
+        starts[buf_first[b] + 1].push_back((int)b);
+        ends[buf_last[b] + 1].push_back((int)b);
+    }
+    Arena ar;
+    for (size_t t = 0; t < starts.size(); ++t) {
+        for (int b : starts[t]) p.buf_off[b] = ar.alloc(buf_bytes[b]);
+        for (int b : ends[t]) ar.release(p.buf_off[b], buf_bytes[b]);
+    }
+    p.arena_bytes = ar.end;
+    p.launches = (int)p.steps.size();
+}
+
+void Plan::launch(cudaStream_t st) {
+    for (auto& s : steps) s(st);
+}
+
+void Model::run_host(const float* nchw, int n, int c, int h, int w, std::vector<int64_t>* out_shape, float* out,
+                     size_t out_capacity, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (c != in_c_) throw std::runtime_error("input has " + std::to_string(c) + " channels, model expects " + std::to_string(in_c_));
+    Plan* p = plan_for(n, h, w);
+    size_t in_bytes = (size_t)n * c * h * w * sizeof(float);
+    if (in_bytes > stage_in_bytes_) {
+        if (stage_in_) cudaFree(stage_in_);
+        stage_in_ = nullptr;
+        B200_CUDA_CHECK(cudaMalloc(&stage_in_, in_bytes));
+        stage_in_bytes_ = in_bytes;
+    }
+    B200_CUDA_CHECK(cudaMemcpyAsync(stage_in_, nchw, in_bytes, cudaMemcpyHostToDevice, st));
+    int cp = cpad_of(c);
+    int64_t tot = (int64_t)n * h * w * cp;
+    if (prec_ == PREC_BF16)
+        nchw_to_nhwc_kernel<bf16><<<grid_for(tot), 256, 0, st>>>(stage_in_, (bf16*)p->in_ptr(), n, c, h, w, cp);
+    else
+        nchw_to_nhwc_kernel<float><<<grid_for(tot), 256, 0, st>>>(stage_in_, (float*)p->in_ptr(), n, c, h, w, cp);
+    p->launch(st);
+    B200_CUDA_CHECK(cudaGetLastError());
+    if (out_shape) *out_shape = p->out_shape;
+    if (out) {
+        if (p->out_dense_elems > out_capacity)
+            throw std::runtime_error("output buffer too small: need " + std::to_string(p->out_dense_elems) + " floats");
+        B200_CUDA_CHECK(cudaMemcpyAsync(out, p->out_dense, p->out_dense_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+Plan* Model::run_device(const void* nhwc_in, int n, int h, int w, cudaStream_t st, bool want_dense) {
+    (void)want_dense;
+    Plan* p = plan_for(n, h, w);
+    if (nhwc_in && nhwc_in != p->in_ptr())
+        B200_CUDA_CHECK(cudaMemcpyAsync(p->in_ptr(), nhwc_in, (size_t)p->vals[p->in_val].elems() * elem_size(),
+                                        cudaMemcpyDeviceToDevice, st));
+    p->launch(st);
+    B200_CUDA_CHECK(cudaGetLastError());
+    return p;
+}
+
+}  // namespace b200ocr

@@ -1,0 +1,104 @@
+// B200 graph executor: canonical graph -> per-shape launch plan -> kernels on a stream.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "graph.h"
+
+namespace b200ocr {
+
+enum Precision : int { PREC_FP32 = 0, PREC_BF16 = 1 };
+
+// How a logical ONNX tensor sits on the physical NHWC(cpad) buffer.
+enum Form : int {
+    F_NCHW = 0,   // logical [n,c,h,w]
+    F_NCS,        // logical [n,c,h*w]
+    F_NSC,        // logical [n,h*w,c]
+    F_NHWC,       // logical [n,h,w,c]
+    F_NC,         // logical [n,c]      (h = w = 1)
+    F_HOST,       // small integer vector living on the host (shape arithmetic)
+};
+
+struct PVal {
+    int form = F_NCHW;
+    int n = 0, h = 0, w = 0, c = 0, cp = 0;
+    int root = -1;                 // buffer id
+    // virtual nearest-upsample of `up_src` (a C_RESIZE that was not materialised)
+    int up_src = -1, fh = 1, fw = 1;
+    std::vector<int64_t> host;
+    std::vector<int64_t> logical() const;
+    int64_t elems() const { return (int64_t)n * h * w * cp; }
+};
+
+struct DevWeights {
+    float* w = nullptr;            // [Kpad][ColsW] fp32 (dense) or [taps][CP] (depthwise)
+    float* bias = nullptr;         // [ColsW]
+    void* w_bf16 = nullptr;        // tcgen05 operand pack (optional)
+    int K = 0, Kpad = 0, ColsW = 0;
+};
+
+struct Plan {
+    int n = 0, h = 0, w = 0;
+    std::vector<PVal> vals;
+    std::vector<size_t> buf_off, buf_bytes;
+    size_t arena_bytes = 0;
+    char** model_arena = nullptr;  // the owning Model's activation slab (shared by all of its plans)
+    std::vector<std::function<void(cudaStream_t)>> steps;
+    std::vector<std::string> step_names;
+    int in_val = -1, out_val = -1;
+    float* out_dense = nullptr;    // dense fp32 logical output (device)
+    size_t out_dense_elems = 0;
+    bool out_written_dense = false;
+    std::vector<int64_t> out_shape;
+    double flops = 0;              // 2*MACs of Conv/ConvT/MatMul at this shape
+    int launches = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    void* ptr(int v) const { return *model_arena + buf_off[vals[v].root]; }
+    void* bufptr(int b) const { return *model_arena + buf_off[b]; }
+    void* in_ptr() const { return ptr(in_val); }
+    void launch(cudaStream_t st);
+    ~Plan();
+};
+
+class Model {
+public:
+    Model(const std::string& path, int precision);
+    ~Model();
+    Model(const Model&) = delete;
+
+    // Input already on the device in the executor's own layout: NHWC, storage type T, cpad(3)=4.
+    // Returns the plan (its out_dense holds the logical fp32 output after the stream completes).
+    Plan* run_device(const void* nhwc_in, int n, int h, int w, cudaStream_t st, bool want_dense = true);
+    // Host NCHW fp32 in -> logical fp32 out (the onnxruntime-compatible seam).
+    void run_host(const float* nchw, int n, int c, int h, int w, std::vector<int64_t>* out_shape,
+                  float* out, size_t out_capacity, cudaStream_t st);
+    Plan* plan_for(int n, int h, int w);
+    size_t elem_size() const { return prec_ == PREC_BF16 ? 2 : 4; }
+    int precision() const { return prec_; }
+    const CGraph& graph() const { return *g_; }
+    int in_channels() const { return in_c_; }
+    std::string describe() const;
+
+private:
+    std::unique_ptr<Plan> build_plan(int n, int h, int w);
+    template <typename T> void build_steps(Plan& p);
+    std::unique_ptr<CGraph> g_;
+    int prec_;
+    int in_c_ = 3;
+    std::vector<DevWeights> dw_;
+    std::vector<std::pair<float*, float*>> dvec_;
+    std::map<std::vector<int>, std::unique_ptr<Plan>> plans_;
+    char* arena_ = nullptr;        // activation slab, grown to the largest plan
+    size_t arena_cap_ = 0;
+    float* stage_in_ = nullptr;    // device staging for host NCHW input
+    size_t stage_in_bytes_ = 0;
+    std::mutex mu_;
+};
+
+}  // namespace b200ocr

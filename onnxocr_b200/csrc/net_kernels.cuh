@@ -1,0 +1,611 @@
+// CUDA-core kernels of the graph executor.  All activations are NHWC with the channel
+// count padded to cpad (1, 4 or a multiple of 8); pad lanes always hold zeros.
+// T is the storage type (float for the exact fp32 mode, bf16 for the fast mode);
+// accumulation is always fp32.
+#pragma once
+#include "common.cuh"
+
+namespace b200ocr {
+
+// ----------------------------------------------------------------------------------------
+// layout conversion at the session seam (reference feeds NCHW f32: predict_det.py:102-107)
+// ----------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int N, int C, int H, int W,
+                                    int CP) {
+    int64_t total = (int64_t)N * H * W * CP;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % CP);
+        int64_t p = i / CP;
+        int x = (int)(p % W);
+        int64_t q = p / W;
+        int y = (int)(q % H);
+        int n = (int)(q / H);
+        float v = c < C ? in[(((int64_t)n * C + c) * H + y) * W + x] : 0.f;
+        ST<T>::st(out + i, v);
+    }
+}
+
+// NHWC(cpad) T -> dense fp32.  to_nchw: output [N,C,H,W]; else [N,H,W,C] (pad stripped).
+template <typename T>
+__global__ void to_dense_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int N, int C, int H, int W,
+                                    int CP, int to_nchw) {
+    int64_t total = (int64_t)N * C * H * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int n, c, y, x;
+        if (to_nchw) {
+            x = (int)(i % W);
+            int64_t q = i / W;
+            y = (int)(q % H);
+            q /= H;
+            c = (int)(q % C);
+            n = (int)(q / C);
+        } else {
+            c = (int)(i % C);
+            int64_t q = i / C;
+            x = (int)(q % W);
+            q /= W;
+            y = (int)(q % H);
+            n = (int)(q / H);
+        }
+        out[i] = ST<T>::ld(in + (((int64_t)n * H + y) * W + x) * CP + c);
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// dense convolution / linear / 2x2-stride-2 transposed conv as an implicit GEMM on CUDA cores
+//   M = N*Ho*Wo output pixels, Ncol = Cout (x4 taps for convT), K = kh*kw*CinP
+//   weights: fp32 [Kpad][ColsW] (K index = tap*CinP + ci), zero padded
+// ----------------------------------------------------------------------------------------
+struct ConvP {
+    int N, H, W, CinP;
+    int Ho, Wo, Cout, CoutP;
+    int kh, kw, sh, sw, pt, pl;
+    int K;          // kh*kw*CinP
+    int ColsW;      // padded weight row length
+    int Cols;       // GEMM columns that carry data (CoutP, or 4*CoutP for convT)
+    int convT;      // 1: columns are (tap, co); store with pixel shuffle to (2y+dy, 2x+dx)
+    int M;
+    Epilogue epi;
+};
+
+constexpr int IG_BK = 16;
+
+template <typename T, int BM, int BN>
+__global__ void __launch_bounds__(256) conv_igemm_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, T* __restrict__ y,
+                                                          const ConvP p) {
+    constexpr int TM = 4, TN = 4;
+    constexpr int TX = BN / TN;            // threads along columns
+    constexpr int TY = BM / TM;            // threads along rows
+    static_assert(TX * TY == 256, "tile must map to 256 threads");
+    constexpr int A_LD = BM / 64;          // float4 A loads per thread per chunk (BM*4 groups / 256)
+    __shared__ __align__(16) float As[IG_BK][BM + 4];
+    __shared__ __align__(16) float Bs[IG_BK][BN];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    const int m0 = blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+
+    // A-load assignment: slot s = tid + j*256 -> row = s / 4, kgroup = s % 4
+    int a_row[A_LD], a_kg[A_LD], a_n[A_LD], a_oy[A_LD], a_ox[A_LD];
+    bool a_valid[A_LD];
+#pragma unroll
+    for (int j = 0; j < A_LD; ++j) {
+        int s = tid + j * 256;
+        a_row[j] = s >> 2;
+        a_kg[j] = s & 3;
+        int m = m0 + a_row[j];
+        a_valid[j] = m < p.M;
+        int mm = a_valid[j] ? m : 0;
+        a_ox[j] = mm % p.Wo;
+        int q = mm / p.Wo;
+        a_oy[j] = q % p.Ho;
+        a_n[j] = q / p.Ho;
+    }
+    // B-load assignment: 16 x BN floats = 4*BN float4; thread loads float4 index tid (if < 4*BN)
+    constexpr int B_F4 = IG_BK * BN / 4;
+    const int b_k = tid / (BN / 4), b_c = (tid % (BN / 4)) * 4;
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    float a_reg[A_LD][4];
+    float4 b_reg = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    auto load_chunk = [&](int k0) {
+#pragma unroll
+        for (int j = 0; j < A_LD; ++j) {
+            int k = k0 + a_kg[j] * 4;
+            a_reg[j][0] = a_reg[j][1] = a_reg[j][2] = a_reg[j][3] = 0.f;
+            if (a_valid[j] && k < p.K) {
+                int tap = k / p.CinP;
+                int ci = k - tap * p.CinP;
+                int ky = tap / p.kw, kx = tap - ky * p.kw;
+                int iy = a_oy[j] * p.sh - p.pt + ky;
+                int ix = a_ox[j] * p.sw - p.pl + kx;
+                if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W)
+                    ST<T>::ld4(x + (((int64_t)a_n[j] * p.H + iy) * p.W + ix) * p.CinP + ci, a_reg[j]);
+            }
+        }
+        if (tid < B_F4) b_reg = *reinterpret_cast<const float4*>(w + (int64_t)(k0 + b_k) * p.ColsW + n0 + b_c);
+    };
+    auto store_chunk = [&]() {
+#pragma unroll
+        for (int j = 0; j < A_LD; ++j) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) As[a_kg[j] * 4 + e][a_row[j]] = a_reg[j][e];
+        }
+        if (tid < B_F4) *reinterpret_cast<float4*>(&Bs[b_k][b_c]) = b_reg;
+    };
+
+    const int nchunks = (p.K + IG_BK - 1) / IG_BK;
+    load_chunk(0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        store_chunk();
+        __syncthreads();
+        if (ch + 1 < nchunks) load_chunk((ch + 1) * IG_BK);
+#pragma unroll
+        for (int k = 0; k < IG_BK; ++k) {
+            float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * TM]);
+            float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * TN]);
+            float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    // epilogue
+    const int col0 = n0 + tx * TN;
+    if (col0 >= p.Cols) return;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int m = m0 + ty * TM + i;
+        if (m >= p.M) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            int col = col0 + j;
+            int co = p.convT ? col % p.CoutP : col;
+            float r = 0.f;
+            if (col < p.Cols && co < p.Cout) r = epi_apply(acc[i][j] + bias[co], p.epi);
+            v[j] = r;
+        }
+        if (!p.convT) {
+            T* dst = y + (int64_t)m * p.CoutP + col0;
+            if ((p.CoutP & 3) == 0) {
+                ST<T>::st4(dst, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < TN; ++j)
+                    if (col0 + j < p.CoutP) ST<T>::st(dst + j, v[j]);
+            }
+        } else {
+            int ox = m % p.Wo;
+            int q = m / p.Wo;
+            int oy = q % p.Ho;
+            int n = q / p.Ho;
+            if ((p.CoutP & 3) == 0) {
+                int tap = col0 / p.CoutP, co = col0 - tap * p.CoutP;
+                int dy = tap >> 1, dx = tap & 1;
+                T* dst = y + ((((int64_t)n * (2 * p.Ho) + 2 * oy + dy) * (2 * p.Wo)) + 2 * ox + dx) * p.CoutP + co;
+                ST<T>::st4(dst, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    int col = col0 + j;
+                    if (col >= p.Cols) continue;
+                    int tap = col / p.CoutP, co = col - tap * p.CoutP;
+                    int dy = tap >> 1, dx = tap & 1;
+                    ST<T>::st(y + ((((int64_t)n * (2 * p.Ho) + 2 * oy + dy) * (2 * p.Wo)) + 2 * ox + dx) * p.CoutP + co,
+                              v[j]);
+                }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// depthwise k x k convolution, V channels per thread (V*sizeof(T) == 16 bytes or 4 channels)
+// ----------------------------------------------------------------------------------------
+struct DwP {
+    int N, H, W, CP, C;
+    int Ho, Wo;
+    int kh, kw, sh, sw, pt, pl;
+    Epilogue epi;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, T* __restrict__ y, const DwP p) {
+    const int cg = p.CP >> 2;                       // 4-channel groups
+    int64_t total = (int64_t)p.N * p.Ho * p.Wo * cg;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int g = (int)(i % cg);
+        int64_t q = i / cg;
+        int ox = (int)(q % p.Wo);
+        q /= p.Wo;
+        int oy = (int)(q % p.Ho);
+        int n = (int)(q / p.Ho);
+        int c = g * 4;
+        float acc[4];
+        float4 b4 = *reinterpret_cast<const float4*>(bias + c);
+        acc[0] = b4.x; acc[1] = b4.y; acc[2] = b4.z; acc[3] = b4.w;
+        for (int ky = 0; ky < p.kh; ++ky) {
+            int iy = oy * p.sh - p.pt + ky;
+            if ((unsigned)iy >= (unsigned)p.H) continue;
+            for (int kx = 0; kx < p.kw; ++kx) {
+                int ix = ox * p.sw - p.pl + kx;
+                if ((unsigned)ix >= (unsigned)p.W) continue;
+                float v[4];
+                ST<T>::ld4(x + (((int64_t)n * p.H + iy) * p.W + ix) * p.CP + c, v);
+                float4 w4 = *reinterpret_cast<const float4*>(w + (int64_t)(ky * p.kw + kx) * p.CP + c);
+                acc[0] = fmaf(v[0], w4.x, acc[0]);
+                acc[1] = fmaf(v[1], w4.y, acc[1]);
+                acc[2] = fmaf(v[2], w4.z, acc[2]);
+                acc[3] = fmaf(v[3], w4.w, acc[3]);
+            }
+        }
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = (c + j < p.C) ? epi_apply(acc[j], p.epi) : 0.f;
+        ST<T>::st4(y + (((int64_t)n * p.Ho + oy) * p.Wo + ox) * p.CP + c, o);
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// global average pool (deterministic two-stage) + squeeze-excite
+// ----------------------------------------------------------------------------------------
+// partial[n][chunk][CP] = sum over the chunk's pixels.  grid (chunks, N), block 256.
+template <typename T>
+__global__ void __launch_bounds__(256) gap_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, int HW,
+                                                           int CP, int chunks) {
+    extern __shared__ float sm[];                   // [rows][CP]
+    const int cg = CP >> 2;
+    const int rows = max(1, 256 / cg);
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int per = (HW + chunks - 1) / chunks;
+    const int p0 = chunk * per, p1 = min(HW, p0 + per);
+    const int r = threadIdx.x / cg, g = threadIdx.x % cg;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < rows) {
+        for (int px = p0 + r; px < p1; px += rows) {
+            float v[4];
+            ST<T>::ld4(x + ((int64_t)n * HW + px) * CP + g * 4, v);
+            acc[0] += v[0]; acc[1] += v[1]; acc[2] += v[2]; acc[3] += v[3];
+        }
+        for (int j = 0; j < 4; ++j) sm[r * CP + g * 4 + j] = acc[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < CP; c += blockDim.x) {
+        float s = 0.f;
+        for (int rr = 0; rr < rows; ++rr) s += sm[rr * CP + c];
+        partial[((int64_t)n * chunks + chunk) * CP + c] = s;
+    }
+}
+
+// GAP as a tensor: out[n][c] = mean
+template <typename T>
+__global__ void gap_finish_kernel(const float* __restrict__ partial, T* __restrict__ out, int HW, int C, int CP,
+                                  int chunks) {
+    int n = blockIdx.x;
+    for (int c = threadIdx.x; c < CP; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < chunks; ++k) s += partial[((int64_t)n * chunks + k) * CP + c];
+        ST<T>::st(out + (int64_t)n * CP + c, c < C ? s / (float)HW : 0.f);
+    }
+}
+
+// scale[n][c] = hsigmoid(W2 relu(W1 mean + b1) + b2).  One block per image.
+// w1: [C][mid] (rows padded as stored: K index = ci, ColsW stride), w2: [mid][C].
+__global__ void se_fc_kernel(const float* __restrict__ partial, int chunks, int HW, int C, int CP, int mid,
+                             const float* __restrict__ w1, int w1_ld, const float* __restrict__ b1,
+                             const float* __restrict__ w2, int w2_ld, const float* __restrict__ b2, float alpha,
+                             float beta, float* __restrict__ scale) {
+    extern __shared__ float sm[];                   // mean[CP] + hidden[mid]
+    float* mean = sm;
+    float* hid = sm + CP;
+    int n = blockIdx.x;
+    for (int c = threadIdx.x; c < CP; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < chunks; ++k) s += partial[((int64_t)n * chunks + k) * CP + c];
+        mean[c] = c < C ? s / (float)HW : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < mid; j += blockDim.x) {
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s = fmaf(mean[c], w1[(int64_t)c * w1_ld + j], s);
+        hid[j] = fmaxf(s + b1[j], 0.f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < CP; c += blockDim.x) {
+        float s = 0.f;
+        if (c < C) {
+            for (int j = 0; j < mid; ++j) s = fmaf(hid[j], w2[(int64_t)j * w2_ld + c], s);
+            s = fminf(fmaxf(fmaf(s + b2[c], alpha, beta), 0.f), 1.f);
+        }
+        scale[(int64_t)n * CP + c] = s;
+    }
+}
+
+// y = epi(x * scale[n][c]) (+ x when residual)
+template <typename T>
+__global__ void se_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale, T* __restrict__ y, int64_t HW,
+                                int CP, int C, int64_t total4, int residual, const Epilogue epi) {
+    const int cg = CP >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        int g = (int)(i % cg);
+        int64_t px = i / cg;
+        int n = (int)(px / HW);
+        float v[4], o[4];
+        ST<T>::ld4(x + i * 4, v);
+        float4 s = *reinterpret_cast<const float4*>(scale + (int64_t)n * CP + g * 4);
+        float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float t = epi_apply(v[j] * sv[j], epi);
+            if (residual) t = v[j] + t;
+            o[j] = (g * 4 + j < C) ? t : 0.f;
+        }
+        ST<T>::st4(y + i * 4, o);
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// pooling
+// ----------------------------------------------------------------------------------------
+struct PoolP {
+    int N, H, W, CP, C, Ho, Wo, kh, kw, sh, sw, pt, pl, is_max, count_include_pad;
+};
+template <typename T>
+__global__ void pool_kernel(const T* __restrict__ x, T* __restrict__ y, const PoolP p) {
+    int64_t total = (int64_t)p.N * p.Ho * p.Wo * p.CP;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % p.CP);
+        int64_t q = i / p.CP;
+        int ox = (int)(q % p.Wo);
+        q /= p.Wo;
+        int oy = (int)(q % p.Ho);
+        int n = (int)(q / p.Ho);
+        float acc = p.is_max ? -3.4e38f : 0.f;
+        int cnt = 0;
+        for (int ky = 0; ky < p.kh; ++ky) {
+            int iy = oy * p.sh - p.pt + ky;
+            if ((unsigned)iy >= (unsigned)p.H) continue;
+            for (int kx = 0; kx < p.kw; ++kx) {
+                int ix = ox * p.sw - p.pl + kx;
+                if ((unsigned)ix >= (unsigned)p.W) continue;
+                float v = ST<T>::ld(x + (((int64_t)n * p.H + iy) * p.W + ix) * p.CP + c);
+                acc = p.is_max ? fmaxf(acc, v) : acc + v;
+                ++cnt;
+            }
+        }
+        if (!p.is_max) acc = acc / (float)(p.count_include_pad ? p.kh * p.kw : max(cnt, 1));
+        ST<T>::st(y + i, c < p.C ? acc : 0.f);
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// element-wise: out = epi(a (op) b'), b' = b nearest-upsampled by (fh, fw) and/or broadcast over pixels
+// ----------------------------------------------------------------------------------------
+struct EltP {
+    int N, H, W, CP, C;
+    int fh, fw;           // upsample factors applied to b
+    int b_bcast;          // 1: b is [N,1,1,CP]
+    int op;               // 0 add, 1 mul
+    Epilogue epi;
+};
+template <typename T>
+__global__ void eltwise_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, const EltP p) {
+    const int cg = p.CP >> 2;
+    int64_t total = (int64_t)p.N * p.H * p.W * cg;
+    const int Hb = p.H / p.fh, Wb = p.W / p.fw;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int g = (int)(i % cg);
+        int64_t q = i / cg;
+        int xw = (int)(q % p.W);
+        q /= p.W;
+        int yh = (int)(q % p.H);
+        int n = (int)(q / p.H);
+        float va[4], vb[4], o[4];
+        ST<T>::ld4(a + i * 4, va);
+        int64_t bi = p.b_bcast ? ((int64_t)n * p.CP + g * 4)
+                               : ((((int64_t)n * Hb + yh / p.fh) * Wb + xw / p.fw) * p.CP + g * 4);
+        ST<T>::ld4(b + bi, vb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float t = p.op == 0 ? va[j] + vb[j] : va[j] * vb[j];
+            o[j] = (g * 4 + j < p.C) ? epi_apply(t, p.epi) : 0.f;
+        }
+        ST<T>::st4(y + i * 4, o);
+    }
+}
+
+// generic scalar version for cpad == 1 tensors
+template <typename T>
+__global__ void eltwise_scalar_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t total,
+                                      int op, const Epilogue epi) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        float va = ST<T>::ld(a + i), vb = ST<T>::ld(b + i);
+        ST<T>::st(y + i, epi_apply(op == 0 ? va + vb : va * vb, epi));
+    }
+}
+
+// y = epi(x) ; optional per-channel vector op first (vec_op: -1 none, 0 add, 1 mul)
+template <typename T>
+__global__ void unary_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t total, int CP, int C,
+                             const float* __restrict__ vec, int vec_op, const Epilogue epi) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % CP);
+        float v = ST<T>::ld(x + i);
+        if (vec_op == 0) v += vec[c];
+        else if (vec_op == 1) v *= vec[c];
+        ST<T>::st(y + i, c < C ? epi_apply(v, epi) : 0.f);
+    }
+}
+
+// channel concat with per-input nearest upsampling: copies one input into its channel slice.
+template <typename T>
+__global__ void concat_slice_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int H, int W, int Cs, int CsP,
+                                    int CdP, int c_off, int fh, int fw) {
+    int64_t total = (int64_t)N * H * W * Cs;
+    const int Hs = H / fh, Ws = W / fw;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % Cs);
+        int64_t q = i / Cs;
+        int xw = (int)(q % W);
+        q /= W;
+        int yh = (int)(q % H);
+        int n = (int)(q / H);
+        dst[(((int64_t)n * H + yh) * W + xw) * CdP + c_off + c] =
+            src[(((int64_t)n * Hs + yh / fh) * Ws + xw / fw) * CsP + c];
+    }
+}
+
+template <typename T>
+__global__ void fill_zero_kernel(T* __restrict__ p, int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        ST<T>::st(p + i, 0.f);
+}
+
+// ----------------------------------------------------------------------------------------
+// LayerNorm over channels: one warp per row
+// ----------------------------------------------------------------------------------------
+template <typename T>
+__global__ void layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, int64_t rows, int C, int CP, float eps) {
+    int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const T* xr = x + (int64_t)warp * CP;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += ST<T>::ld(xr + c);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    float mean = s / (float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        float d = ST<T>::ld(xr + c) - mean;
+        v = fmaf(d, d, v);
+    }
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    float sd = sqrtf(v / (float)C + eps);
+    T* yr = y + (int64_t)warp * CP;
+    for (int c = lane; c < CP; c += 32) {
+        float o = 0.f;
+        if (c < C) o = (ST<T>::ld(xr + c) - mean) / sd * gamma[c] + beta[c];
+        ST<T>::st(yr + c, o);
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// SVTR global-mixer attention.  qkv rows: [3][heads][hd]; one thread per query, K/V of the
+// (batch, head) pair staged in shared memory.
+// ----------------------------------------------------------------------------------------
+template <typename T, int HD>
+__global__ void attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int Tn, int heads, int CPin, int CPout,
+                                 float scale) {
+    extern __shared__ float sm[];                   // K[Tn][HD] V[Tn][HD]
+    float* Ks = sm;
+    float* Vs = sm + (size_t)Tn * HD;
+    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int dim = heads * HD;
+    const T* base = qkv + (int64_t)b * Tn * CPin;
+    for (int i = threadIdx.x; i < Tn * HD; i += blockDim.x) {
+        int t = i / HD, d = i % HD;
+        Ks[i] = ST<T>::ld(base + (int64_t)t * CPin + dim + h * HD + d);
+        Vs[i] = ST<T>::ld(base + (int64_t)t * CPin + 2 * dim + h * HD + d);
+    }
+    __syncthreads();
+    for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < Tn; t += gridDim.y * blockDim.x) {
+        float q[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) q[d] = ST<T>::ld(base + (int64_t)t * CPin + h * HD + d) * scale;
+        float mx = -3.4e38f;
+        for (int j = 0; j < Tn; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) s = fmaf(q[d], Ks[j * HD + d], s);
+            mx = fmaxf(mx, s);
+        }
+        float acc[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+        float den = 0.f;
+        for (int j = 0; j < Tn; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) s = fmaf(q[d], Ks[j * HD + d], s);
+            float e = expf(s - mx);
+            den += e;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) acc[d] = fmaf(e, Vs[j * HD + d], acc[d]);
+        }
+        float inv = 1.f / den;
+        T* o = out + ((int64_t)b * Tn + t) * CPout + h * HD;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) ST<T>::st(o + d, acc[d] * inv);
+    }
+}
+
+// zero the pad lanes [C, CP) of every row (used after attention, whose threads write only real channels)
+template <typename T>
+__global__ void zero_pad_lanes_kernel(T* __restrict__ x, int64_t rows, int C, int CP) {
+    int padn = CP - C;
+    int64_t total = rows * padn;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        ST<T>::st(x + (i / padn) * CP + C + (i % padn), 0.f);
+}
+
+// ----------------------------------------------------------------------------------------
+// softmax over channels, one block per row.  Writes either T NHWC(CP) or dense fp32 (ld = C).
+// ----------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                       float* __restrict__ y_dense, int C, int CP) {
+    __shared__ float red[32];
+    const int64_t row = blockIdx.x;
+    const T* xr = x + row * CP;
+    float mx = -3.4e38f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, ST<T>::ld(xr + c));
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -3.4e38f;
+        for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (threadIdx.x == 0) red[0] = v;
+    }
+    __syncthreads();
+    mx = red[0];
+    __syncthreads();
+    float s = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s += expf(ST<T>::ld(xr + c) - mx);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) red[0] = v;
+    }
+    __syncthreads();
+    float inv = 1.f / red[0];
+    if (y_dense) {
+        float* yr = y_dense + row * C;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) yr[c] = expf(ST<T>::ld(xr + c) - mx) * inv;
+    } else {
+        T* yr = y + row * CP;
+        for (int c = threadIdx.x; c < CP; c += blockDim.x)
+            ST<T>::st(yr + c, c < C ? expf(ST<T>::ld(xr + c) - mx) * inv : 0.f);
+    }
+}
+
+}  // namespace b200ocr

@@ -1,0 +1,663 @@
+#include "stages.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "pre_kernels.cuh"
+
+namespace b200ocr {
+
+void* DevBuf::get(size_t bytes) {
+    if (bytes > cap) {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = bytes + bytes / 4 + 256;
+        B200_CUDA_CHECK(cudaMalloc(&p, cap));
+    }
+    return p;
+}
+DevBuf::~DevBuf() {
+    if (p) cudaFree(p);
+}
+void* PinBuf::get(size_t bytes) {
+    if (bytes > cap) {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = bytes + bytes / 4 + 256;
+        B200_CUDA_CHECK(cudaMallocHost(&p, cap));
+    }
+    return p;
+}
+PinBuf::~PinBuf() {
+    if (p) cudaFreeHost(p);
+}
+
+// DetResizeForTest.resize_image_type0 (operators.py:91-138) — Python float/int semantics in C++:
+// int() truncates, round() is half-to-even (nearbyint under the default rounding mode).
+DetGeom det_geometry(int h, int w, const b200ocr_det_params& p) {
+    DetGeom g;
+    g.src_h = h;
+    g.src_w = w;
+    g.pad_h = h;
+    g.pad_w = w;
+    if (h + w < 64) {
+        g.pad_h = std::max(32, h);
+        g.pad_w = std::max(32, w);
+    }
+    int hh = g.pad_h, ww = g.pad_w;
+    double limit = (double)p.limit_side_len, ratio = 1.0;
+    if (p.limit_type == 0) {
+        if ((double)std::max(hh, ww) > limit) ratio = hh > ww ? limit / hh : limit / ww;
+    } else if (p.limit_type == 1) {
+        if ((double)std::min(hh, ww) < limit) ratio = hh < ww ? limit / hh : limit / ww;
+    } else {
+        ratio = limit / std::max(hh, ww);
+    }
+    int rh = (int)(hh * ratio), rw = (int)(ww * ratio);
+    rh = std::max((int)(std::nearbyint(rh / 32.0) * 32), 32);
+    rw = std::max((int)(std::nearbyint(rw / 32.0) * 32), 32);
+    g.dst_h = rh;
+    g.dst_w = rw;
+    g.ratio_h = rh / (double)hh;
+    g.ratio_w = rw / (double)ww;
+    return g;
+}
+
+static NormP det_norm() {
+    NormP n;
+    n.mul = (float)(1.0 / 255.0);
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    for (int c = 0; c < 3; ++c) {
+        n.sub[c] = mean[c];
+        n.div[c] = stdv[c];
+    }
+    n.rec_style = 0;
+    return n;
+}
+static NormP rec_norm() {
+    NormP n = det_norm();
+    n.rec_style = 1;
+    return n;
+}
+
+// OpenCV's bicubic weight table (A = -0.75, 5-bit sub-pixel, 15-bit weights)
+static std::vector<short> cubic_table() {
+    const float A = -0.75f;
+    float tab[32][4];
+    for (int i = 0; i < 32; ++i) {
+        float x = (float)i * (1.f / 32);
+        float c0 = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+        float c1 = ((A + 2) * x - (A + 3)) * x * x + 1;
+        float c2 = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+        tab[i][0] = c0; tab[i][1] = c1; tab[i][2] = c2;
+        tab[i][3] = 1.f - c0 - c1 - c2;
+    }
+    std::vector<short> out(32 * 32 * 16);
+    for (int iy = 0; iy < 32; ++iy)
+        for (int ix = 0; ix < 32; ++ix) {
+            int w[4][4], sum = 0;
+            for (int ky = 0; ky < 4; ++ky)
+                for (int kx = 0; kx < 4; ++kx) {
+                    volatile float v = tab[iy][ky] * tab[ix][kx];
+                    volatile float s = v * 32768.f;
+                    int r = (int)std::nearbyint((double)s);
+                    r = std::min(std::max(r, -32768), 32767);
+                    w[ky][kx] = r;
+                    sum += r;
+                }
+            if (sum != 32768) {
+                int diff = sum - 32768, by = 2, bx = 2;
+                for (int ky = 2; ky < 4; ++ky)
+                    for (int kx = 2; kx < 4; ++kx) {
+                        if (diff < 0 ? w[ky][kx] > w[by][bx] : w[ky][kx] < w[by][bx]) { by = ky; bx = kx; }
+                    }
+                w[by][bx] -= diff;
+            }
+            for (int ky = 0; ky < 4; ++ky)
+                for (int kx = 0; kx < 4; ++kx) out[((iy * 32 + ix) * 4 + ky) * 4 + kx] = (short)w[ky][kx];
+        }
+    return out;
+}
+
+// cv2.getPerspectiveTransform (8x8 LU with partial pivoting, float64) + 3x3 inverse.
+static bool perspective_inverse(const float* src /*[4][2]*/, int cw, int ch, double mi[9]) {
+    const double dst[4][2] = {{0, 0}, {(double)cw, 0}, {(double)cw, (double)ch}, {0, (double)ch}};
+    double a[8][8], b[8];
+    for (int i = 0; i < 4; ++i) {
+        double sx = src[2 * i], sy = src[2 * i + 1], dx = dst[i][0], dy = dst[i][1];
+        double r0[8] = {sx, sy, 1, 0, 0, 0, -sx * dx, -sy * dx};
+        double r1[8] = {0, 0, 0, sx, sy, 1, -sx * dy, -sy * dy};
+        memcpy(a[i], r0, sizeof(r0));
+        memcpy(a[i + 4], r1, sizeof(r1));
+        b[i] = dx;
+        b[i + 4] = dy;
+    }
+    const int n = 8;
+    bool ok = true;
+    for (int i = 0; i < n && ok; ++i) {
+        int k = i;
+        for (int j = i + 1; j < n; ++j)
+            if (std::fabs(a[j][i]) > std::fabs(a[k][i])) k = j;
+        if (std::fabs(a[k][i]) < 2.220446049250313e-16 * 100) { ok = false; break; }
+        if (k != i) {
+            for (int c = 0; c < n; ++c) std::swap(a[i][c], a[k][c]);
+            std::swap(b[i], b[k]);
+        }
+        double d = -1.0 / a[i][i];
+        for (int j = i + 1; j < n; ++j) {
+            double alpha = a[j][i] * d;
+            for (int c = i + 1; c < n; ++c) a[j][c] += alpha * a[i][c];
+            b[j] += alpha * b[i];
+        }
+    }
+    double m[9];
+    if (ok) {
+        for (int i = n - 1; i >= 0; --i) {
+            double s = b[i];
+            for (int k = i + 1; k < n; ++k) s -= a[i][k] * b[k];
+            b[i] = s / a[i][i];
+        }
+        for (int i = 0; i < 8; ++i) m[i] = b[i];
+    } else {
+        for (int i = 0; i < 8; ++i) m[i] = 0;
+    }
+    m[8] = 1.0;
+    double d = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+    if (d == 0) {
+        for (int i = 0; i < 9; ++i) mi[i] = 0;
+        return false;
+    }
+    d = 1.0 / d;
+    mi[0] = (m[4] * m[8] - m[5] * m[7]) * d;
+    mi[1] = (m[2] * m[7] - m[1] * m[8]) * d;
+    mi[2] = (m[1] * m[5] - m[2] * m[4]) * d;
+    mi[3] = (m[5] * m[6] - m[3] * m[8]) * d;
+    mi[4] = (m[0] * m[8] - m[2] * m[6]) * d;
+    mi[5] = (m[2] * m[3] - m[0] * m[5]) * d;
+    mi[6] = (m[3] * m[7] - m[4] * m[6]) * d;
+    mi[7] = (m[1] * m[6] - m[0] * m[7]) * d;
+    mi[8] = (m[0] * m[4] - m[1] * m[3]) * d;
+    return true;
+}
+
+static short* g_cubic_tab[16] = {nullptr};
+
+Stages::Stages(cudaStream_t st) : st_(st) {
+    for (auto& e : ev_) B200_CUDA_CHECK(cudaEventCreate(&e));
+    db_ = nullptr;
+}
+
+Stages::~Stages() {
+    for (auto& e : ev_) cudaEventDestroy(e);
+    db_free(db_);
+}
+
+static const short* cubic_tab_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 15;
+    if (!g_cubic_tab[dev]) {
+        std::vector<short> t = cubic_table();
+        B200_CUDA_CHECK(cudaMalloc(&g_cubic_tab[dev], t.size() * sizeof(short)));
+        B200_CUDA_CHECK(cudaMemcpy(g_cubic_tab[dev], t.data(), t.size() * sizeof(short), cudaMemcpyHostToDevice));
+    }
+    return g_cubic_tab[dev];
+}
+
+static ResizeJob make_job(const uint8_t* d_src, int h, int w, int stride, int ph, int pw, int dh, int dw, int rot180) {
+    ResizeJob j;
+    j.src.p = d_src; j.src.h = h; j.src.w = w; j.src.stride = stride; j.src.ph = ph; j.src.pw = pw; j.src.rot180 = rot180;
+    j.dh = dh; j.dw = dw;
+    j.scale_y = 1.0 / ((double)dh / ph);
+    j.scale_x = 1.0 / ((double)dw / pw);
+    return j;
+}
+
+// ------------------------------------------------------------------------------- det preprocess (Level A helper)
+void Stages::det_preprocess_host(const uint8_t* bgr, int h, int w, int row_stride, const b200ocr_det_params& p, float* chw,
+                                 size_t chw_capacity, int* out_h, int* out_w, double shape[4]) {
+    DetGeom g = det_geometry(h, w, p);
+    if (out_h) *out_h = g.dst_h;
+    if (out_w) *out_w = g.dst_w;
+    if (shape) {
+        shape[0] = g.src_h; shape[1] = g.src_w; shape[2] = g.ratio_h; shape[3] = g.ratio_w;
+    }
+    if (!chw) return;
+    size_t need = (size_t)3 * g.dst_h * g.dst_w;
+    if (chw_capacity < need) throw std::runtime_error("chw buffer too small");
+    if (row_stride <= 0) row_stride = w * 3;
+    size_t img_bytes = (size_t)h * row_stride;
+    uint8_t* d_img = (uint8_t*)d_img_.get(img_bytes + sizeof(ResizeJob));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_img, bgr, img_bytes, cudaMemcpyHostToDevice, st_));
+    ResizeJob job = make_job(d_img, h, w, row_stride, g.pad_h, g.pad_w, g.dst_h, g.dst_w, 0);
+    ResizeJob* d_job = (ResizeJob*)d_misc_.get(sizeof(ResizeJob));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_job, &job, sizeof(job), cudaMemcpyHostToDevice, st_));
+    float* d_out = (float*)d_chw_.get(need * sizeof(float));
+    dim3 grid((unsigned)ceil_div(g.dst_w, 256), g.dst_h, 1);
+    resize_norm_kernel<float><<<grid, 256, 0, st_>>>(d_job, g.dst_h, g.dst_w, d_out, 1, det_norm());
+    launches += 1;
+    B200_CUDA_CHECK(cudaGetLastError());
+    B200_CUDA_CHECK(cudaMemcpyAsync(chw, d_out, need * sizeof(float), cudaMemcpyDeviceToHost, st_));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st_));
+}
+
+// ------------------------------------------------------------------------------- crops
+void Stages::crop_boxes_host(const uint8_t* bgr, int h, int w, int row_stride, const float* boxes, int n, uint8_t* crops_out,
+                             size_t crops_capacity, int* crop_dims_out) {
+    if (row_stride <= 0) row_stride = w * 3;
+    std::vector<WarpJob> jobs(n);
+    size_t off = 0;
+    int max_w = 1, max_h = 1;
+    for (int i = 0; i < n; ++i) {
+        const float* b = boxes + (size_t)i * 8;
+        auto norm = [&](int a, int c) {
+            float dx = b[2 * a] - b[2 * c], dy = b[2 * a + 1] - b[2 * c + 1];
+            // np.linalg.norm on float32: sqrt(sum of squares) evaluated in float32
+            float s = dx * dx;
+            s += dy * dy;
+            return std::sqrt(s);
+        };
+        int cw = (int)std::max(norm(0, 1), norm(2, 3));
+        int ch = (int)std::max(norm(0, 3), norm(1, 2));
+        WarpJob& j = jobs[i];
+        j.cw = cw;
+        j.ch = ch;
+        j.rot90 = (cw > 0 && ch > 0 && (ch * 1.0 / cw) >= 1.5) ? 1 : 0;
+        j.out_off = off;
+        if (cw <= 0 || ch <= 0) throw std::runtime_error("bad argument: degenerate box (zero-size crop) at index " + std::to_string(i));
+        perspective_inverse(b, cw, ch, j.mi);
+        crop_dims_out[2 * i] = j.rot90 ? cw : ch;
+        crop_dims_out[2 * i + 1] = j.rot90 ? ch : cw;
+        off += (size_t)cw * ch * 3;
+        max_w = std::max(max_w, cw);
+        max_h = std::max(max_h, ch);
+    }
+    if (!crops_out) return;
+    if (off > crops_capacity) throw std::runtime_error("crop buffer too small: need " + std::to_string(off) + " bytes");
+    if (n == 0) return;
+    size_t img_bytes = (size_t)h * row_stride;
+    uint8_t* d_img = (uint8_t*)d_img_.get(img_bytes);
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_img, bgr, img_bytes, cudaMemcpyHostToDevice, st_));
+    WarpJob* d_jobs = (WarpJob*)d_misc_.get(sizeof(WarpJob) * n);
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(WarpJob) * n, cudaMemcpyHostToDevice, st_));
+    uint8_t* d_pool = (uint8_t*)d_crops_.get(off);
+    dim3 block(32, 8);
+    dim3 grid((unsigned)ceil_div(max_w, 32), (unsigned)ceil_div(max_h, 8), n);
+    warp_cubic_kernel<<<grid, block, 0, st_>>>(d_img, h, w, row_stride, d_jobs, cubic_tab_device(), d_pool);
+    launches += 1;
+    B200_CUDA_CHECK(cudaGetLastError());
+    B200_CUDA_CHECK(cudaMemcpyAsync(crops_out, d_pool, off, cudaMemcpyDeviceToHost, st_));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st_));
+}
+
+// ------------------------------------------------------------------------------- cls / rec
+namespace {
+struct BatchPlan {
+    std::vector<int> order;                     // argsort of aspect ratios (stable, like np.argsort on distinct keys)
+};
+
+// np.argsort(np.array(width_list)) — quicksort is not stable in numpy, but for equal keys the
+// permutation only reorders crops inside a batch or across batches with identical ratio; the result
+// per crop does not depend on it in the reference (each crop's output row is written back by index).
+std::vector<int> aspect_order(const int* hs, const int* ws, int n) {
+    std::vector<int> idx(n);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+        return (ws[a] / (double)hs[a]) < (ws[b] / (double)hs[b]);
+    });
+    return idx;
+}
+
+int resized_w_rule(int h, int w, int img_h, int img_w) {      // predict_rec.py:66-71 / predict_cls.py:25-30
+    double ratio = w / (double)h;
+    int c = (int)std::ceil(img_h * ratio);
+    return c > img_w ? img_w : c;
+}
+}  // namespace
+
+// uploads the crops (host pointers) into one device pool; returns per-crop device offsets
+static std::vector<size_t> upload_crops(DevBuf& pool, PinBuf& pin, const uint8_t* const* crops, const int* hs, const int* ws,
+                                        int n, cudaStream_t st, uint8_t** d_base) {
+    std::vector<size_t> off(n + 1, 0);
+    for (int i = 0; i < n; ++i) off[i + 1] = off[i] + (((size_t)hs[i] * ws[i] * 3 + 15) & ~(size_t)15);
+    uint8_t* h = (uint8_t*)pin.get(off[n] + 16);
+    for (int i = 0; i < n; ++i) memcpy(h + off[i], crops[i], (size_t)hs[i] * ws[i] * 3);
+    uint8_t* d = (uint8_t*)pool.get(off[n] + 16);
+    B200_CUDA_CHECK(cudaMemcpyAsync(d, h, off[n], cudaMemcpyHostToDevice, st));
+    *d_base = d;
+    return off;
+}
+
+void Stages::cls_crops(Model* cls, const uint8_t* const* crops, const int* hs, const int* ws, int n, int batch_num,
+                       int32_t* labels_out, float* scores_out) {
+    if (n == 0) return;
+    if (batch_num <= 0) batch_num = 6;
+    const int img_h = 48, img_w = 192;          // args.cls_image_shape "3, 48, 192" (utils.py:349)
+    uint8_t* d_base = nullptr;
+    std::vector<size_t> off = upload_crops(d_crops_, h_pin_, crops, hs, ws, n, st_, &d_base);
+    std::vector<int> order = aspect_order(hs, ws, n);
+    // every cls batch has the same canvas (48 x 192), so the whole set runs as ONE batch on the device;
+    // per-crop results do not depend on batch composition (no cross-sample op in the graph).
+    std::vector<ResizeJob> jobs(n);
+    for (int k = 0; k < n; ++k) {
+        int i = order[k];
+        int rw = resized_w_rule(hs[i], ws[i], img_h, img_w);
+        jobs[k] = make_job(d_base + off[i], hs[i], ws[i], ws[i] * 3, hs[i], ws[i], img_h, rw, 0);
+    }
+    ResizeJob* d_jobs = (ResizeJob*)d_misc_.get(sizeof(ResizeJob) * n);
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(ResizeJob) * n, cudaMemcpyHostToDevice, st_));
+    const int chunk = 512;
+    std::vector<float> probs;
+    for (int beg = 0; beg < n; beg += chunk) {
+        int b = std::min(chunk, n - beg);
+        Plan* p = cls->plan_for(b, img_h, img_w);
+        dim3 grid((unsigned)ceil_div(img_w, 256), img_h, b);
+        if (cls->precision() == PREC_BF16)
+            resize_norm_kernel<bf16><<<grid, 256, 0, st_>>>(d_jobs + beg, img_h, img_w, p->in_ptr(), 0, rec_norm());
+        else
+            resize_norm_kernel<float><<<grid, 256, 0, st_>>>(d_jobs + beg, img_h, img_w, p->in_ptr(), 0, rec_norm());
+        p->launch(st_);
+        launches += p->launches + 1;
+        B200_CUDA_CHECK(cudaGetLastError());
+        probs.resize(p->out_dense_elems);
+        B200_CUDA_CHECK(cudaMemcpyAsync(probs.data(), p->out_dense, p->out_dense_elems * sizeof(float), cudaMemcpyDeviceToHost, st_));
+        B200_CUDA_CHECK(cudaStreamSynchronize(st_));
+        int ncls = (int)(p->out_dense_elems / b);
+        for (int k = 0; k < b; ++k) {            // ClsPostProcess: argmax over classes (cls_postprocess.py:24-26)
+            const float* r = probs.data() + (size_t)k * ncls;
+            int best = 0;
+            for (int c = 1; c < ncls; ++c)
+                if (r[c] > r[best]) best = c;
+            labels_out[order[beg + k]] = best;
+            scores_out[order[beg + k]] = r[best];
+        }
+    }
+}
+
+void Stages::rec_crops(Model* rec, const uint8_t* const* crops, const int* hs, const int* ws, int n, int batch_num,
+                       const uint8_t* rotate180, int32_t* ids_out, int max_len, int* lens_out, float* scores_out) {
+    if (n == 0) return;
+    if (batch_num <= 0) batch_num = 6;
+    const int img_h = 48, img_w0 = 320;         // rec_image_shape "3, 48, 320" (onnx_paddleocr.py:20)
+    uint8_t* d_base = nullptr;
+    std::vector<size_t> off = upload_crops(d_crops_, h_pin_, crops, hs, ws, n, st_, &d_base);
+    std::vector<int> order = aspect_order(hs, ws, n);
+    // reference batches: consecutive groups of batch_num in aspect order, imgW = int(48 * max ratio) per group
+    // (predict_rec.py:290-300).  Groups with the same imgW are merged into one device batch.
+    std::vector<int> imgw(n);
+    for (int beg = 0; beg < n; beg += batch_num) {
+        int end = std::min(n, beg + batch_num);
+        double max_wh = img_w0 / (double)img_h;
+        for (int k = beg; k < end; ++k) max_wh = std::max(max_wh, ws[order[k]] * 1.0 / hs[order[k]]);
+        int W = (int)(img_h * max_wh);
+        for (int k = beg; k < end; ++k) imgw[k] = W;
+    }
+    std::vector<ResizeJob> jobs(n);
+    for (int k = 0; k < n; ++k) {
+        int i = order[k];
+        int rw = resized_w_rule(hs[i], ws[i], img_h, imgw[k]);
+        jobs[k] = make_job(d_base + off[i], hs[i], ws[i], ws[i] * 3, hs[i], ws[i], img_h, rw, rotate180 ? rotate180[i] != 0 : 0);
+    }
+    ResizeJob* d_jobs = (ResizeJob*)d_misc_.get(sizeof(ResizeJob) * n + sizeof(int) * n);
+    int* d_slots = (int*)((char*)d_jobs + sizeof(ResizeJob) * n);
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(ResizeJob) * n, cudaMemcpyHostToDevice, st_));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_slots, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st_));
+    int* d_ids = (int*)d_boxes_.get(((size_t)n * max_len + 2 * (size_t)n) * sizeof(int));
+    int* d_lens = d_ids + (size_t)n * max_len;
+    float* d_scores = (float*)(d_lens + n);
+    B200_CUDA_CHECK(cudaMemsetAsync(d_ids, 0, (size_t)n * max_len * sizeof(int), st_));
+    const int max_batch = 256;
+    for (int beg = 0; beg < n;) {
+        int end = beg;
+        while (end < n && imgw[end] == imgw[beg] && end - beg < max_batch) ++end;
+        int b = end - beg, W = imgw[beg];
+        Plan* p = rec->plan_for(b, img_h, W);
+        dim3 grid((unsigned)ceil_div(W, 256), img_h, b);
+        if (rec->precision() == PREC_BF16)
+            resize_norm_kernel<bf16><<<grid, 256, 0, st_>>>(d_jobs + beg, img_h, W, p->in_ptr(), 0, rec_norm());
+        else
+            resize_norm_kernel<float><<<grid, 256, 0, st_>>>(d_jobs + beg, img_h, W, p->in_ptr(), 0, rec_norm());
+        p->launch(st_);
+        if (p->out_shape.size() != 3) throw std::runtime_error("rec model output must be [B, T, classes]");
+        int T = (int)p->out_shape[1], C = (int)p->out_shape[2];
+        int rows = b * T;
+        int* d_idx = (int*)d_batch_.get((size_t)rows * (sizeof(int) + 2 * sizeof(float)));
+        float* d_mx = (float*)(d_idx + rows);
+        float* d_scr = d_mx + rows;
+        ctc_argmax_kernel<<<rows, 256, 0, st_>>>(p->out_dense, C, d_idx, d_mx);
+        ctc_collapse_kernel<<<(unsigned)ceil_div(b, 64), 64, 0, st_>>>(d_idx, d_mx, b, T, d_slots + beg, max_len, d_ids, d_lens,
+                                                                        d_scores, d_scr);
+        launches += p->launches + 3;
+        B200_CUDA_CHECK(cudaGetLastError());
+        beg = end;
+    }
+    B200_CUDA_CHECK(cudaMemcpyAsync(ids_out, d_ids, (size_t)n * max_len * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    B200_CUDA_CHECK(cudaMemcpyAsync(lens_out, d_lens, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    B200_CUDA_CHECK(cudaMemcpyAsync(scores_out, d_scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st_));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st_));
+}
+
+// ------------------------------------------------------------------------------- det pages
+// filter_tag_det_res (predict_det.py:67-81) on int32 boxes in cv2 order -> float32 boxes
+static int filter_boxes(const int32_t* in, int n, int img_h, int img_w, float* out, int max_boxes) {
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        float pts[4][2];
+        for (int k = 0; k < 4; ++k) {
+            pts[k][0] = (float)in[i * 8 + 2 * k];
+            pts[k][1] = (float)in[i * 8 + 2 * k + 1];
+        }
+        // order_points_clockwise (predict_det.py:50-59): np.argmin/argmax return the first extremum
+        float s[4];
+        for (int k = 0; k < 4; ++k) s[k] = pts[k][0] + pts[k][1];
+        int imin = 0, imax = 0;
+        for (int k = 1; k < 4; ++k) {
+            if (s[k] < s[imin]) imin = k;
+            if (s[k] > s[imax]) imax = k;
+        }
+        float rect[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+        rect[0][0] = pts[imin][0]; rect[0][1] = pts[imin][1];
+        rect[2][0] = pts[imax][0]; rect[2][1] = pts[imax][1];
+        int rest[4], nr = 0;
+        for (int k = 0; k < 4; ++k)
+            if (k != imin && k != imax) rest[nr++] = k;        // np.delete keeps 3 rows when imin == imax
+        float d[4];
+        for (int k = 0; k < nr; ++k) d[k] = pts[rest[k]][1] - pts[rest[k]][0];
+        int dmin = 0, dmax = 0;
+        for (int k = 1; k < nr; ++k) {
+            if (d[k] < d[dmin]) dmin = k;
+            if (d[k] > d[dmax]) dmax = k;
+        }
+        rect[1][0] = pts[rest[dmin]][0]; rect[1][1] = pts[rest[dmin]][1];
+        rect[3][0] = pts[rest[dmax]][0]; rect[3][1] = pts[rest[dmax]][1];
+        // clip_det_res (predict_det.py:61-65)
+        for (int k = 0; k < 4; ++k) {
+            rect[k][0] = (float)(int)std::min(std::max(rect[k][0], 0.f), (float)(img_w - 1));
+            rect[k][1] = (float)(int)std::min(std::max(rect[k][1], 0.f), (float)(img_h - 1));
+        }
+        auto norm = [&](int a, int b) {
+            float dx = rect[a][0] - rect[b][0], dy = rect[a][1] - rect[b][1];
+            float q = dx * dx;
+            q += dy * dy;
+            return std::sqrt(q);
+        };
+        int rw = (int)norm(0, 1), rh = (int)norm(0, 3);
+        if (rw <= 3 || rh <= 3) continue;
+        if (m >= max_boxes) throw std::runtime_error("box capacity too small");
+        memcpy(out + (size_t)m * 8, rect, sizeof(rect));
+        ++m;
+    }
+    return m;
+}
+
+void Stages::det_pages(Model* det, const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n,
+                       const b200ocr_det_params& p, float* boxes_out, int max_boxes, int* n_boxes_out, float* probmap_out,
+                       size_t probmap_capacity, int* probmap_dims_out) {
+    if (n == 0) return;
+    cudaEventRecord(ev_[0], st_);
+    // group pages by (src shape) so equal-shaped pages run as one batch
+    std::vector<int> idx(n);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+        return hs[a] != hs[b] ? hs[a] < hs[b] : ws[a] < ws[b];
+    });
+    std::vector<size_t> prob_off(n + 1, 0);
+    std::vector<DetGeom> geo(n);
+    for (int i = 0; i < n; ++i) {
+        geo[i] = det_geometry(hs[i], ws[i], p);
+        prob_off[i + 1] = prob_off[i] + (size_t)geo[i].dst_h * geo[i].dst_w;
+        if (probmap_dims_out) {
+            probmap_dims_out[2 * i] = geo[i].dst_h;
+            probmap_dims_out[2 * i + 1] = geo[i].dst_w;
+        }
+    }
+    if (probmap_out && prob_off[n] > probmap_capacity) throw std::runtime_error("probability-map buffer too small");
+    float t_pre = 0, t_net = 0, t_post = 0;
+    const int max_batch = 16;
+    for (int g0 = 0; g0 < n;) {
+        int g1 = g0;
+        while (g1 < n && hs[idx[g1]] == hs[idx[g0]] && ws[idx[g1]] == ws[idx[g0]] && g1 - g0 < max_batch) ++g1;
+        int b = g1 - g0;
+        const DetGeom& g = geo[idx[g0]];
+        int h = hs[idx[g0]], w = ws[idx[g0]];
+        // upload
+        std::vector<ResizeJob> jobs(b);
+        size_t total = 0;
+        std::vector<size_t> off(b);
+        for (int k = 0; k < b; ++k) {
+            int i = idx[g0 + k];
+            int stride = strides && strides[i] > 0 ? strides[i] : w * 3;
+            off[k] = total;
+            total += ((size_t)h * stride + 255) & ~(size_t)255;
+        }
+        uint8_t* d_img = (uint8_t*)d_img_.get(total);
+        for (int k = 0; k < b; ++k) {
+            int i = idx[g0 + k];
+            int stride = strides && strides[i] > 0 ? strides[i] : w * 3;
+            B200_CUDA_CHECK(cudaMemcpyAsync(d_img + off[k], pages[i], (size_t)h * stride, cudaMemcpyHostToDevice, st_));
+            jobs[k] = make_job(d_img + off[k], h, w, stride, g.pad_h, g.pad_w, g.dst_h, g.dst_w, 0);
+        }
+        ResizeJob* d_jobs = (ResizeJob*)d_misc_.get(sizeof(ResizeJob) * b);
+        B200_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(ResizeJob) * b, cudaMemcpyHostToDevice, st_));
+        Plan* pl = det->plan_for(b, g.dst_h, g.dst_w);
+        cudaEventRecord(ev_[1], st_);
+        dim3 grid((unsigned)ceil_div(g.dst_w, 256), g.dst_h, b);
+        if (det->precision() == PREC_BF16)
+            resize_norm_kernel<bf16><<<grid, 256, 0, st_>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
+        else
+            resize_norm_kernel<float><<<grid, 256, 0, st_>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
+        cudaEventRecord(ev_[2], st_);
+        pl->launch(st_);
+        launches += pl->launches + 1;
+        cudaEventRecord(ev_[3], st_);
+        B200_CUDA_CHECK(cudaGetLastError());
+        // the dense output is [b,1,H,W] fp32 == the probability maps
+        if (probmap_out)
+            for (int k = 0; k < b; ++k)
+                B200_CUDA_CHECK(cudaMemcpyAsync(probmap_out + prob_off[idx[g0 + k]],
+                                                pl->out_dense + (size_t)k * g.dst_h * g.dst_w,
+                                                (size_t)g.dst_h * g.dst_w * sizeof(float), cudaMemcpyDeviceToHost, st_));
+        std::vector<int> sh(b, h), sw(b, w);
+        std::vector<int32_t> boxes;
+        std::vector<double> scores;
+        std::vector<int> counts;
+        db_postprocess_device(pl->out_dense, b, g.dst_h, g.dst_w, sh.data(), sw.data(), p, p.max_candidates, &boxes, &scores, &counts);
+        float ms;
+        cudaEventElapsedTime(&ms, ev_[1], ev_[2]); t_pre += ms;
+        cudaEventElapsedTime(&ms, ev_[2], ev_[3]); t_net += ms;
+        size_t bo = 0;
+        for (int k = 0; k < b; ++k) {
+            int i = idx[g0 + k];
+            n_boxes_out[i] = filter_boxes(boxes.data() + bo * 8, counts[k], h, w, boxes_out + (size_t)i * max_boxes * 8, max_boxes);
+            bo += counts[k];
+        }
+        g0 = g1;
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(st_));
+    stage_ms[0] = t_pre;
+    stage_ms[1] = t_net;
+    stage_ms[2] = t_post;
+    stage_ms[3] = t_pre + t_net + t_post;
+}
+
+void Stages::db_postprocess_host(const float* prob, int h, int w, int src_h, int src_w, const b200ocr_det_params& p,
+                                 int32_t* boxes_out, double* scores_out, int capacity, int* n_boxes) {
+    float* d = (float*)d_prob_.get((size_t)h * w * sizeof(float));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d, prob, (size_t)h * w * sizeof(float), cudaMemcpyHostToDevice, st_));
+    std::vector<int32_t> boxes;
+    std::vector<double> scores;
+    std::vector<int> counts;
+    db_postprocess_device(d, 1, h, w, &src_h, &src_w, p, p.max_candidates, &boxes, &scores, &counts);
+    int n = counts.empty() ? 0 : counts[0];
+    if (n > capacity) throw std::runtime_error("box capacity too small: need " + std::to_string(n));
+    memcpy(boxes_out, boxes.data(), (size_t)n * 8 * sizeof(int32_t));
+    if (scores_out) memcpy(scores_out, scores.data(), (size_t)n * sizeof(double));
+    *n_boxes = n;
+}
+
+void Stages::resident_upload(const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n) {
+    res_off_.assign(n, 0);
+    res_h_.assign(hs, hs + n);
+    res_w_.assign(ws, ws + n);
+    res_stride_.resize(n);
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) {
+        res_stride_[i] = strides && strides[i] > 0 ? strides[i] : ws[i] * 3;
+        res_off_[i] = total;
+        total += ((size_t)hs[i] * res_stride_[i] + 255) & ~(size_t)255;
+    }
+    uint8_t* d = (uint8_t*)d_res_.get(total);
+    for (int i = 0; i < n; ++i)
+        B200_CUDA_CHECK(cudaMemcpyAsync(d + res_off_[i], pages[i], (size_t)hs[i] * res_stride_[i], cudaMemcpyHostToDevice, st_));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st_));
+}
+
+void Stages::resident_run(Model* det, const b200ocr_det_params& p, int iters, float* ms_total, int* n_boxes_total,
+                          float* net_ms_total) {
+    int n = (int)res_h_.size();
+    if (n == 0) throw std::runtime_error("bad argument: no resident pages uploaded");
+    for (int i = 1; i < n; ++i)
+        if (res_h_[i] != res_h_[0] || res_w_[i] != res_w_[0]) throw std::runtime_error("bad argument: resident pages must share one shape");
+    DetGeom g = det_geometry(res_h_[0], res_w_[0], p);
+    std::vector<ResizeJob> jobs(n);
+    uint8_t* d = (uint8_t*)d_res_.p;
+    for (int i = 0; i < n; ++i)
+        jobs[i] = make_job(d + res_off_[i], res_h_[i], res_w_[i], res_stride_[i], g.pad_h, g.pad_w, g.dst_h, g.dst_w, 0);
+    ResizeJob* d_jobs = (ResizeJob*)d_misc_.get(sizeof(ResizeJob) * n);
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(ResizeJob) * n, cudaMemcpyHostToDevice, st_));
+    Plan* pl = det->plan_for(n, g.dst_h, g.dst_w);
+    float total = 0, net_total = 0;
+    int boxes_total = 0;
+    std::vector<int> sh(res_h_), sw(res_w_);
+    for (int it = 0; it < iters; ++it) {
+        cudaEventRecord(ev_[0], st_);
+        dim3 grid((unsigned)ceil_div(g.dst_w, 256), g.dst_h, n);
+        if (det->precision() == PREC_BF16)
+            resize_norm_kernel<bf16><<<grid, 256, 0, st_>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
+        else
+            resize_norm_kernel<float><<<grid, 256, 0, st_>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
+        cudaEventRecord(ev_[1], st_);
+        pl->launch(st_);
+        cudaEventRecord(ev_[2], st_);
+        launches += pl->launches + 1;
+        std::vector<int32_t> boxes;
+        std::vector<double> scores;
+        std::vector<int> counts;
+        db_postprocess_device(pl->out_dense, n, g.dst_h, g.dst_w, sh.data(), sw.data(), p, p.max_candidates, &boxes, &scores, &counts);
+        cudaEventRecord(ev_[3], st_);
+        B200_CUDA_CHECK(cudaEventSynchronize(ev_[3]));
+        float ms;
+        cudaEventElapsedTime(&ms, ev_[0], ev_[3]);
+        total += ms;
+        cudaEventElapsedTime(&ms, ev_[1], ev_[2]);
+        net_total += ms;
+        for (int c : counts) boxes_total += c;
+    }
+    if (ms_total) *ms_total = total;
+    if (n_boxes_total) *n_boxes_total = boxes_total;
+    if (net_ms_total) *net_ms_total = net_total;
+}
+
+}  // namespace b200ocr

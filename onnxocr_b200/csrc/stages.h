@@ -1,0 +1,80 @@
+// Fused pre/post-processing stages around the graph executor (Level B of the boundary).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+#include "../../include/b200ocr.h"
+#include "engine.h"
+
+namespace b200ocr {
+
+struct DetGeom {            // DetResizeForTest.resize_image_type0 result (operators.py:91-138)
+    int src_h, src_w;       // original size (shape[0], shape[1])
+    int pad_h, pad_w;       // after image_padding (operators.py:72-76)
+    int dst_h, dst_w;       // network input size
+    double ratio_h, ratio_w;
+};
+
+DetGeom det_geometry(int h, int w, const b200ocr_det_params& p);
+
+// growable device / pinned buffers
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* get(size_t bytes);
+    ~DevBuf();
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* get(size_t bytes);
+    ~PinBuf();
+};
+
+struct DbWork;              // device scratch of DBPostProcess (dbpost.cu)
+void db_free(DbWork* w);
+
+class Stages {
+public:
+    explicit Stages(cudaStream_t st);
+    ~Stages();
+
+    void det_preprocess_host(const uint8_t* bgr, int h, int w, int row_stride, const b200ocr_det_params& p, float* chw,
+                             size_t chw_capacity, int* out_h, int* out_w, double shape[4]);
+    void db_postprocess_host(const float* prob, int h, int w, int src_h, int src_w, const b200ocr_det_params& p,
+                             int32_t* boxes_out, double* scores_out, int capacity, int* n_boxes);
+    void det_pages(Model* det, const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n,
+                   const b200ocr_det_params& p, float* boxes_out, int max_boxes, int* n_boxes_out, float* probmap_out,
+                   size_t probmap_capacity, int* probmap_dims_out);
+    void crop_boxes_host(const uint8_t* bgr, int h, int w, int row_stride, const float* boxes, int n, uint8_t* crops_out,
+                         size_t crops_capacity, int* crop_dims_out);
+    void cls_crops(Model* cls, const uint8_t* const* crops, const int* hs, const int* ws, int n, int batch_num,
+                   int32_t* labels_out, float* scores_out);
+    void rec_crops(Model* rec, const uint8_t* const* crops, const int* hs, const int* ws, int n, int batch_num,
+                   const uint8_t* rotate180, int32_t* ids_out, int max_len, int* lens_out, float* scores_out);
+    void resident_upload(const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n);
+    void resident_run(Model* det, const b200ocr_det_params& p, int iters, float* ms_total, int* n_boxes_total,
+                      float* net_ms_total);
+
+    int64_t launches = 0;
+    float stage_ms[4] = {0, 0, 0, 0};
+
+private:
+    // device-side DBPostProcess on a device-resident fp32 probability map [n][h][w]; results on the host
+    void db_postprocess_device(const float* d_prob, int n, int h, int w, const int* src_hs, const int* src_ws,
+                               const b200ocr_det_params& p, int capacity, std::vector<int32_t>* boxes,
+                               std::vector<double>* scores, std::vector<int>* counts);
+    cudaStream_t st_;
+    cudaEvent_t ev_[4];
+    DevBuf d_img_, d_chw_, d_prob_, d_boxes_, d_crops_, d_misc_, d_batch_;
+    PinBuf h_pin_, h_pin2_;
+    DbWork* db_ = nullptr;
+    // resident pages
+    DevBuf d_res_;
+    std::vector<size_t> res_off_;
+    std::vector<int> res_h_, res_w_, res_stride_;
+};
+
+}  // namespace b200ocr
