@@ -54,6 +54,11 @@ def _compile(src, extra, verbose):
 
 
 def build(verbose=False, force=False):
+    """Compiles every TU for sm_100a and links libb200ocr.so; a no-op when sources are unchanged."""
+    stamp = LIB + ".stamp"
+    total = _digest("all", ARCH + COMMON + [repr(SOURCES)])
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == total:
+        return LIB
     os.makedirs(OBJ, exist_ok=True)
     if force:
         for f in os.listdir(OBJ):
@@ -68,6 +73,8 @@ def build(verbose=False, force=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    with open(stamp, "w") as fh:
+        fh.write(total)
     return LIB
 
 

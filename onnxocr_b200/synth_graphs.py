@@ -149,10 +149,16 @@ class _G(object):
             y = self.hardswish(y)
         return y
 
-    def linear(self, x, cin, cout, gain=1.0):
+    def linear(self, x, cin, cout, gain=1.0, bias_shift=0.0):
         name = self._n("linear")
         w = (self.rng.standard_normal((cin, cout)) * gain / np.sqrt(cin)).astype(np.float32)
-        b = (self.rng.standard_normal(cout) * 0.05).astype(np.float32)
+        b = (self.rng.standard_normal(cout) * 0.05 + bias_shift).astype(np.float32)
+        # fitted column subset (tools/train_synth_rec.py stores only the classes it trained)
+        cols = self.overrides.get(name + ".cols")
+        if cols is not None:
+            cols = np.asarray(cols).astype(np.int64)
+            w[:, cols] = np.asarray(self.overrides[name + ".w_cols"]).astype(np.float32)
+            b[cols] = np.asarray(self.overrides[name + ".b_cols"]).astype(np.float32)
         y = self.op("MatMul", [x, self.const(w, name + ".w_0")])
         return self.op("Add", [y, self.const(b, name + ".b_0")])
 
@@ -276,9 +282,10 @@ def build_det(seed=50, gains=None, fitted=True):
     return model, g.params
 
 
-def build_rec(seed=51, n_classes=18385, gains=None):
+def build_rec(seed=51, n_classes=18385, gains=None, fitted=True):
     """SVTR_LCNet recogniser: input 'x' [B,3,48,W], output 'softmax_0.tmp_0' [B,W/8,n_classes]."""
-    g = _G(seed, _load_gains("rec") if gains is None else gains)
+    ov = _load_overrides("rec_synth_weights.npz") if fitted else {}
+    g = _G(seed, _load_gains("rec") if gains is None else gains, ov)
     scale = 0.95
     y, taps = _backbone(g, "x", _REC_CFG, scale)
     c = taps[-1][1]                                           # 480
@@ -332,7 +339,9 @@ def build_rec(seed=51, n_classes=18385, gains=None):
     z = g.op("Squeeze", [z], axes=[2])
     z = g.op("Transpose", [z], perm=[0, 2, 1])
     # CTCHead.fc + softmax(axis=2)
-    z = g.linear(z, dims, n_classes, gain=6.0)
+    # when fitted weights exist, classes outside the fitted subset keep small seeded weights and a
+    # strongly negative bias, so they never win the argmax (the FC still computes all 18385 logits)
+    z = g.linear(z, dims, n_classes, gain=0.5 if ov else 6.0, bias_shift=-12.0 if ov else 0.0)
     g.nodes.append(ow.enc_node("Softmax", [z], ["softmax_0.tmp_0"], axis=2))
     n = "p2o.DynamicDimension."
     model = ow.enc_model(g.nodes, [ow.enc_value_info("x", [n + "0", 3, 48, n + "1"])],
