@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Headline benchmark: PP-OCRv5 mobile det pages/s on B200 (BASELINE.json config 2).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision bf16|fp32]
+
+One "step" = one pass of the det hot path (fused resize/normalise -> DBNet -> DBPostProcess -> boxes) over a
+batch of 16 synthetic 960x960 pages per GPU.  Pages shard across GPUs as independent per-GPU pipelines
+(weak scaling, no collective on the data path); torch.distributed is used for the barrier and the max-over-ranks
+of the device time only.
+
+  value     pages/s with the page bytes already resident in HBM (CUDA events on the engine stream)
+  e2e       pages/s through the public API (`Engine.det_pages`) with HOST page buffers: H2D of the page
+            bytes from pinned memory and D2H of the boxes are inside the timed region
+  roofline  dominant kernel class of the step, timed live per launch with CUDA events
+  cpu_baseline / --impl reference: the oracle port of the reference's CPU path (reference pre/post-processing
+            restated with cv2/numpy, network through the torch-CPU fp32 interpreter: onnxruntime is not
+            installed in this image) timed on the host cores of the same box.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PAGES_PER_GPU = 16
+SIDE = 960
+LINES = 40
+METRIC = "PP-OCRv5 mobile det pages/sec (960x960 pages, batch 16, prob map + DBPostProcess boxes)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device = device
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 6:
+                    continue
+                try:
+                    self.samples.append((float(parts[0]), float(parts[1])))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": statistics.median(s[0] for s in self.samples), "sm_max_mhz": self.samples[0][1],
+                "reasons": sorted(self.reasons)}
+
+
+def make_pages(rank):
+    from onnxocr_b200 import synth_pages
+    return synth_pages.det_pages_c2(PAGES_PER_GPU, SIDE, LINES, seed=rank)
+
+
+def oracle_det_pages(pages, graph):
+    """The reference's det path on the CPU: DetResizeForTest/NormalizeImage/ToCHWImage -> session.run -> DBPostProcess
+    -> filter_tag_det_res, one page at a time like TextDetector.__call__ (predict_det.py:94-120)."""
+    from oracle import restate_post, restate_pre
+    n_boxes = 0
+    for img in pages:
+        x, shape = restate_pre.det_preprocess(img)
+        prob = graph.run(None, {"x": x})[0]
+        boxes, _ = restate_post.db_postprocess(prob, shape[None])[0]
+        n_boxes += len(restate_post.filter_tag_det_res(boxes, img.shape))
+    return n_boxes
+
+
+def cpu_arm(pages, steps, warmup, sample_pages):
+    import torch
+    from onnxocr_b200 import synth_graphs
+    from oracle.torch_interp import TorchGraph
+    torch.set_num_threads(os.cpu_count() or 1)
+    graph = TorchGraph(synth_graphs.ensure_models()["det"])
+    sample = pages[:sample_pages]
+    for _ in range(warmup):
+        oracle_det_pages(sample[:1], graph)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_det_pages(sample, graph)
+    dt = time.perf_counter() - t0
+    return {"value": len(sample) * steps / dt, "ms_per_step": dt / steps * 1e3, "cores": torch.get_num_threads(),
+            "sample": "%d of the %d 960x960 pages per step, %d step(s); torch-CPU restatement of the ORT-CPU path "
+                      "(onnxruntime absent), cv2 %s pre/post-processing" % (len(sample), PAGES_PER_GPU, steps,
+                                                                           __import__("cv2").__version__)}
+
+
+def kernel_class(name):
+    return name.split(" ")[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        pages = make_pages(0)
+        r = cpu_arm(pages, max(1, args.steps), min(warmup, 1), sample_pages=2)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "pages/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2 det-only: 960x960 synthetic pages, prob map + DBPostProcess boxes",
+                       "pages_per_step": 2},
+            "cpu_baseline": {"value": r["value"], "unit": "pages/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from onnxocr_b200 import _lib, build, synth_graphs
+    build.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libb200ocr has no CPU fallback")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    prec = _lib.BF16 if args.precision == "bf16" else _lib.FP32
+    paths = synth_graphs.ensure_models()
+    eng = _lib.Engine(local_rank)
+    eng.load_onnx(_lib.DET, paths["det"], prec)
+    pages = make_pages(rank)
+    params = _lib.det_params()
+
+    # ---- device-resident timing ("value")
+    eng.det_resident_upload(pages)
+    for _ in range(max(warmup, 3)):
+        eng.det_resident_run(params, 1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    barrier()
+    dev_ms = net_ms = 0.0
+    n_boxes = 0
+    for _ in range(args.steps):
+        eng.l2_flush()
+        ms, nb, net = eng.det_resident_run(params, 1)
+        dev_ms += ms
+        net_ms += net
+        n_boxes += nb
+    barrier()
+    launches = eng.launch_count() - launches0
+    dev_ms = max_over_ranks(dev_ms)
+    value = PAGES_PER_GPU * world * args.steps / (dev_ms / 1e3)
+
+    # ---- end to end through the public API with host buffers ("e2e")
+    pinned = []
+    for p in pages:
+        a = eng.pinned_array(p.shape, np.uint8)
+        a[...] = p
+        pinned.append(a)
+    for _ in range(max(warmup, 3)):
+        eng.det_pages(pinned, params)
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        out = eng.det_pages(pinned, params)
+        d2h = sum(b.nbytes for b in out) + 4 * len(out)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = PAGES_PER_GPU * world * args.steps / e2e_s
+    h2d = sum(p.nbytes for p in pages)
+    if rank == 0:
+        sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class (live CUDA-event timing per launch)
+    peaks = load_peaks()
+    prof = eng.profile_plan(_lib.DET, PAGES_PER_GPU, SIDE, SIDE, iters=3)
+    classes = {}
+    for s in prof:
+        c = classes.setdefault(kernel_class(s["name"]), {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        c["ms"] += s["ms"]
+        c["flops"] += s["flops"]
+        c["bytes"] += s["bytes"]
+        c["launches"] += 1
+    total_ms = sum(c["ms"] for c in classes.values())
+    top = max(classes.items(), key=lambda kv: kv[1]["ms"])
+    tname, t = top
+    tensor_bound = tname in ("conv", "linear", "convT")
+    if tensor_bound:
+        ach = t["flops"] / (t["ms"] / 1e3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None}
+    else:
+        ach = t["bytes"] / (t["ms"] / 1e3) / 1e9
+        peak = peaks["hbm_gbs"]
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None}
+    roof.update({"kernel": tname, "launches_per_step": t["launches"], "share_of_network_time": t["ms"] / total_ms,
+                 "peak_source": peaks["source"]})
+    breakdown = {k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4),
+                     "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 3),
+                     "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1), "launches": v["launches"]}
+                 for k, v in sorted(classes.items(), key=lambda kv: -kv[1]["ms"])}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "C2 det-only: 16 synthetic 960x960 pages per GPU per step (synthetic-weight PP-OCRv5 mobile "
+                               "det graph, fitted on rendered pages), prob map + DBPostProcess boxes",
+                   "pages_per_gpu": PAGES_PER_GPU, "l2": "flushed between timed iterations (256 MiB write)",
+                   "boxes_per_step": n_boxes / max(args.steps, 1)},
+        "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "network_ms_per_step": net_ms / args.steps,
+        "roofline": roof,
+        "kernel_classes": breakdown,
+        "clocks": sampler.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_arm(pages, 1, 1, sample_pages=8)
+        out["cpu_baseline"] = {"value": r["value"], "unit": "pages/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -70,12 +70,12 @@ int b200ocr_session_run(b200ocr_engine* e, int kind, const float* nchw, const in
 typedef struct b200ocr_det_params {
     float limit_side_len;     /* args.det_limit_side_len (960)        utils.py:271 */
     int limit_type;           /* 0 'max', 1 'min', 2 'resize_long'    utils.py:272 */
-    float thresh;             /* det_db_thresh 0.3                    utils.py:276 */
-    float box_thresh;         /* det_db_box_thresh 0.6                utils.py:277 */
-    float unclip_ratio;       /* det_db_unclip_ratio 1.5              utils.py:278 */
+    float thresh;             /* det_db_thresh 0.3 (compared in float32, like `pred > self.thresh`)  utils.py:276 */
     int max_candidates;       /* 1000                                 predict_det.py:33 */
     int min_size;             /* 3                                    db_postprocess.py:47 */
     int use_dilation;         /* 0                                    utils.py:280 */
+    double box_thresh;        /* det_db_box_thresh 0.6 (Python float, compared in float64)  utils.py:277 */
+    double unclip_ratio;      /* det_db_unclip_ratio 1.5 (Python float)                      utils.py:278 */
 } b200ocr_det_params;
 
 void b200ocr_det_params_default(b200ocr_det_params* p);
@@ -132,6 +132,17 @@ int b200ocr_describe(b200ocr_engine* e, int kind, char* buf, size_t cap);
 /* 2*MACs and kernel-launch count of the plan for a given input shape. */
 int b200ocr_plan_stats(b200ocr_engine* e, int kind, int n, int h, int w, double* flops, int* launches,
                        double* arena_bytes);
+/* Per-kernel device time of one plan, measured live with CUDA events between launches on the engine
+ * stream (the plan's input buffer keeps whatever the last run left there).  For step i: ms_out[i] (average
+ * over iters), flops_out[i] / bytes_out[i] = algorithmic work of that launch (2*MACs; unique input + output +
+ * weight bytes at the storage type); names are written NUL-separated into names_buf.  Returns the step count. */
+int b200ocr_profile_plan(b200ocr_engine* e, int kind, int n, int h, int w, int iters, float* ms_out, double* flops_out,
+                         double* bytes_out, int capacity, char* names_buf, size_t names_cap);
+/* Writes a buffer larger than L2 (256 MiB) on the engine stream: an L2 flush between timed iterations. */
+int b200ocr_l2_flush(b200ocr_engine* e);
+/* Page-locked host memory for callers that want the H2D copies of their page buffers to be truly async. */
+void* b200ocr_host_alloc(size_t bytes);
+void b200ocr_host_free(void* p);
 /* Kernels launched by this engine since creation (bench.py's gpu_launches). */
 int64_t b200ocr_launch_count(const b200ocr_engine* e);
 /* Device time (ms, CUDA events on the engine stream) of the stages of the last fused call:

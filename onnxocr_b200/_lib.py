@@ -21,8 +21,8 @@ _lock = threading.Lock()
 
 class DetParams(C.Structure):
     _fields_ = [("limit_side_len", C.c_float), ("limit_type", C.c_int), ("thresh", C.c_float),
-                ("box_thresh", C.c_float), ("unclip_ratio", C.c_float), ("max_candidates", C.c_int),
-                ("min_size", C.c_int), ("use_dilation", C.c_int)]
+                ("max_candidates", C.c_int), ("min_size", C.c_int), ("use_dilation", C.c_int),
+                ("box_thresh", C.c_double), ("unclip_ratio", C.c_double)]
 
 
 _LIMIT_TYPES = {"max": 0, "min": 1, "resize_long": 2}
@@ -30,8 +30,8 @@ _LIMIT_TYPES = {"max": 0, "min": 1, "resize_long": 2}
 
 def det_params(limit_side_len=960, limit_type="max", thresh=0.3, box_thresh=0.6, unclip_ratio=1.5,
                max_candidates=1000, min_size=3, use_dilation=False):
-    return DetParams(float(limit_side_len), _LIMIT_TYPES[limit_type], float(thresh), float(box_thresh),
-                     float(unclip_ratio), int(max_candidates), int(min_size), int(bool(use_dilation)))
+    return DetParams(float(limit_side_len), _LIMIT_TYPES[limit_type], float(thresh), int(max_candidates),
+                     int(min_size), int(bool(use_dilation)), float(box_thresh), float(unclip_ratio))
 
 
 def lib():
@@ -67,6 +67,12 @@ def lib():
         L.b200ocr_rec_crops.argtypes = [vp, C.POINTER(vp), pi, pi, i, i, vp, vp, i, pi, vp]
         L.b200ocr_describe.argtypes = [vp, i, C.c_char_p, sz]
         L.b200ocr_plan_stats.argtypes = [vp, i, i, i, i, pd, pi, pd]
+        L.b200ocr_profile_plan.argtypes = [vp, i, i, i, i, i, pf, pd, pd, i, C.c_char_p, sz]
+        L.b200ocr_l2_flush.argtypes = [vp]
+        L.b200ocr_host_alloc.argtypes = [sz]
+        L.b200ocr_host_alloc.restype = vp
+        L.b200ocr_host_free.argtypes = [vp]
+        L.b200ocr_host_free.restype = None
         L.b200ocr_launch_count.argtypes = [vp]
         L.b200ocr_launch_count.restype = C.c_int64
         L.b200ocr_stage_times.argtypes = [vp, pf]
@@ -101,6 +107,9 @@ class Engine(object):
         if getattr(self, "_h", None):
             self._L.b200ocr_destroy(self._h)
             self._h = None
+            for ptr in getattr(self, "_pinned", []):
+                self._L.b200ocr_host_free(ptr)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -148,6 +157,31 @@ class Engine(object):
         la = C.c_int()
         self._check(self._L.b200ocr_plan_stats(self._h, kind, n, h, w, C.byref(fl), C.byref(la), C.byref(ar)))
         return {"flops": fl.value, "launches": la.value, "arena_bytes": ar.value}
+
+    def profile_plan(self, kind, n, h, w, iters=3):
+        """-> list of dict(name, ms, flops, bytes) per kernel launch of the plan for input [n,3,h,w]."""
+        cap = 4096
+        ms = (C.c_float * cap)()
+        fl = (C.c_double * cap)()
+        by = (C.c_double * cap)()
+        names = C.create_string_buffer(1 << 18)
+        ns = self._check(self._L.b200ocr_profile_plan(self._h, kind, n, h, w, iters, ms, fl, by, cap, names, len(names)))
+        parts = names.raw.split(b"\0")
+        return [{"name": parts[k].decode(), "ms": ms[k], "flops": fl[k], "bytes": by[k]} for k in range(ns)]
+
+    def l2_flush(self):
+        self._check(self._L.b200ocr_l2_flush(self._h))
+
+    def pinned_array(self, shape, dtype=np.uint8):
+        """numpy array over page-locked host memory (b200ocr_host_alloc); freed with the engine."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = self._L.b200ocr_host_alloc(nbytes)
+        if not ptr:
+            raise MemoryError("b200ocr_host_alloc(%d) failed" % nbytes)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        buf = (C.c_uint8 * nbytes).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     def launch_count(self):
         return int(self._L.b200ocr_launch_count(self._h))

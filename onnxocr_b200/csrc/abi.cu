@@ -157,8 +157,8 @@ void b200ocr_det_params_default(b200ocr_det_params* p) {
     p->limit_side_len = 960.f;
     p->limit_type = 0;
     p->thresh = 0.3f;
-    p->box_thresh = 0.6f;
-    p->unclip_ratio = 1.5f;
+    p->box_thresh = 0.6;
+    p->unclip_ratio = 1.5;
     p->max_candidates = 1000;
     p->min_size = 3;
     p->use_dilation = 0;
@@ -253,6 +253,52 @@ int b200ocr_plan_stats(b200ocr_engine* e, int kind, int n, int h, int w, double*
         if (arena_bytes) *arena_bytes = (double)p->arena_bytes;
         return B200OCR_OK;
     });
+}
+
+int b200ocr_profile_plan(b200ocr_engine* e, int kind, int n, int h, int w, int iters, float* ms_out, double* flops_out,
+                         double* bytes_out, int capacity, char* names_buf, size_t names_cap) {
+    return guarded(e, [&]() {
+        Model* m = need(e, kind);
+        std::lock_guard<std::mutex> lk(e->mu);
+        std::vector<float> ms;
+        m->profile(n, h, w, iters < 1 ? 1 : iters, e->stream, &ms);
+        Plan* p = m->plan_for(n, h, w);
+        int ns = (int)ms.size();
+        if (ns > capacity) throw std::runtime_error("profile buffers too small: need " + std::to_string(ns));
+        size_t off = 0;
+        for (int i = 0; i < ns; ++i) {
+            ms_out[i] = ms[i];
+            if (flops_out) flops_out[i] = p->step_flops[i];
+            if (bytes_out) bytes_out[i] = p->step_bytes[i];
+            if (names_buf) {
+                const std::string& nm = p->step_names[i];
+                if (off + nm.size() + 1 < names_cap) {
+                    memcpy(names_buf + off, nm.c_str(), nm.size() + 1);
+                    off += nm.size() + 1;
+                }
+            }
+        }
+        e->stages->launches += (int64_t)ns * (iters < 1 ? 1 : iters);
+        return ns;
+    });
+}
+
+int b200ocr_l2_flush(b200ocr_engine* e) {
+    return guarded(e, [&]() {
+        std::lock_guard<std::mutex> lk(e->mu);
+        e->stages->l2_flush();
+        return B200OCR_OK;
+    });
+}
+
+void* b200ocr_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void b200ocr_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 int64_t b200ocr_launch_count(const b200ocr_engine* e) { return e && e->stages ? e->stages->launches : 0; }

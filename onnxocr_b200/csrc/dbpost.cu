@@ -1,11 +1,412 @@
-// placeholder until the device DBPostProcess lands
-#include "stages.h"
+// DBPostProcess on the device (onnxocr/db_postprocess.py:220-246, 104-149).
+//
+//   threshold (pred > thresh, float32)                         -> u8 bitmap           [HBM bound]
+//   union-find labelling: fg 8-connected, bg 4-connected       -> roots = raster-first pixel of each component
+//   candidates = fg roots (outer borders) + roots of bg components that do not touch the frame (hole borders),
+//                ordered by descending start pixel == cv2.findContours(RETR_LIST) order, first max_candidates
+//   per candidate: border following, convex hull, rotating calipers, box score, Clipper offset, calipers, scaling
+//                (dbgeom.h — the literal restatement of the cv2 / Clipper arithmetic)
+//
+// Only the final [n_pages][max_candidates] box table crosses PCIe; the filter_tag_det_res tail runs on the host.
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
 #include <stdexcept>
+
+#include "common.cuh"
+#include "dbgeom.h"
+#include "stages.h"
+
 namespace b200ocr {
-struct DbWork { int unused; };
+
+using namespace geom;
+
+struct DbWork {
+    DevBuf bitmap, labels, flags, pos, border, scan_tmp;
+    DevBuf cand, counts, npts, offs, box1, valid, score, res_box;
+    DevBuf keys, ipool, fpool;
+    PinBuf h_counts, h_res;
+};
+
 void db_free(DbWork* w) { delete w; }
-void Stages::db_postprocess_device(const float*, int, int, int, const int*, const int*, const b200ocr_det_params&, int,
-                                   std::vector<int32_t>*, std::vector<double>*, std::vector<int>*) {
-    throw std::runtime_error("unsupported: device DBPostProcess not built yet");
+
+namespace {
+
+constexpr int kHoleBit = 1 << 30;
+constexpr int kUnclipCap = 256;
+
+__global__ void threshold_kernel(const float* __restrict__ prob, uint8_t* __restrict__ bm, int64_t total, float thresh) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        bm[i] = prob[i] > thresh ? 1 : 0;
 }
+
+// cv2.dilate(mask, ones((2, 2))): anchor (1, 1) -> out(y, x) = max over in(y-1..y, x-1..x)
+__global__ void dilate2x2_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int n, int h, int w) {
+    int64_t total = (int64_t)n * h * w;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % w);
+        int y = (int)((i / w) % h);
+        uint8_t v = in[i];
+        if (x > 0) v |= in[i - 1];
+        if (y > 0) v |= in[i - w];
+        if (x > 0 && y > 0) v |= in[i - w - 1];
+        out[i] = v;
+    }
 }
+
+__device__ __forceinline__ int find_root(const int* L, int i) {
+    int p = L[i];
+    while (p != i) {
+        i = p;
+        p = L[i];
+    }
+    return i;
+}
+
+__device__ __forceinline__ void unite(int* L, int a, int b) {
+    for (;;) {
+        a = find_root(L, a);
+        b = find_root(L, b);
+        if (a == b) return;
+        if (a < b) {
+            int old = atomicMin(&L[b], a);
+            if (old == b) return;
+            b = old;
+        } else {
+            int old = atomicMin(&L[a], b);
+            if (old == a) return;
+            a = old;
+        }
+    }
+}
+
+// label initialisation: every pixel points at the first pixel of its horizontal run inside its 32-pixel warp segment
+__global__ void ccl_init_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int64_t total, int w) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool in = i < total;
+    int v = in ? bm[i] : 2;
+    int x = in ? (int)(i % w) : 0;
+    int lane = threadIdx.x & 31;
+    // a run breaks where the class changes or a new image row starts
+    int left = __shfl_up_sync(0xffffffffu, v, 1);
+    bool brk = lane == 0 || left != v || x == 0;
+    unsigned m = __ballot_sync(0xffffffffu, brk);
+    unsigned upto = m & (0xffffffffu >> (31 - lane));
+    int start_lane = 31 - __clz(upto);
+    if (in) L[i] = (int)(i - (lane - start_lane));
+}
+
+__global__ void ccl_merge_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int n, int h, int w) {
+    int64_t total = (int64_t)n * h * w;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % w);
+        int y = (int)((i / w) % h);
+        int v = bm[i];
+        bool hasN = y > 0, hasW = x > 0, hasE = x + 1 < w;
+        bool N = hasN && bm[i - w] == v;
+        bool W = hasW && bm[i - 1] == v;
+        if (v) {                                  // foreground: 8-connectivity
+            bool NW = hasN && hasW && bm[i - w - 1];
+            bool NE = hasN && hasE && bm[i - w + 1];
+            if (N) {
+                unite(L, (int)i, (int)(i - w));
+            } else {
+                if (NW) unite(L, (int)i, (int)(i - w - 1));
+                if (NE) unite(L, (int)i, (int)(i - w + 1));
+            }
+            // ccl_init_kernel already joined W inside a 32-pixel segment; join across segment boundaries here
+            if (W && (i & 31) == 0) unite(L, (int)i, (int)(i - 1));
+        } else {                                  // background: 4-connectivity
+            if (N) unite(L, (int)i, (int)(i - w));
+            if (W && (i & 31) == 0) unite(L, (int)i, (int)(i - 1));
+        }
+    }
+}
+
+__global__ void ccl_flatten_kernel(int* __restrict__ L, int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        L[i] = find_root(L, (int)i);
+}
+
+// background components touching the image frame are not holes
+__global__ void border_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ L, uint8_t* __restrict__ border, int n,
+                              int h, int w) {
+    int per = 2 * (h + w);
+    int64_t total = (int64_t)n * per;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int p = (int)(t / per), k = (int)(t % per);
+        int x, y;
+        if (k < w) { x = k; y = 0; }
+        else if (k < 2 * w) { x = k - w; y = h - 1; }
+        else if (k < 2 * w + h) { x = 0; y = k - 2 * w; }
+        else { x = w - 1; y = k - 2 * w - h; }
+        int64_t i = ((int64_t)p * h + y) * w + x;
+        if (!bm[i]) border[L[i]] = 1;
+    }
+}
+
+__global__ void cand_flag_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ L, const uint8_t* __restrict__ border,
+                                 int* __restrict__ flags, int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        flags[i] = (L[i] == (int)i && (bm[i] || !border[i])) ? 1 : 0;
+}
+
+// cand[p][r]: r-th contour of page p in cv2 order (descending start pixel); counts[p] = min(total, maxc)
+__global__ void compact_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ flags, const int* __restrict__ pos,
+                               int* __restrict__ cand, int* __restrict__ counts, int n, int hw, int maxc) {
+    int64_t total = (int64_t)n * hw;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int p = (int)(i / hw);
+        int64_t first = (int64_t)p * hw, last = first + hw - 1;
+        int page_total = pos[last] + flags[last] - pos[first];
+        if (i == first) counts[p] = page_total < maxc ? page_total : maxc;
+        if (!flags[i]) continue;
+        int r = page_total - 1 - (pos[i] - pos[first]);
+        if (r >= maxc) continue;
+        int local = (int)(i - first);
+        cand[(int64_t)p * maxc + r] = bm[i] ? local : ((local - 1) | kHoleBit);
+    }
+}
+
+__global__ void trace_count_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ cand, const int* __restrict__ counts,
+                                   int* __restrict__ npts, int n, int h, int w, int maxc) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * maxc) return;
+    int p = t / maxc, r = t % maxc;
+    int cnt = 0;
+    if (r < counts[p]) {
+        int c = cand[t];
+        int local = c & (kHoleBit - 1);
+        Bitmap img{bm + (size_t)p * h * w, h, w};
+        cnt = trace_contour(img, local % w, local / w, (c & kHoleBit) != 0, nullptr, 0);
+    }
+    npts[t] = cnt;
+}
+
+// phase A: contour -> minAreaRect -> get_mini_boxes
+__global__ void contour_box_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ cand, const int* __restrict__ counts,
+                                   const int* __restrict__ npts, const int* __restrict__ offs, uint64_t* __restrict__ keys,
+                                   int* __restrict__ ipool, float* __restrict__ fpool, float* __restrict__ box1,
+                                   uint8_t* __restrict__ valid, int n, int h, int w, int maxc, float min_size) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * maxc) return;
+    int p = t / maxc, r = t % maxc;
+    valid[t] = 0;
+    if (r >= counts[p]) return;
+    int np = npts[t];
+    int64_t off = offs[t];
+    uint64_t* k = keys + off;
+    int* stack = ipool + 2 * off + 2 * (int64_t)t;
+    int* hull = stack + np + 2;
+    PtF* hp = (PtF*)(fpool + 5 * off);
+    PtF* vect = hp + np;
+    float* inv = (float*)(vect + np);
+    int c = cand[t];
+    int local = c & (kHoleBit - 1);
+    Bitmap img{bm + (size_t)p * h * w, h, w};
+    trace_contour(img, local % w, local / w, (c & kHoleBit) != 0, k, np);
+    RotRect rr = min_area_rect_keys(k, np, stack, hull, hp, vect, inv);
+    PtF box[4];
+    float sside = mini_box(rr, box);
+    if (sside < min_size) return;                     // db_postprocess.py:127
+    for (int i = 0; i < 4; ++i) {
+        box1[(size_t)t * 8 + 2 * i] = box[i].x;
+        box1[(size_t)t * 8 + 2 * i + 1] = box[i].y;
+    }
+    valid[t] = 1;
+}
+
+// phase B: box_score_fast, one block per candidate (rows of the bounding box are spread over the threads;
+// partial sums are combined in a fixed order, so the result is deterministic)
+__global__ void __launch_bounds__(128) score_kernel(const float* __restrict__ prob, const float* __restrict__ box1,
+                                                     uint8_t* __restrict__ valid, double* __restrict__ score, int h, int w,
+                                                     int maxc, double box_thresh) {
+    int t = blockIdx.x;
+    if (!valid[t]) return;
+    int p = t / maxc;
+    const float* pred = prob + (size_t)p * h * w;
+    PtF box[4];
+    for (int i = 0; i < 4; ++i) {
+        box[i].x = box1[(size_t)t * 8 + 2 * i];
+        box[i].y = box1[(size_t)t * 8 + 2 * i + 1];
+    }
+    float fxmin = box[0].x, fxmax = box[0].x, fymin = box[0].y, fymax = box[0].y;
+    for (int i = 1; i < 4; ++i) {
+        fxmin = fminf(fxmin, box[i].x); fxmax = fmaxf(fxmax, box[i].x);
+        fymin = fminf(fymin, box[i].y); fymax = fmaxf(fymax, box[i].y);
+    }
+    int xmin = min(max((int)floorf(fxmin), 0), w - 1), xmax = min(max((int)ceilf(fxmax), 0), w - 1);
+    int ymin = min(max((int)floorf(fymin), 0), h - 1), ymax = min(max((int)ceilf(fymax), 0), h - 1);
+    int qx[4], qy[4];
+    for (int i = 0; i < 4; ++i) {
+        qx[i] = (int)(box[i].x - (float)xmin);
+        qy[i] = (int)(box[i].y - (float)ymin);
+    }
+    FillPoly4 fp;
+    fp.init(qx, qy, xmax - xmin + 1, ymax - ymin + 1);
+    double sum = 0;
+    long long cnt = 0;
+    int bw = xmax - xmin + 1, bh = ymax - ymin + 1;
+    // thread -> (row, column stripe): keeps a warp on one row when the box is wide
+    for (int y = threadIdx.x / 32; y < bh; y += blockDim.x / 32) {
+        fp.set_row(y);
+        for (int x = threadIdx.x % 32; x < bw; x += 32)
+            if (fp.test(x, y)) {
+                sum += (double)pred[(size_t)(y + ymin) * w + x + xmin];
+                ++cnt;
+            }
+    }
+    __shared__ double ssum[128];
+    __shared__ long long scnt[128];
+    ssum[threadIdx.x] = sum;
+    scnt[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int s = 64; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            ssum[threadIdx.x] += ssum[threadIdx.x + s];
+            scnt[threadIdx.x] += scnt[threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double sc = scnt[0] ? ssum[0] / (double)scnt[0] : 0.0;
+        score[t] = sc;
+        if (box_thresh > sc) valid[t] = 0;            // db_postprocess.py:134
+    }
+}
+
+// phase C: unclip -> minAreaRect -> get_mini_boxes -> scale/round/clip
+__global__ void unclip_kernel(const float* __restrict__ box1, uint8_t* __restrict__ valid, int* __restrict__ res_box,
+                              const int* __restrict__ src_hw, int n, int h, int w, int maxc, double unclip_ratio, float min_size2) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * maxc || !valid[t]) return;
+    int p = t / maxc;
+    PtF box[4];
+    for (int i = 0; i < 4; ++i) {
+        box[i].x = box1[(size_t)t * 8 + 2 * i];
+        box[i].y = box1[(size_t)t * 8 + 2 * i + 1];
+    }
+    int ox[kUnclipCap], oy[kUnclipCap];
+    int m = unclip_offset(box, unclip_ratio, ox, oy, kUnclipCap, nullptr);
+    if (m <= 0 || m > kUnclipCap) { valid[t] = 0; return; }
+    uint64_t k2[kUnclipCap];
+    int stack[kUnclipCap + 2], hull[kUnclipCap];
+    PtF hp[kUnclipCap], vect[kUnclipCap];
+    float inv[kUnclipCap];
+    for (int i = 0; i < m; ++i) k2[i] = pack_key(ox[i], oy[i], i);
+    RotRect rr = min_area_rect_keys(k2, m, stack, hull, hp, vect, inv);
+    PtF b2[4];
+    float sside = mini_box(rr, b2);
+    if (sside < min_size2) { valid[t] = 0; return; }  // db_postprocess.py:139
+    double dest_h = (double)src_hw[2 * p], dest_w = (double)src_hw[2 * p + 1];
+    for (int i = 0; i < 4; ++i) {
+        res_box[(size_t)t * 8 + 2 * i] = scale_coord(b2[i].x, w, dest_w);
+        res_box[(size_t)t * 8 + 2 * i + 1] = scale_coord(b2[i].y, h, dest_h);
+    }
+}
+
+int grid_for(int64_t total, int block = 256) {
+    int64_t g = (total + block - 1) / block;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, 148 * 16));
+}
+
+}  // namespace
+
+void Stages::db_postprocess_device(const float* d_prob, int n, int h, int w, const int* src_hs, const int* src_ws,
+                                   const b200ocr_det_params& p, int capacity, std::vector<int32_t>* boxes,
+                                   std::vector<double>* scores, std::vector<int>* counts_out) {
+    if (!db_) db_ = new DbWork();
+    DbWork& W = *db_;
+    if ((int64_t)n * h * w >= (int64_t)1 << 30) throw std::runtime_error("bad argument: probability-map batch too large for 30-bit pixel indices");
+    if (h >= 60000 || w >= 60000) throw std::runtime_error("bad argument: probability map too large");
+    const int64_t total = (int64_t)n * h * w;
+    const int hw = h * w;
+    const int maxc = std::max(1, std::min(capacity, p.max_candidates));
+    cudaStream_t st = st_;
+    uint8_t* bm = (uint8_t*)W.bitmap.get((size_t)total * (p.use_dilation ? 2 : 1));
+    int* L = (int*)W.labels.get((size_t)total * sizeof(int));
+    int* flags = (int*)W.flags.get((size_t)total * sizeof(int));
+    int* pos = (int*)W.pos.get((size_t)total * sizeof(int));
+    uint8_t* border = (uint8_t*)W.border.get((size_t)total);
+    threshold_kernel<<<grid_for(total), 256, 0, st>>>(d_prob, bm, total, p.thresh);
+    if (p.use_dilation) {
+        dilate2x2_kernel<<<grid_for(total), 256, 0, st>>>(bm, bm + total, n, h, w);
+        bm += total;
+        launches += 1;
+    }
+    ccl_init_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(bm, L, total, w);
+    ccl_merge_kernel<<<grid_for(total), 256, 0, st>>>(bm, L, n, h, w);
+    ccl_flatten_kernel<<<grid_for(total), 256, 0, st>>>(L, total);
+    B200_CUDA_CHECK(cudaMemsetAsync(border, 0, (size_t)total, st));
+    border_kernel<<<grid_for((int64_t)n * 2 * (h + w)), 256, 0, st>>>(bm, L, border, n, h, w);
+    cand_flag_kernel<<<grid_for(total), 256, 0, st>>>(bm, L, border, flags, total);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flags, pos, (int)total, st);
+    void* tmp = W.scan_tmp.get(tmp_bytes + 256);
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flags, pos, (int)total, st);
+    const int nt = n * maxc;
+    int* cand = (int*)W.cand.get((size_t)nt * sizeof(int));
+    int* counts = (int*)W.counts.get((size_t)(n + 2 * n + 1) * sizeof(int));
+    int* d_src = counts + n;
+    int* npts = (int*)W.npts.get((size_t)(nt + 1) * sizeof(int));
+    int* offs = (int*)W.offs.get((size_t)(nt + 1) * sizeof(int));
+    compact_kernel<<<grid_for(total), 256, 0, st>>>(bm, flags, pos, cand, counts, n, hw, maxc);
+    trace_count_kernel<<<(unsigned)ceil_div(nt, 64), 64, 0, st>>>(bm, cand, counts, npts, n, h, w, maxc);
+    B200_CUDA_CHECK(cudaMemsetAsync(npts + nt, 0, sizeof(int), st));
+    size_t tmp2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, npts, offs, nt + 1, st);
+    tmp = W.scan_tmp.get(std::max(tmp_bytes, tmp2) + 256);
+    cub::DeviceScan::ExclusiveSum(tmp, tmp2, npts, offs, nt + 1, st);
+    int* h_counts = (int*)W.h_counts.get((size_t)(n + 1) * sizeof(int) + 2 * n * sizeof(int));
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_counts, counts, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_counts + n, offs + nt, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int* h_src = h_counts + n + 1;
+    for (int i = 0; i < n; ++i) {
+        h_src[2 * i] = src_hs[i];
+        h_src[2 * i + 1] = src_ws[i];
+    }
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_src, h_src, 2 * n * sizeof(int), cudaMemcpyHostToDevice, st));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    launches += 10;
+    int64_t total_pts = h_counts[n];
+    if (total_pts >= (1 << 20) * (int64_t)64) throw std::runtime_error("bad argument: contour point pool overflow");
+    uint64_t* keys = (uint64_t*)W.keys.get((size_t)(total_pts + 1) * sizeof(uint64_t));
+    int* ipool = (int*)W.ipool.get((size_t)(2 * total_pts + 2 * (int64_t)nt + 2) * sizeof(int));
+    float* fpool = (float*)W.fpool.get((size_t)(5 * total_pts + 5) * sizeof(float));
+    float* box1 = (float*)W.box1.get((size_t)nt * 8 * sizeof(float));
+    uint8_t* valid = (uint8_t*)W.valid.get((size_t)nt);
+    double* score = (double*)W.score.get((size_t)nt * sizeof(double));
+    int* res_box = (int*)W.res_box.get((size_t)nt * 8 * sizeof(int));
+    contour_box_kernel<<<(unsigned)ceil_div(nt, 64), 64, 0, st>>>(bm, cand, counts, npts, offs, keys, ipool, fpool, box1, valid,
+                                                                   n, h, w, maxc, (float)p.min_size);
+    score_kernel<<<nt, 128, 0, st>>>(d_prob, box1, valid, score, h, w, maxc, p.box_thresh);
+    unclip_kernel<<<(unsigned)ceil_div(nt, 32), 32, 0, st>>>(box1, valid, res_box, d_src, n, h, w, maxc, p.unclip_ratio,
+                                                              (float)(p.min_size + 2));
+    launches += 3;
+    B200_CUDA_CHECK(cudaGetLastError());
+    // results -> host
+    size_t res_bytes = (size_t)nt * (8 * sizeof(int) + sizeof(double) + 1);
+    char* h_res = (char*)W.h_res.get(res_bytes + 64);
+    int* hb = (int*)h_res;
+    double* hs = (double*)(h_res + (size_t)nt * 8 * sizeof(int));
+    uint8_t* hv = (uint8_t*)(h_res + (size_t)nt * (8 * sizeof(int) + sizeof(double)));
+    B200_CUDA_CHECK(cudaMemcpyAsync(hb, res_box, (size_t)nt * 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(hs, score, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(hv, valid, (size_t)nt, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    boxes->clear();
+    scores->clear();
+    counts_out->assign(n, 0);
+    for (int pg = 0; pg < n; ++pg) {
+        int c = h_counts[pg];
+        for (int r = 0; r < c; ++r) {
+            size_t t = (size_t)pg * maxc + r;
+            if (!hv[t]) continue;
+            boxes->insert(boxes->end(), hb + t * 8, hb + t * 8 + 8);
+            scores->push_back(hs[t]);
+            (*counts_out)[pg]++;
+        }
+    }
+}
+
+}  // namespace b200ocr

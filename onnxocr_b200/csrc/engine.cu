@@ -269,10 +269,16 @@ void Model::build_steps(Plan& p) {
         return it->second;
     };
     Plan* pp = &p;
+    double cost_flops = 0, cost_bytes = 0;      // set by a handler right before its emit()
+    const double esz = (double)sizeof(T);
     auto emit = [&](const std::string& name, std::function<void(cudaStream_t)> fn) {
         p.steps.push_back(std::move(fn));
         p.step_names.push_back(name);
+        p.step_flops.push_back(cost_flops);
+        p.step_bytes.push_back(cost_bytes);
+        cost_flops = cost_bytes = 0;
     };
+    auto vbytes = [&](int v) { return (double)p.vals[v].n * p.vals[v].h * p.vals[v].w * p.vals[v].c * esz; };
     // materialise a virtual upsample
     auto materialize = [&](int v) -> int {
         if (p.vals[v].up_src < 0) return v;
@@ -368,6 +374,8 @@ void Model::build_steps(Plan& p) {
                 cp.M = iv.n * Ho * Wo;
                 cp.epi = c.epi;
                 p.flops += 2.0 * cp.M * (double)c.cout * c.cin * (convt ? 4 : c.kh * c.kw);
+                cost_flops = 2.0 * cp.M * (double)c.cout * c.cin * (convt ? 4 : c.kh * c.kw);
+                cost_bytes = vbytes(in) + vbytes(out) + (double)c.cout * c.cin * (convt ? 4 : c.kh * c.kw) * esz;
                 const float* wptr = dw.w;
                 const float* bptr = dw.bias;
                 int cols = cp.Cols;
@@ -404,6 +412,8 @@ void Model::build_steps(Plan& p) {
                 const float* wptr = dw_[c.weight_id].w;
                 const float* bptr = dw_[c.weight_id].bias;
                 int64_t total = (int64_t)iv.n * Ho * Wo * (iv.cp / 4);
+                cost_flops = 2.0 * iv.n * Ho * Wo * (double)c.cout * c.kh * c.kw;
+                cost_bytes = vbytes(in) + vbytes(out);
                 emit("dwconv " + c.name, [=](cudaStream_t st) {
                     dwconv_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)pp->ptr(in), wptr, bptr, (T*)pp->ptr(out), dp);
                 });
@@ -423,6 +433,7 @@ void Model::build_steps(Plan& p) {
                 size_t smem = (size_t)rows * iv.cp * sizeof(float);
                 int N = iv.n, CP = iv.cp, C = iv.c;
                 use(in);
+                cost_bytes = vbytes(in);
                 emit("gap_partial " + c.name, [=](cudaStream_t st) {
                     gap_partial_kernel<T><<<dim3(chunks, N), 256, smem, st>>>((const T*)pp->ptr(in), (float*)pp->bufptr(partial),
                                                                                 HW, CP, chunks);
@@ -460,6 +471,7 @@ void Model::build_steps(Plan& p) {
                                                          w1.bias, w2.w, w2.ColsW, w2.bias, alpha, beta, (float*)pp->bufptr(scale));
                 });
                 int64_t total4 = (int64_t)iv.n * HW * (iv.cp / 4);
+                cost_bytes = vbytes(in) + vbytes(out);
                 emit("se_apply " + c.name, [=](cudaStream_t st) {
                     se_apply_kernel<T><<<grid_for(total4), 256, 0, st>>>((const T*)pp->ptr(in), (const float*)pp->bufptr(scale),
                                                                           (T*)pp->ptr(out), HW, CP, C, total4, residual, epi);
@@ -487,6 +499,7 @@ void Model::build_steps(Plan& p) {
                 int out = new_val(F_NCHW, iv.n, pl.Ho, pl.Wo, iv.c);
                 use(in);
                 int64_t total = (int64_t)iv.n * pl.Ho * pl.Wo * iv.cp;
+                cost_bytes = vbytes(in) + vbytes(out);
                 emit("pool " + c.name, [=](cudaStream_t st) {
                     pool_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)pp->ptr(in), (T*)pp->ptr(out), pl);
                 });
@@ -533,6 +546,7 @@ void Model::build_steps(Plan& p) {
                     int src = pv.up_src >= 0 ? pv.up_src : v;
                     use(v);
                     int N = pv.n, H = pv.h, W = pv.w, Cs = pv.c, CsP = pv.cp, fh = pv.fh, fw = pv.fw, coff = off;
+                    cost_bytes = vbytes(src) + (double)N * H * W * Cs * esz;
                     emit("concat " + c.name, [=](cudaStream_t st) {
                         concat_slice_kernel<T><<<grid_for((int64_t)N * H * W * Cs), 256, 0, st>>>(
                             (const T*)pp->ptr(src), (T*)pp->ptr(out), N, H, W, Cs, CsP, cdp, coff, fh, fw);
@@ -577,6 +591,7 @@ void Model::build_steps(Plan& p) {
                     });
                 } else {
                     int64_t tot = (int64_t)av.n * av.h * av.w * (av.cp / 4);
+                    cost_bytes = vbytes(a) + vbytes(bsrc) + vbytes(out);
                     emit("eltwise " + c.name, [=](cudaStream_t st) {
                         eltwise_kernel<T><<<grid_for(tot), 256, 0, st>>>((const T*)pp->ptr(a), (const T*)pp->ptr(bsrc),
                                                                           (T*)pp->ptr(out), ep);
@@ -597,6 +612,7 @@ void Model::build_steps(Plan& p) {
                 int64_t tot = iv.elems();
                 int CP = iv.cp, C = iv.c;
                 Epilogue epi = c.epi;
+                cost_bytes = vbytes(in) + vbytes(out);
                 emit("unary " + c.name, [=](cudaStream_t st) {
                     unary_kernel<T><<<grid_for(tot), 256, 0, st>>>((const T*)pp->ptr(in), (T*)pp->ptr(out), tot, CP, C, vec, vop, epi);
                 });
@@ -616,6 +632,7 @@ void Model::build_steps(Plan& p) {
                 float eps = c.eps;
                 const float* ga = dvec_[c.ln_id].first;
                 const float* be = dvec_[c.ln_id].second;
+                cost_bytes = vbytes(in) + vbytes(out);
                 emit("layernorm " + c.name, [=](cudaStream_t st) {
                     layernorm_kernel<T><<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>((const T*)pp->ptr(in), (T*)pp->ptr(out),
                                                                                              ga, be, rows, C, CP, eps);
@@ -636,6 +653,8 @@ void Model::build_steps(Plan& p) {
                 float scale = c.scale;
                 int qblocks = std::max(1, std::min(8, (Tn + 63) / 64));
                 p.flops += 4.0 * B * heads * (double)Tn * Tn * hd;
+                cost_flops = 4.0 * B * heads * (double)Tn * Tn * hd;
+                cost_bytes = vbytes(in) + vbytes(out);
                 emit("attention " + c.name, [=](cudaStream_t st) {
                     const T* q = (const T*)pp->ptr(in);
                     T* o = (T*)pp->ptr(out);
@@ -821,6 +840,30 @@ void Model::build_steps(Plan& p) {
 
 void Plan::launch(cudaStream_t st) {
     for (auto& s : steps) s(st);
+}
+
+void Model::profile(int n, int h, int w, int iters, cudaStream_t st, std::vector<float>* ms) {
+    std::lock_guard<std::mutex> lk(mu_);
+    Plan* p = plan_for(n, h, w);
+    size_t ns = p->steps.size();
+    std::vector<cudaEvent_t> ev(ns + 1);
+    for (auto& e : ev) B200_CUDA_CHECK(cudaEventCreate(&e));
+    ms->assign(ns, 0.f);
+    for (int it = 0; it < iters; ++it) {
+        B200_CUDA_CHECK(cudaEventRecord(ev[0], st));
+        for (size_t i = 0; i < ns; ++i) {
+            p->steps[i](st);
+            B200_CUDA_CHECK(cudaEventRecord(ev[i + 1], st));
+        }
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < ns; ++i) {
+            float t = 0;
+            cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+            (*ms)[i] += t / iters;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    B200_CUDA_CHECK(cudaGetLastError());
 }
 
 void Model::run_host(const float* nchw, int n, int c, int h, int w, std::vector<int64_t>* out_shape, float* out,

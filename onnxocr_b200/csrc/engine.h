@@ -51,6 +51,7 @@ struct Plan {
     char** model_arena = nullptr;  // the owning Model's activation slab (shared by all of its plans)
     std::vector<std::function<void(cudaStream_t)>> steps;
     std::vector<std::string> step_names;
+    std::vector<double> step_flops, step_bytes;   // algorithmic work per launch (unique in+out+weight bytes)
     int in_val = -1, out_val = -1;
     float* out_dense = nullptr;    // dense fp32 logical output (device)
     size_t out_dense_elems = 0;
@@ -79,6 +80,8 @@ public:
     void run_host(const float* nchw, int n, int c, int h, int w, std::vector<int64_t>* out_shape,
                   float* out, size_t out_capacity, cudaStream_t st);
     Plan* plan_for(int n, int h, int w);
+    // Per-step device time (ms, averaged over iters) measured with CUDA events between launches.
+    void profile(int n, int h, int w, int iters, cudaStream_t st, std::vector<float>* ms);
     size_t elem_size() const { return prec_ == PREC_BF16 ? 2 : 4; }
     int precision() const { return prec_; }
     const CGraph& graph() const { return *g_; }

@@ -597,6 +597,13 @@ void Stages::db_postprocess_host(const float* prob, int h, int w, int src_h, int
     *n_boxes = n;
 }
 
+void Stages::l2_flush() {
+    const size_t bytes = (size_t)256 << 20;      // > 126 MB L2
+    void* p = d_flush_.get(bytes);
+    B200_CUDA_CHECK(cudaMemsetAsync(p, 0x5a, bytes, st_));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st_));
+}
+
 void Stages::resident_upload(const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n) {
     res_off_.assign(n, 0);
     res_h_.assign(hs, hs + n);

@@ -58,6 +58,8 @@ public:
     void resident_run(Model* det, const b200ocr_det_params& p, int iters, float* ms_total, int* n_boxes_total,
                       float* net_ms_total);
 
+    void l2_flush();
+
     int64_t launches = 0;
     float stage_ms[4] = {0, 0, 0, 0};
 
@@ -72,7 +74,7 @@ private:
     PinBuf h_pin_, h_pin2_;
     DbWork* db_ = nullptr;
     // resident pages
-    DevBuf d_res_;
+    DevBuf d_res_, d_flush_;
     std::vector<size_t> res_off_;
     std::vector<int> res_h_, res_w_, res_stride_;
 };

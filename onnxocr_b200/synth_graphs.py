@@ -357,7 +357,10 @@ def ensure_models(asset_dir=None):
     out = {}
     for kind, fn in (("det", build_det), ("rec", build_rec)):
         p = os.path.join(asset_dir, "ppocrv5_%s_synth.onnx" % kind)
-        if not os.path.exists(p):
+        deps = [os.path.join(_HERE, "synth_gains.json"), os.path.join(ASSET_DIR, "%s_synth_weights.npz" % kind),
+                os.path.abspath(__file__)]
+        stale = os.path.exists(p) and any(os.path.exists(d) and os.path.getmtime(d) > os.path.getmtime(p) for d in deps)
+        if stale or not os.path.exists(p):
             blob, _ = fn()
             tmp = p + ".tmp%d" % os.getpid()
             with open(tmp, "wb") as fh:

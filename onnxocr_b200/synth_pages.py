@@ -29,46 +29,52 @@ def _sentence(rng, n_chars):
     return " ".join(out)[:n_chars].strip() or "text"
 
 
-def render_page(h, w, n_lines, seed, rot180_frac=0.0, font_path=None, min_px=20, max_px=32):
-    """White page (BGR u8, [h,w,3]) with `n_lines` dark text lines; returns (img, line_boxes)."""
+def render_page(h, w, n_lines, seed, rot180_frac=0.0, font_path=None, min_px=20, max_px=32, columns=1):
+    """White page (BGR u8, [h,w,3]) with up to `n_lines` dark text lines in `columns` columns; returns (img, line_boxes)."""
     rng = np.random.default_rng(seed)
     page = Image.new("RGB", (w, h), (255, 255, 255))
     draw = ImageDraw.Draw(page)
     margin = max(8, w // 40)
-    y = margin
     boxes = []
-    gap_budget = max(0, h - 2 * margin - n_lines * (max_px + min_px) // 2)
-    for i in range(n_lines):
-        px = int(rng.integers(min_px, max_px + 1))
-        if y + px + 4 >= h - margin:
-            break
-        font = _font(px, font_path)
-        n_chars = int(rng.integers(12, max(13, int((w - 2 * margin) / (0.55 * px)))))
-        text = _sentence(rng, n_chars)
-        x = margin + int(rng.integers(0, max(1, w // 10)))
-        shade = int(rng.integers(0, 80))
-        bbox = draw.textbbox((x, y), text, font=font)
-        if bbox[2] > w - margin:
-            # truncate to fit
-            keep = max(4, int(len(text) * (w - margin - x) / max(1, bbox[2] - x)) - 1)
-            text = text[:keep]
+    per_col = (n_lines + columns - 1) // columns
+    col_w = (w - margin) // columns
+    gap_budget = max(0, h - 2 * margin - per_col * ((max_px + min_px) // 2 + 4))
+    for col in range(columns):
+        x0 = margin + col * col_w
+        x1 = x0 + col_w - margin
+        y = margin
+        for i in range(per_col):
+            if len(boxes) >= n_lines:
+                break
+            px = int(rng.integers(min_px, max_px + 1))
+            if y + px + 4 >= h - margin:
+                break
+            font = _font(px, font_path)
+            n_chars = int(rng.integers(8, max(9, int((x1 - x0) / (0.55 * px)))))
+            text = _sentence(rng, n_chars)
+            x = x0 + int(rng.integers(0, max(1, col_w // 10)))
+            shade = int(rng.integers(0, 80))
             bbox = draw.textbbox((x, y), text, font=font)
-        if rot180_frac > 0 and rng.random() < rot180_frac:
-            tw, th = bbox[2] - bbox[0] + 4, bbox[3] - bbox[1] + 4
-            tile = Image.new("RGB", (tw, th), (255, 255, 255))
-            ImageDraw.Draw(tile).text((2 - (bbox[0] - x), 2 - (bbox[1] - y)), text, font=font, fill=(shade,) * 3)
-            page.paste(tile.rotate(180), (bbox[0] - 2, bbox[1] - 2))
-        else:
-            draw.text((x, y), text, font=font, fill=(shade, shade, shade))
-        boxes.append(bbox)
-        y = bbox[3] + 4 + int(rng.integers(0, max(1, 2 * gap_budget // max(1, n_lines) + 1)))
+            if bbox[2] > x1:
+                keep = max(3, int(len(text) * (x1 - x) / max(1, bbox[2] - x)) - 1)
+                text = text[:keep].strip() or "ab"
+                bbox = draw.textbbox((x, y), text, font=font)
+            if rot180_frac > 0 and rng.random() < rot180_frac:
+                tw, th = bbox[2] - bbox[0] + 4, bbox[3] - bbox[1] + 4
+                tile = Image.new("RGB", (tw, th), (255, 255, 255))
+                ImageDraw.Draw(tile).text((2 - (bbox[0] - x), 2 - (bbox[1] - y)), text, font=font, fill=(shade,) * 3)
+                page.paste(tile.rotate(180), (bbox[0] - 2, bbox[1] - 2))
+            else:
+                draw.text((x, y), text, font=font, fill=(shade, shade, shade))
+            boxes.append(bbox)
+            y = bbox[3] + 4 + int(rng.integers(0, max(1, 2 * gap_budget // max(1, per_col) + 1)))
     img = np.ascontiguousarray(np.array(page)[:, :, ::-1])
     return img, boxes
 
 
 def det_pages_c2(n=16, side=960, lines=40, seed=0, font_path=None):
     """C2: `n` pages of side×side×3 u8 BGR, `lines` text lines each."""
-    return [render_page(side, side, lines, seed * 1000 + i, font_path=font_path)[0] for i in range(n)]
+    return [render_page(side, side, lines, seed * 1000 + i, font_path=font_path, columns=2)[0] for i in range(n)]
 
 
 def rec_crops_c3(n=256, seed=1, h=48, w=320, font_path=None):
