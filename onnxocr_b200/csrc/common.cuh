@@ -54,20 +54,29 @@ template <> struct ST<bf16> {
     }
 };
 
+__device__ __forceinline__ float epi_act(float v, int type, float a, float b) {
+    switch (type) {
+        case EPI_RELU: return fmaxf(v, 0.f);
+        case EPI_HSWISH: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * 0.16666667f;
+        case EPI_SIGMOID: return 1.f / (1.f + expf(-v));
+        case EPI_SWISH: return v / (1.f + expf(-v));
+        case EPI_HSIGMOID: return fminf(fmaxf(fmaf(v, a, b), 0.f), 1.f);
+        case EPI_CLIP: return fminf(fmaxf(v, a), b);
+        default: return v;
+    }
+}
+
 __device__ __forceinline__ float epi_apply(float v, const Epilogue& e) {
+    if (e.n == 0) return v;
+    if (e.fast) {
+        v = fmaf(v, e.a0, e.b0);
+        v = epi_act(v, e.act, e.pa, e.pb);
+        return fmaf(v, e.a1, e.b1);
+    }
 #pragma unroll 1
     for (int i = 0; i < e.n; ++i) {
         const EpiStep s = e.s[i];
-        switch (s.type) {
-            case EPI_AFFINE: v = fmaf(v, s.a, s.b); break;
-            case EPI_RELU: v = fmaxf(v, 0.f); break;
-            case EPI_HSWISH: v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) / 6.f; break;
-            case EPI_SIGMOID: v = 1.f / (1.f + expf(-v)); break;
-            case EPI_SWISH: v = v * (1.f / (1.f + expf(-v))); break;
-            case EPI_HSIGMOID: v = fminf(fmaxf(fmaf(v, s.a, s.b), 0.f), 1.f); break;
-            case EPI_CLIP: v = fminf(fmaxf(v, s.a), s.b); break;
-            default: break;
-        }
+        v = s.type == EPI_AFFINE ? fmaf(v, s.a, s.b) : epi_act(v, s.type, s.a, s.b);
     }
     return v;
 }

@@ -1,10 +1,13 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
+#include <type_traits>
 
 #include "net_kernels.cuh"
+#include "tc_conv.cuh"
 
 namespace b200ocr {
 
@@ -38,6 +41,54 @@ static float* upload(const std::vector<float>& v) {
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+// ------------------------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        B200_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) throw std::runtime_error("CUDA error: cuTensorMapEncodeTiled not available");
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// bf16 tensor map, 128-byte swizzle, zero fill out of bounds.  dims/box innermost first; strides in bytes for dims 1..rank-1.
+static void make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+    cuuint64_t gd[4], gs[3];
+    cuuint32_t bx[4], es[4];
+    for (int i = 0; i < rank; ++i) {
+        gd[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i) gs[i - 1] = strides_bytes[i - 1];
+    }
+    CUresult r = encode_tiled_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("CUDA error: cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+}
+
+static bool tc_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200OCR_NO_TC");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+struct TcState {            // per conv step: tensor maps, re-encoded when the activation slab moves
+    CUtensorMap map_a, map_b;
+    const void* a_ptr = nullptr;
+};
+
 // ------------------------------------------------------------------------------------ load
 Model::Model(const std::string& path, int precision) : prec_(precision) {
     OnnxModel m = load_onnx(path);
@@ -64,6 +115,26 @@ Model::Model(const std::string& path, int precision) : prec_(precision) {
         for (int co = 0; co < cw.cout; ++co) bias[co] = cw.bias[co];
         d.w = upload(w);
         d.bias = upload(bias);
+        if (!convt && prec_ == PREC_BF16 && cinp % 8 == 0) {
+            // tcgen05 operand pack: bf16 [rows = round_up(CoutP, BN)][K = taps * kchunks * 64], K-major, zero padded
+            int bn = coutp <= 32 ? 32 : (coutp <= 64 ? 64 : 128);
+            int kchunks = (cinp + 63) / 64;
+            int rows = round_up(coutp, bn);
+            size_t K = (size_t)taps * kchunks * 64;
+            std::vector<bf16> wb((size_t)rows * K, __float2bfloat16(0.f));
+            for (int t = 0; t < taps; ++t)
+                for (int ci = 0; ci < cw.cin; ++ci)
+                    for (int co = 0; co < cw.cout; ++co)
+                        wb[(size_t)co * K + (size_t)t * kchunks * 64 + ci] = __float2bfloat16(cw.w[((size_t)t * cw.cin + ci) * cw.cout + co]);
+            B200_CUDA_CHECK(cudaMalloc(&d.w_bf16, wb.size() * sizeof(bf16)));
+            B200_CUDA_CHECK(cudaMemcpy(d.w_bf16, wb.data(), wb.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+            std::vector<float> tb(rows + 128, 0.f);
+            for (int co = 0; co < cw.cout; ++co) tb[co] = cw.bias[co];
+            d.tc_bias = upload(tb);
+            d.tc_bn = bn;
+            d.tc_rows = rows;
+            d.tc_k = (int)K;
+        }
     };
     for (auto& c : g_->nodes) {
         if (c.kind == C_CONV) pack_dense(c.weight_id, false);
@@ -98,6 +169,7 @@ Model::~Model() {
         if (d.w) cudaFree(d.w);
         if (d.bias) cudaFree(d.bias);
         if (d.w_bf16) cudaFree(d.w_bf16);
+        if (d.tc_bias) cudaFree(d.tc_bias);
     }
     for (auto& v : dvec_) {
         cudaFree(v.first);
@@ -379,6 +451,75 @@ void Model::build_steps(Plan& p) {
                 const float* wptr = dw.w;
                 const float* bptr = dw.bias;
                 int cols = cp.Cols;
+                // ---- tensor-core path (bf16 storage, stride-1 "same" convolutions and linear layers)
+                bool same = !convt && c.sh == 1 && c.sw == 1 && Ho == iv.h && Wo == iv.w;
+                bool pointwise = same && c.kh == 1 && c.kw == 1;
+                if (std::is_same<T, bf16>::value && tc_enabled() && same && iv.cp % 8 == 0 && cp.CoutP % 8 == 0 && dw.w_bf16) {
+                    tc::Params tp;
+                    memset(&tp, 0, sizeof(tp));
+                    tp.mode = pointwise ? 0 : 1;
+                    tp.M = cp.M;
+                    tp.N = iv.n; tp.H = iv.h; tp.W = iv.w;
+                    tp.taps = c.kh * c.kw; tp.kw = c.kw; tp.pad_t = c.pt; tp.pad_l = c.pl;
+                    tp.kchunks = (iv.cp + tc::BK - 1) / tc::BK;
+                    tp.Cout = c.cout; tp.CoutP = cp.CoutP;
+                    tp.epi = c.epi;
+                    tp.TW = 128; tp.TH = 1;
+                    if (tp.mode == 1) {
+                        int64_t best = -1;
+                        for (int tw = 128; tw >= 8; tw >>= 1) {
+                            int th = 128 / tw;
+                            int64_t cover = (int64_t)ceil_div(iv.w, tw) * tw * ceil_div(iv.h, th) * th;
+                            if (best < 0 || cover < best) { best = cover; tp.TW = tw; tp.TH = th; }
+                        }
+                    }
+                    tp.tiles_x = (int)ceil_div(iv.w, tp.TW);
+                    tp.tiles_y = (int)ceil_div(iv.h, tp.TH);
+                    int bn = dw.tc_bn;
+                    std::shared_ptr<TcState> ts(new TcState());
+                    {
+                        uint64_t dims[2] = {(uint64_t)dw.tc_k, (uint64_t)dw.tc_rows};
+                        uint64_t str[1] = {(uint64_t)dw.tc_k * 2};
+                        uint32_t box[2] = {(uint32_t)tc::BK, (uint32_t)bn};
+                        make_tmap(&ts->map_b, dw.w_bf16, 2, dims, str, box);
+                    }
+                    const float* tbias = dw.tc_bias;
+                    int icp = iv.cp, iN = iv.n, iH = iv.h, iW = iv.w;
+                    emit(std::string(c.is_linear ? "tclinear " : "tcconv ") + c.name, [=](cudaStream_t st) {
+                        const void* x = pp->ptr(in);
+                        if (ts->a_ptr != x) {
+                            if (tp.mode == 0) {
+                                uint64_t dims[2] = {(uint64_t)icp, (uint64_t)tp.M};
+                                uint64_t str[1] = {(uint64_t)icp * 2};
+                                uint32_t box[2] = {(uint32_t)tc::BK, (uint32_t)tc::BM};
+                                make_tmap(&ts->map_a, x, 2, dims, str, box);
+                            } else {
+                                uint64_t dims[4] = {(uint64_t)icp, (uint64_t)iW, (uint64_t)iH, (uint64_t)iN};
+                                uint64_t str[3] = {(uint64_t)icp * 2, (uint64_t)iW * icp * 2, (uint64_t)iH * iW * icp * 2};
+                                uint32_t box[4] = {(uint32_t)tc::BK, (uint32_t)tp.TW, (uint32_t)tp.TH, 1};
+                                make_tmap(&ts->map_a, x, 4, dims, str, box);
+                            }
+                            ts->a_ptr = x;
+                        }
+                        int m_tiles = tp.mode == 0 ? (int)ceil_div(tp.M, tc::BM) : tp.tiles_x * tp.tiles_y * tp.N;
+                        int total_tiles = m_tiles * (int)ceil_div(tp.CoutP, bn);
+                        int per_sm = bn == 128 ? 1 : 2;                     // shared-memory footprint per CTA
+                        dim3 grid((unsigned)std::min(total_tiles, 148 * per_sm));
+                        bf16* yo = (bf16*)pp->ptr(out);
+                        if (bn == 32) {
+                            cudaFuncSetAttribute(tc::conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes<32>());
+                            tc::conv_tc_kernel<32><<<grid, tc::kThreads, tc::smem_bytes<32>(), st>>>(ts->map_a, ts->map_b, tbias, yo, tp);
+                        } else if (bn == 64) {
+                            cudaFuncSetAttribute(tc::conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes<64>());
+                            tc::conv_tc_kernel<64><<<grid, tc::kThreads, tc::smem_bytes<64>(), st>>>(ts->map_a, ts->map_b, tbias, yo, tp);
+                        } else {
+                            cudaFuncSetAttribute(tc::conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes<128>());
+                            tc::conv_tc_kernel<128><<<grid, tc::kThreads, tc::smem_bytes<128>(), st>>>(ts->map_a, ts->map_b, tbias, yo, tp);
+                        }
+                    });
+                    vid[c.out] = out;
+                    break;
+                }
                 emit(std::string(convt ? "convT " : c.is_linear ? "linear " : "conv ") + c.name, [=](cudaStream_t st) {
                     const T* x = (const T*)pp->ptr(in);
                     T* y = (T*)pp->ptr(out);

@@ -39,7 +39,9 @@ struct PVal {
 struct DevWeights {
     float* w = nullptr;            // [Kpad][ColsW] fp32 (dense) or [taps][CP] (depthwise)
     float* bias = nullptr;         // [ColsW]
-    void* w_bf16 = nullptr;        // tcgen05 operand pack (optional)
+    void* w_bf16 = nullptr;        // tcgen05 operand pack: bf16 [tc_rows][tc_k], K-major (bf16 models only)
+    float* tc_bias = nullptr;
+    int tc_bn = 0, tc_rows = 0, tc_k = 0;
     int K = 0, Kpad = 0, ColsW = 0;
 };
 

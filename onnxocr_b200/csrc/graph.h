@@ -42,10 +42,30 @@ constexpr int kMaxEpi = 8;
 struct Epilogue {
     int n = 0;
     EpiStep s[kMaxEpi];
+    // Compiled form: v = act(v * a0 + b0) * a1 + b1, valid when `fast` (covers every chain paddle2onnx emits for these
+    // models: [LearnableAffine] -> activation -> [LearnableAffine]).  Kernels evaluate this instead of interpreting s[].
+    int fast = 1, act = 0;
+    float a0 = 1.f, b0 = 0.f, a1 = 1.f, b1 = 0.f, pa = 0.f, pb = 0.f;
     bool push(int type, float a = 0.f, float b = 0.f) {
         if (n >= kMaxEpi) return false;
         s[n++] = {type, a, b};
+        compile();
         return true;
+    }
+    void compile() {
+        fast = 1; act = 0; a0 = 1.f; b0 = 0.f; a1 = 1.f; b1 = 0.f; pa = 0.f; pb = 0.f;
+        for (int i = 0; i < n; ++i) {
+            const EpiStep& e = s[i];
+            if (e.type == EPI_AFFINE) {
+                if (act == 0) { a0 = a0 * e.a; b0 = b0 * e.a + e.b; }
+                else { a1 = a1 * e.a; b1 = b1 * e.a + e.b; }
+            } else if (act == 0) {
+                act = e.type; pa = e.a; pb = e.b;
+            } else {
+                fast = 0;            // two non-affine steps: interpret
+                return;
+            }
+        }
     }
 };
 
