@@ -115,6 +115,28 @@ Model::Model(const std::string& path, int precision) : prec_(precision) {
         for (int co = 0; co < cw.cout; ++co) bias[co] = cw.bias[co];
         d.w = upload(w);
         d.bias = upload(bias);
+        if (convt && prec_ == PREC_BF16 && cinp % 8 == 0 && coutp % 8 == 0) {
+            // transposed conv as one GEMM: column = tap * coutp + co, K = cin (single tap)
+            int gcols = 4 * coutp;
+            int bn = gcols <= 32 ? 32 : (gcols <= 64 ? 64 : 128);
+            int kchunks = (cinp + 63) / 64;
+            int rows = round_up(gcols, bn);
+            size_t K = (size_t)kchunks * 64;
+            std::vector<bf16> wb((size_t)rows * K, __float2bfloat16(0.f));
+            std::vector<float> tb(rows + 128, 0.f);
+            for (int t = 0; t < taps; ++t)
+                for (int co = 0; co < cw.cout; ++co) {
+                    for (int ci = 0; ci < cw.cin; ++ci)
+                        wb[(size_t)(t * coutp + co) * K + ci] = __float2bfloat16(cw.w[((size_t)t * cw.cin + ci) * cw.cout + co]);
+                    tb[t * coutp + co] = cw.bias[co];
+                }
+            B200_CUDA_CHECK(cudaMalloc(&d.w_bf16, wb.size() * sizeof(bf16)));
+            B200_CUDA_CHECK(cudaMemcpy(d.w_bf16, wb.data(), wb.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+            d.tc_bias = upload(tb);
+            d.tc_bn = bn;
+            d.tc_rows = rows;
+            d.tc_k = (int)K;
+        }
         if (!convt && prec_ == PREC_BF16 && cinp % 8 == 0) {
             // tcgen05 operand pack: bf16 [rows = round_up(CoutP, BN)][K = taps * kchunks * 64], K-major, zero padded
             int bn = coutp <= 32 ? 32 : (coutp <= 64 ? 64 : 128);
@@ -153,6 +175,12 @@ Model::Model(const std::string& path, int precision) : prec_(precision) {
             d.w = upload(w);
             d.bias = upload(bias);
             d.ColsW = cp;
+            if (prec_ == PREC_BF16) {
+                std::vector<bf16> wb(w.size());
+                for (size_t i = 0; i < w.size(); ++i) wb[i] = __float2bfloat16(w[i]);
+                B200_CUDA_CHECK(cudaMalloc(&d.w_bf16, wb.size() * sizeof(bf16)));
+                B200_CUDA_CHECK(cudaMemcpy(d.w_bf16, wb.data(), wb.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+            }
         }
     }
     for (auto& v : g_->vecs) {
@@ -454,15 +482,22 @@ void Model::build_steps(Plan& p) {
                 // ---- tensor-core path (bf16 storage, stride-1 "same" convolutions and linear layers)
                 bool same = !convt && c.sh == 1 && c.sw == 1 && Ho == iv.h && Wo == iv.w;
                 bool pointwise = same && c.kh == 1 && c.kw == 1;
-                if (std::is_same<T, bf16>::value && tc_enabled() && same && iv.cp % 8 == 0 && cp.CoutP % 8 == 0 && dw.w_bf16) {
+                bool tc_ct = convt && cp.CoutP % 8 == 0;
+                if (std::is_same<T, bf16>::value && tc_enabled() && (same || tc_ct) && iv.cp % 8 == 0 && cp.CoutP % 8 == 0 && dw.w_bf16) {
                     tc::Params tp;
                     memset(&tp, 0, sizeof(tp));
-                    tp.mode = pointwise ? 0 : 1;
+                    tp.mode = (pointwise || tc_ct) ? 0 : 1;
                     tp.M = cp.M;
                     tp.N = iv.n; tp.H = iv.h; tp.W = iv.w;
                     tp.taps = c.kh * c.kw; tp.kw = c.kw; tp.pad_t = c.pt; tp.pad_l = c.pl;
                     tp.kchunks = (iv.cp + tc::BK - 1) / tc::BK;
                     tp.Cout = c.cout; tp.CoutP = cp.CoutP;
+                    if (tc_ct) {
+                        tp.taps = 1; tp.kw = 1; tp.pad_t = tp.pad_l = 0;
+                        tp.M = iv.n * iv.h * iv.w;
+                        tp.convT = 1; tp.ctC = cp.CoutP; tp.ctCout = c.cout;
+                        tp.Cout = tp.CoutP = 4 * cp.CoutP;
+                    }
                     tp.epi = c.epi;
                     tp.TW = 128; tp.TH = 1;
                     if (tp.mode == 1) {
@@ -485,7 +520,7 @@ void Model::build_steps(Plan& p) {
                     }
                     const float* tbias = dw.tc_bias;
                     int icp = iv.cp, iN = iv.n, iH = iv.h, iW = iv.w;
-                    emit(std::string(c.is_linear ? "tclinear " : "tcconv ") + c.name, [=](cudaStream_t st) {
+                    emit(std::string(tc_ct ? "tcconvT " : c.is_linear ? "tclinear " : "tcconv ") + c.name, [=](cudaStream_t st) {
                         const void* x = pp->ptr(in);
                         if (ts->a_ptr != x) {
                             if (tp.mode == 0) {
@@ -520,9 +555,24 @@ void Model::build_steps(Plan& p) {
                     vid[c.out] = out;
                     break;
                 }
+                int w_ld = dw.ColsW;
                 emit(std::string(convt ? "convT " : c.is_linear ? "linear " : "conv ") + c.name, [=](cudaStream_t st) {
                     const T* x = (const T*)pp->ptr(in);
                     T* y = (T*)pp->ptr(out);
+                    if (convt && cp.Cout <= 4 && (cp.CoutP == 1 || cp.CoutP == 4) && cp.CinP % 4 == 0) {
+                        size_t smem = (size_t)4 * cp.Cout * cp.CinP * sizeof(float);
+                        convt_small_kernel<T><<<grid_for(cp.M), 256, smem, st>>>(x, wptr, w_ld, bptr, y, cp);
+                        return;
+                    }
+                    if (!convt && cp.CinP == 4 && cp.Cout <= 32 && cp.CoutP % 4 == 0) {
+                        int co = cp.Cout <= 8 ? 8 : (cp.Cout <= 16 ? 16 : 32);
+                        size_t smem = (size_t)cp.kh * cp.kw * 4 * co * sizeof(float);
+                        int g = grid_for(cp.M, 128);
+                        if (co == 8) conv_stem_kernel<T, 8><<<g, 128, smem, st>>>(x, wptr, w_ld, bptr, y, cp);
+                        else if (co == 16) conv_stem_kernel<T, 16><<<g, 128, smem, st>>>(x, wptr, w_ld, bptr, y, cp);
+                        else conv_stem_kernel<T, 32><<<g, 128, smem, st>>>(x, wptr, w_ld, bptr, y, cp);
+                        return;
+                    }
                     if (cols <= 16) {
                         dim3 grid((unsigned)ceil_div(cp.M, 256), (unsigned)ceil_div(cols, 16));
                         conv_igemm_kernel<T, 256, 16><<<grid, 256, 0, st>>>(x, wptr, bptr, y, cp);
@@ -552,10 +602,23 @@ void Model::build_steps(Plan& p) {
                 p.flops += 2.0 * iv.n * Ho * Wo * (double)c.cout * c.kh * c.kw;
                 const float* wptr = dw_[c.weight_id].w;
                 const float* bptr = dw_[c.weight_id].bias;
+                const bf16* wb16 = (const bf16*)dw_[c.weight_id].w_bf16;
                 int64_t total = (int64_t)iv.n * Ho * Wo * (iv.cp / 4);
                 cost_flops = 2.0 * iv.n * Ho * Wo * (double)c.cout * c.kh * c.kw;
                 cost_bytes = vbytes(in) + vbytes(out);
                 emit("dwconv " + c.name, [=](cudaStream_t st) {
+                    if (std::is_same<T, bf16>::value && wb16 && dp.CP % 8 == 0 && dp.kh == dp.kw && (dp.kw == 3 || dp.kw == 5) &&
+                        (dp.sw == 1 || dp.sw == 2)) {
+                        int64_t strips = (int64_t)dp.N * dp.Ho * ceil_div(dp.Wo, 4) * (dp.CP / 8);
+                        const bf16* xi = (const bf16*)pp->ptr(in);
+                        bf16* yo = (bf16*)pp->ptr(out);
+                        int g = grid_for(strips);
+                        if (dp.kw == 3 && dp.sw == 1) dwconv_strip_kernel<3, 1><<<g, 256, 0, st>>>(xi, wb16, bptr, yo, dp);
+                        else if (dp.kw == 3) dwconv_strip_kernel<3, 2><<<g, 256, 0, st>>>(xi, wb16, bptr, yo, dp);
+                        else if (dp.sw == 1) dwconv_strip_kernel<5, 1><<<g, 256, 0, st>>>(xi, wb16, bptr, yo, dp);
+                        else dwconv_strip_kernel<5, 2><<<g, 256, 0, st>>>(xi, wb16, bptr, yo, dp);
+                        return;
+                    }
                     dwconv_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)pp->ptr(in), wptr, bptr, (T*)pp->ptr(out), dp);
                 });
                 vid[c.out] = out;
@@ -689,8 +752,13 @@ void Model::build_steps(Plan& p) {
                     int N = pv.n, H = pv.h, W = pv.w, Cs = pv.c, CsP = pv.cp, fh = pv.fh, fw = pv.fw, coff = off;
                     cost_bytes = vbytes(src) + (double)N * H * W * Cs * esz;
                     emit("concat " + c.name, [=](cudaStream_t st) {
-                        concat_slice_kernel<T><<<grid_for((int64_t)N * H * W * Cs), 256, 0, st>>>(
-                            (const T*)pp->ptr(src), (T*)pp->ptr(out), N, H, W, Cs, CsP, cdp, coff, fh, fw);
+                        constexpr int epv = 16 / (int)sizeof(T);
+                        if (Cs % epv == 0 && CsP % epv == 0 && cdp % epv == 0 && coff % epv == 0)
+                            concat_slice_vec_kernel<T><<<grid_for((int64_t)N * H * W * (Cs / epv)), 256, 0, st>>>(
+                                (const T*)pp->ptr(src), (T*)pp->ptr(out), N, H, W, Cs, CsP, cdp, coff, fh, fw);
+                        else
+                            concat_slice_kernel<T><<<grid_for((int64_t)N * H * W * Cs), 256, 0, st>>>(
+                                (const T*)pp->ptr(src), (T*)pp->ptr(out), N, H, W, Cs, CsP, cdp, coff, fh, fw);
                     });
                     off += pv.c;
                 }

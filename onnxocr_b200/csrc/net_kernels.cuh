@@ -261,6 +261,92 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ x, co
     }
 }
 
+// Depthwise convolution, bf16 storage, 8 channels x 4 consecutive output pixels per thread.  Each input column of the
+// strip is loaded once (16-byte vector) and feeds every output of the strip it overlaps; weights are bf16 [tap][CP].
+template <int KW, int SW>
+__global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                            const float* __restrict__ bias, bf16* __restrict__ y, const DwP p) {
+    constexpr int TW = 4;
+    constexpr int NCOL = (TW - 1) * SW + KW;
+    const int cg = p.CP >> 3;
+    const int strips_x = (p.Wo + TW - 1) / TW;
+    const int64_t total = (int64_t)p.N * p.Ho * strips_x * cg;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int g = (int)(i % cg);
+        int64_t q = i / cg;
+        int sx = (int)(q % strips_x);
+        q /= strips_x;
+        int oy = (int)(q % p.Ho);
+        int n = (int)(q / p.Ho);
+        const int c = g * 8;
+        const int ox0 = sx * TW;
+        float acc[TW][8];
+        {
+            float4 b0 = *reinterpret_cast<const float4*>(bias + c);
+            float4 b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+#pragma unroll
+            for (int t = 0; t < TW; ++t) {
+                acc[t][0] = b0.x; acc[t][1] = b0.y; acc[t][2] = b0.z; acc[t][3] = b0.w;
+                acc[t][4] = b1.x; acc[t][5] = b1.y; acc[t][6] = b1.z; acc[t][7] = b1.w;
+            }
+        }
+        const int ix0 = ox0 * SW - p.pl;
+        for (int ky = 0; ky < p.kh; ++ky) {
+            int iy = oy * p.sh - p.pt + ky;
+            if ((unsigned)iy >= (unsigned)p.H) continue;
+            float wv[KW][8];
+#pragma unroll
+            for (int kx = 0; kx < KW; ++kx) {
+                uint4 t = *reinterpret_cast<const uint4*>(w + (int64_t)(ky * KW + kx) * p.CP + c);
+                wv[kx][0] = __uint_as_float(t.x << 16); wv[kx][1] = __uint_as_float(t.x & 0xffff0000u);
+                wv[kx][2] = __uint_as_float(t.y << 16); wv[kx][3] = __uint_as_float(t.y & 0xffff0000u);
+                wv[kx][4] = __uint_as_float(t.z << 16); wv[kx][5] = __uint_as_float(t.z & 0xffff0000u);
+                wv[kx][6] = __uint_as_float(t.w << 16); wv[kx][7] = __uint_as_float(t.w & 0xffff0000u);
+            }
+            const bf16* row = x + (((int64_t)n * p.H + iy) * p.W) * p.CP + c;
+#pragma unroll
+            for (int xi = 0; xi < NCOL; ++xi) {
+                int ix = ix0 + xi;
+                if ((unsigned)ix >= (unsigned)p.W) continue;
+                uint4 t = *reinterpret_cast<const uint4*>(row + (int64_t)ix * p.CP);
+                float v[8];
+                v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+                v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+                v[4] = __uint_as_float(t.z << 16); v[5] = __uint_as_float(t.z & 0xffff0000u);
+                v[6] = __uint_as_float(t.w << 16); v[7] = __uint_as_float(t.w & 0xffff0000u);
+#pragma unroll
+                for (int t2 = 0; t2 < TW; ++t2) {
+                    constexpr int dummy = 0;
+                    (void)dummy;
+                    int kx = xi - t2 * SW;
+                    if (kx >= 0 && kx < KW) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[t2][j] = fmaf(v[j], wv[kx][j], acc[t2][j]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < TW; ++t) {
+            int ox = ox0 + t;
+            if (ox >= p.Wo) break;
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (c + j < p.C) ? epi_apply(acc[t][j], p.epi) : 0.f;
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(o[0], o[1]);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(o[2], o[3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(o[4], o[5]);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(o[6], o[7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&t0);
+            pk.y = *reinterpret_cast<uint32_t*>(&t1);
+            pk.z = *reinterpret_cast<uint32_t*>(&t2);
+            pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(y + (((int64_t)n * p.Ho + oy) * p.Wo + ox) * p.CP + c) = pk;
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------
 // global average pool (deterministic two-stage) + squeeze-excite
 // ----------------------------------------------------------------------------------------
@@ -467,6 +553,111 @@ __global__ void concat_slice_kernel(const T* __restrict__ src, T* __restrict__ d
         int n = (int)(q / H);
         dst[(((int64_t)n * H + yh) * W + xw) * CdP + c_off + c] =
             src[(((int64_t)n * Hs + yh / fh) * Ws + xw / fw) * CsP + c];
+    }
+}
+
+// 16-byte vector version (channel counts and offset multiples of 16 / sizeof(T))
+template <typename T>
+__global__ void concat_slice_vec_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int H, int W, int Cs, int CsP,
+                                        int CdP, int c_off, int fh, int fw) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    const int vc = Cs / EPV;
+    int64_t total = (int64_t)N * H * W * vc;
+    const int Hs = H / fh, Ws = W / fw;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % vc) * EPV;
+        int64_t q = i / vc;
+        int xw = (int)(q % W);
+        q /= W;
+        int yh = (int)(q % H);
+        int n = (int)(q / H);
+        uint4 v = *reinterpret_cast<const uint4*>(src + (((int64_t)n * Hs + yh / fh) * Ws + xw / fw) * CsP + c);
+        *reinterpret_cast<uint4*>(dst + (((int64_t)n * H + yh) * W + xw) * CdP + c_off + c) = v;
+    }
+}
+
+// Dense k x k convolution for tiny input channel counts (the 3-channel stem): one thread per output pixel computes all
+// COUT channels; weights fp32 [tap][CinP = 4][COUT] in shared memory.
+template <typename T, int COUT>
+__global__ void __launch_bounds__(128) conv_stem_kernel(const T* __restrict__ x, const float* __restrict__ w, int w_ld,
+                                                        const float* __restrict__ bias, T* __restrict__ y, const ConvP p) {
+    extern __shared__ float sw[];                 // [taps * 4][COUT]
+    const int taps = p.kh * p.kw;
+    for (int i = threadIdx.x; i < taps * 4 * COUT; i += blockDim.x) sw[i] = w[(int64_t)(i / COUT) * w_ld + (i % COUT)];
+    __syncthreads();
+    for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < p.M; m += (int64_t)gridDim.x * blockDim.x) {
+        int ox = (int)(m % p.Wo);
+        int64_t q = m / p.Wo;
+        int oy = (int)(q % p.Ho);
+        int n = (int)(q / p.Ho);
+        float acc[COUT];
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) acc[j] = bias[j];
+        for (int ky = 0; ky < p.kh; ++ky) {
+            int iy = oy * p.sh - p.pt + ky;
+            if ((unsigned)iy >= (unsigned)p.H) continue;
+            for (int kx = 0; kx < p.kw; ++kx) {
+                int ix = ox * p.sw - p.pl + kx;
+                if ((unsigned)ix >= (unsigned)p.W) continue;
+                float v[4];
+                ST<T>::ld4(x + (((int64_t)n * p.H + iy) * p.W + ix) * 4, v);
+                const float* wt = sw + (ky * p.kw + kx) * 4 * COUT;
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+                    for (int j = 0; j < COUT; ++j) acc[j] = fmaf(v[ci], wt[ci * COUT + j], acc[j]);
+            }
+        }
+        T* dst = y + m * p.CoutP;
+#pragma unroll
+        for (int j = 0; j < COUT; j += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = (j + e < p.Cout) ? epi_apply(acc[j + e], p.epi) : 0.f;
+            if (j < p.CoutP) ST<T>::st4(dst + j, o);
+        }
+    }
+}
+
+// ConvTranspose 2x2 stride 2 with a tiny output channel count (the DB head's last layer, Cout = 1): one thread per
+// input pixel, weights fp32 [tap][CinP] per output channel in shared memory, output cpad == Cout (1 or 4).
+template <typename T>
+__global__ void __launch_bounds__(256) convt_small_kernel(const T* __restrict__ x, const float* __restrict__ w, int w_ld,
+                                                          const float* __restrict__ bias, T* __restrict__ y, const ConvP p) {
+    extern __shared__ float sw[];                 // [tap][co][CinP]
+    const int CoP = p.CoutP;                      // 1 or 4
+    for (int i = threadIdx.x; i < 4 * p.Cout * p.CinP; i += blockDim.x) {
+        int ci = i % p.CinP, r = i / p.CinP, co = r % p.Cout, tap = r / p.Cout;
+        sw[i] = w[(int64_t)ci * w_ld + tap * CoP + co];
+    }
+    __syncthreads();
+    for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < p.M; m += (int64_t)gridDim.x * blockDim.x) {
+        int ox = (int)(m % p.Wo);
+        int64_t q = m / p.Wo;
+        int oy = (int)(q % p.Ho);
+        int n = (int)(q / p.Ho);
+        const T* src = x + m * p.CinP;
+        float acc[4][4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int co = 0; co < 4; ++co) acc[t][co] = co < p.Cout ? bias[co] : 0.f;
+        for (int c = 0; c < p.CinP; c += 4) {
+            float v[4];
+            ST<T>::ld4(src + c, v);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                for (int co = 0; co < p.Cout; ++co) {
+                    const float* wt = sw + ((t * p.Cout + co) * p.CinP + c);
+                    acc[t][co] = fmaf(v[0], wt[0], fmaf(v[1], wt[1], fmaf(v[2], wt[2], fmaf(v[3], wt[3], acc[t][co]))));
+                }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            int dy = t >> 1, dx = t & 1;
+            T* dst = y + ((((int64_t)n * (2 * p.Ho) + 2 * oy + dy) * (2 * p.Wo)) + 2 * ox + dx) * CoP;
+            for (int co = 0; co < CoP; ++co) ST<T>::st(dst + co, co < p.Cout ? epi_apply(acc[t][co], p.epi) : 0.f);
+        }
     }
 }
 

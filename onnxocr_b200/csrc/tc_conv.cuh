@@ -29,7 +29,9 @@ struct Params {
     int TW, TH, tiles_x, tiles_y;
     int taps, kw, pad_t, pad_l;
     int kchunks;                 // ceil(CinP / 64)
-    int Cout, CoutP;
+    int Cout, CoutP;             // GEMM columns that carry data / padded (for convT: 4 * out channels padded)
+    int convT;                   // 1: column = tap * ctC + co, stored pixel-shuffled to (2y + dy, 2x + dx)
+    int ctC, ctCout;             // convT: padded / real output channels
     Epilogue epi;
 };
 
@@ -131,7 +133,7 @@ __device__ __forceinline__ float epi_fast(float v, const Epilogue& e) {
 // One accumulator row (this thread's pixel) -> bias, activation chain, bf16, 16-byte NHWC stores.
 template <int BN, int ACT>
 __device__ __forceinline__ void epilogue_row(uint32_t trow, const float* __restrict__ bias, bf16* __restrict__ dst, bool valid,
-                                             int n0, const Params& p) {
+                                             int n0, const Params& p, int64_t ct_base = 0) {
 #pragma unroll 1
     for (int c = 0; c < BN; c += 16) {
         uint32_t v[16];
@@ -146,10 +148,17 @@ __device__ __forceinline__ void epilogue_row(uint32_t trow, const float* __restr
                 float4 b1 = *reinterpret_cast<const float4*>(bias + col + 4);
                 float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 float o[8];
+                int64_t doff = col;
+                int lim = p.Cout - col;
+                if (p.convT) {                            // 8-column groups never straddle taps (ctC % 8 == 0)
+                    int tap = col / p.ctC, co = col - tap * p.ctC;
+                    doff = ct_base + ((int64_t)(tap >> 1) * (2 * p.W) + (tap & 1)) * p.ctC + co;
+                    lim = p.ctCout - co;
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float f = epi_fast<ACT>(__uint_as_float(v[8 * h + j]) + bb[j], p.epi);
-                    o[j] = (col + j < p.Cout) ? f : 0.f;
+                    o[j] = (j < lim) ? f : 0.f;
                 }
                 uint4 pk;
                 __nv_bfloat162 t0 = __floats2bfloat162_rn(o[0], o[1]);
@@ -160,7 +169,7 @@ __device__ __forceinline__ void epilogue_row(uint32_t trow, const float* __restr
                 pk.y = *reinterpret_cast<uint32_t*>(&t1);
                 pk.z = *reinterpret_cast<uint32_t*>(&t2);
                 pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                *reinterpret_cast<uint4*>(dst + col) = pk;
+                *reinterpret_cast<uint4*>(dst + doff) = pk;
             }
         }
     }
@@ -307,14 +316,25 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
                 off = (((int64_t)img * p.H + yy) * p.W + xx) * p.CoutP;
             }
             const uint32_t trow = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+            int64_t ctb = 0;
+            bf16* dst = y + off;
+            if (p.convT) {                                  // mode 0 rows are input pixels (n, yy, xx)
+                int m = m0 + row;
+                int xx = m % p.W;
+                int r = m / p.W;
+                int yy = r % p.H;
+                int nn = r / p.H;
+                ctb = ((((int64_t)nn * (2 * p.H) + 2 * yy) * (2 * p.W)) + 2 * xx) * p.ctC;
+                dst = y;
+            }
             switch (act_code) {
-                case 0: epilogue_row<BN, 0>(trow, bias, y + off, valid, n0, p); break;
-                case EPI_RELU: epilogue_row<BN, EPI_RELU>(trow, bias, y + off, valid, n0, p); break;
-                case EPI_HSWISH: epilogue_row<BN, EPI_HSWISH>(trow, bias, y + off, valid, n0, p); break;
-                case EPI_SIGMOID: epilogue_row<BN, EPI_SIGMOID>(trow, bias, y + off, valid, n0, p); break;
-                case EPI_SWISH: epilogue_row<BN, EPI_SWISH>(trow, bias, y + off, valid, n0, p); break;
-                case EPI_HSIGMOID: epilogue_row<BN, EPI_HSIGMOID>(trow, bias, y + off, valid, n0, p); break;
-                default: epilogue_row<BN, -1>(trow, bias, y + off, valid, n0, p); break;
+                case 0: epilogue_row<BN, 0>(trow, bias, dst, valid, n0, p, ctb); break;
+                case EPI_RELU: epilogue_row<BN, EPI_RELU>(trow, bias, dst, valid, n0, p, ctb); break;
+                case EPI_HSWISH: epilogue_row<BN, EPI_HSWISH>(trow, bias, dst, valid, n0, p, ctb); break;
+                case EPI_SIGMOID: epilogue_row<BN, EPI_SIGMOID>(trow, bias, dst, valid, n0, p, ctb); break;
+                case EPI_SWISH: epilogue_row<BN, EPI_SWISH>(trow, bias, dst, valid, n0, p, ctb); break;
+                case EPI_HSIGMOID: epilogue_row<BN, EPI_HSIGMOID>(trow, bias, dst, valid, n0, p, ctb); break;
+                default: epilogue_row<BN, -1>(trow, bias, dst, valid, n0, p, ctb); break;
             }
             // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
