@@ -180,9 +180,9 @@ B200_HDN int sklansky(const uint64_t* k, int start, int end, int* stack, int nsi
 //   keys   : n contour points packed by pack_key, in contour order on entry (sorted in place)
 //   stack  : scratch, n + 2 ints
 //   hull   : out, positions into the sorted key array (<= n entries); returns the hull size
-B200_HDN int convex_hull(uint64_t* keys, int n, int* stack, int* hull, bool clockwise = false) {
+B200_HDN int convex_hull(uint64_t* keys, int n, int* stack, int* hull, bool clockwise = false, bool presorted = false) {
     if (n == 0) return 0;
-    sort_keys(keys, n);
+    if (!presorted) sort_keys(keys, n);
     int miny = 0, maxy = 0;
     for (int i = 1; i < n; ++i) {
         int y = key_y(keys[i]);

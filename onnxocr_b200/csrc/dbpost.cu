@@ -169,12 +169,12 @@ __global__ void compact_kernel(const uint8_t* __restrict__ bm, const int* __rest
 }
 
 __global__ void trace_count_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ cand, const int* __restrict__ counts,
-                                   int* __restrict__ npts, int n, int h, int w, int maxc) {
+                                   const uint8_t* __restrict__ valid, int* __restrict__ npts, int n, int h, int w, int maxc) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * maxc) return;
     int p = t / maxc, r = t % maxc;
     int cnt = 0;
-    if (r < counts[p]) {
+    if (r < counts[p] && valid[t] == 2) {
         int c = cand[t];
         int local = c & (kHoleBit - 1);
         Bitmap img{bm + (size_t)p * h * w, h, w};
@@ -191,6 +191,7 @@ __global__ void contour_box_kernel(const uint8_t* __restrict__ bm, const int* __
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * maxc) return;
     int p = t / maxc, r = t % maxc;
+    if (valid[t] != 2) return;                         // only contours the warp kernel could not hold in shared memory
     valid[t] = 0;
     if (r >= counts[p]) return;
     int np = npts[t];
@@ -216,13 +217,144 @@ __global__ void contour_box_kernel(const uint8_t* __restrict__ bm, const int* __
     valid[t] = 1;
 }
 
+// phase A, fast path: one warp per contour.  The 8 neighbours of the current border pixel are fetched by 8 lanes at
+// once (one memory round trip per step instead of up to 8 dependent ones), contour points go to shared memory, the
+// (x, y, index) sort is a warp bitonic sort, hull + calipers run on lane 0 out of shared memory.  Contours with more than
+// kWarpCap vertices or kWarpHull hull points are flagged and redone by the generic kernels above.
+constexpr int kWarpCap = 1024;
+constexpr int kWarpHull = 256;
+constexpr int kWarpsPerBlock = 4;
+constexpr size_t kWarpSmem = (size_t)kWarpCap * 8 + (size_t)(kWarpCap + 2) * 4 + (size_t)kWarpCap * 4 + (size_t)kWarpHull * 20;
+
+__device__ __forceinline__ unsigned neighbour_mask(const Bitmap& img, int x, int y, int lane) {
+    const int dx8[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+    const int dy8[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+    int v = 0;
+    if (lane < 8) v = img.at(x + dx8[lane], y + dy8[lane]);
+    return __ballot_sync(0xffffffffu, v != 0) & 0xffu;
+}
+
+// Warp-cooperative twin of geom::trace_contour (identical point sequence); all lanes return the point count.
+__device__ int warp_trace_contour(const Bitmap& img, int sx, int sy, bool is_hole, uint64_t* keys, int cap, int lane) {
+    const int dx8[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+    const int dy8[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+    int s_end = is_hole ? 0 : 4, s = s_end;
+    unsigned mask = neighbour_mask(img, sx, sy, lane);
+    do {
+        s = (s - 1) & 7;
+    } while (!((mask >> s) & 1u) && s != s_end);
+    int n = 0;
+    if (s == s_end) {
+        if (lane == 0 && cap > 0) keys[0] = pack_key(sx, sy, 0);
+        return 1;
+    }
+    const int i1x = sx + dx8[s], i1y = sy + dy8[s];
+    int i3x = sx, i3y = sy;
+    int prev_s = s ^ 4;
+    int ptx = sx, pty = sy;
+    for (;;) {
+        // first set direction among s+1, s+2, ... (cyclic); at least the pixel we came from is set
+        unsigned rot = ((mask | (mask << 8)) >> ((s + 1) & 7)) & 0xffu;
+        int step = __ffs(rot) - 1;
+        s = (s + 1 + step) & 7;
+        int i4x = i3x + dx8[s], i4y = i3y + dy8[s];
+        if (s != prev_s) {
+            if (lane == 0 && n < cap) keys[n] = pack_key(ptx, pty, n);
+            ++n;
+            prev_s = s;
+        }
+        ptx += dx8[s];
+        pty += dy8[s];
+        if (i4x == sx && i4y == sy && i3x == i1x && i3y == i1y) break;
+        i3x = i4x;
+        i3y = i4y;
+        s = (s + 4) & 7;
+        mask = neighbour_mask(img, i3x, i3y, lane);
+    }
+    return n;
+}
+
+__device__ void warp_bitonic_sort(uint64_t* a, int npow2, int lane) {
+    for (int k = 2; k <= npow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < npow2; i += 32) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    uint64_t x = a[i], y = a[ixj];
+                    bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncwarp();
+        }
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerBlock) contour_warp_kernel(
+    const uint8_t* __restrict__ bm, const int* __restrict__ cand, const int* __restrict__ counts, float* __restrict__ box1,
+    uint8_t* __restrict__ valid, int* __restrict__ n_flagged, int n, int h, int w, int maxc, float min_size) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= n * maxc) return;
+    uint8_t* base = smem + (size_t)warp * kWarpSmem;
+    uint64_t* keys = (uint64_t*)base;
+    int* stack = (int*)(base + (size_t)kWarpCap * 8);
+    int* hull = stack + kWarpCap + 2;
+    PtF* hp = (PtF*)(hull + kWarpCap);
+    PtF* vect = hp + kWarpHull;
+    float* inv = (float*)(vect + kWarpHull);
+    const int p = t / maxc, r = t % maxc;
+    if (r >= counts[p]) {
+        if (lane == 0) valid[t] = 0;
+        return;
+    }
+    const int c = cand[t];
+    const int local = c & (kHoleBit - 1);
+    Bitmap img{bm + (size_t)p * h * w, h, w};
+    int np = warp_trace_contour(img, local % w, local / w, (c & kHoleBit) != 0, keys, kWarpCap, lane);
+    if (np > kWarpCap) {
+        if (lane == 0) { valid[t] = 2; atomicAdd(n_flagged, 1); }
+        return;
+    }
+    __syncwarp();
+    int npow2 = 1;
+    while (npow2 < np) npow2 <<= 1;
+    for (int i = np + lane; i < npow2; i += 32) keys[i] = ~(uint64_t)0;
+    __syncwarp();
+    warp_bitonic_sort(keys, npow2, lane);
+    if (lane == 0) {
+        int nh = convex_hull(keys, np, stack, hull, false, true);
+        if (nh > kWarpHull) {
+            valid[t] = 2;
+            atomicAdd(n_flagged, 1);
+        } else {
+            for (int i = 0; i < nh; ++i) {
+                hp[i].x = (float)key_x(keys[hull[i]]);
+                hp[i].y = (float)key_y(keys[hull[i]]);
+            }
+            RotRect rr = min_area_rect(hp, nh, vect, inv);
+            PtF box[4];
+            float sside = mini_box(rr, box);
+            if (sside < min_size) {
+                valid[t] = 0;
+            } else {
+                for (int i = 0; i < 4; ++i) {
+                    box1[(size_t)t * 8 + 2 * i] = box[i].x;
+                    box1[(size_t)t * 8 + 2 * i + 1] = box[i].y;
+                }
+                valid[t] = 1;
+            }
+        }
+    }
+}
+
 // phase B: box_score_fast, one block per candidate (rows of the bounding box are spread over the threads;
 // partial sums are combined in a fixed order, so the result is deterministic)
 __global__ void __launch_bounds__(128) score_kernel(const float* __restrict__ prob, const float* __restrict__ box1,
                                                      uint8_t* __restrict__ valid, double* __restrict__ score, int h, int w,
                                                      int maxc, double box_thresh) {
     int t = blockIdx.x;
-    if (!valid[t]) return;
+    if (valid[t] != 1) return;
     int p = t / maxc;
     const float* pred = prob + (size_t)p * h * w;
     PtF box[4];
@@ -279,7 +411,7 @@ __global__ void __launch_bounds__(128) score_kernel(const float* __restrict__ pr
 __global__ void unclip_kernel(const float* __restrict__ box1, uint8_t* __restrict__ valid, int* __restrict__ res_box,
                               const int* __restrict__ src_hw, int n, int h, int w, int maxc, double unclip_ratio, float min_size2) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * maxc || !valid[t]) return;
+    if (t >= n * maxc || valid[t] != 1) return;
     int p = t / maxc;
     PtF box[4];
     for (int i = 0; i < 4; ++i) {
@@ -351,38 +483,39 @@ void Stages::db_postprocess_device(const float* d_prob, int n, int h, int w, con
     int* npts = (int*)W.npts.get((size_t)(nt + 1) * sizeof(int));
     int* offs = (int*)W.offs.get((size_t)(nt + 1) * sizeof(int));
     compact_kernel<<<grid_for(total), 256, 0, st>>>(bm, flags, pos, cand, counts, n, hw, maxc);
-    trace_count_kernel<<<(unsigned)ceil_div(nt, 64), 64, 0, st>>>(bm, cand, counts, npts, n, h, w, maxc);
-    B200_CUDA_CHECK(cudaMemsetAsync(npts + nt, 0, sizeof(int), st));
-    size_t tmp2 = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, npts, offs, nt + 1, st);
-    tmp = W.scan_tmp.get(std::max(tmp_bytes, tmp2) + 256);
-    cub::DeviceScan::ExclusiveSum(tmp, tmp2, npts, offs, nt + 1, st);
-    int* h_counts = (int*)W.h_counts.get((size_t)(n + 1) * sizeof(int) + 2 * n * sizeof(int));
-    B200_CUDA_CHECK(cudaMemcpyAsync(h_counts, counts, n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    B200_CUDA_CHECK(cudaMemcpyAsync(h_counts + n, offs + nt, sizeof(int), cudaMemcpyDeviceToHost, st));
-    int* h_src = h_counts + n + 1;
+    float* box1 = (float*)W.box1.get((size_t)nt * 8 * sizeof(float));
+    uint8_t* valid = (uint8_t*)W.valid.get((size_t)nt);
+    double* score = (double*)W.score.get((size_t)nt * sizeof(double));
+    int* res_box = (int*)W.res_box.get((size_t)nt * 8 * sizeof(int));
+    int* d_flagged = npts + nt;                       // reuse the scan sentinel slot as the overflow counter
+    B200_CUDA_CHECK(cudaMemsetAsync(d_flagged, 0, sizeof(int), st));
+    int* h_counts = (int*)W.h_counts.get((size_t)(n + 2) * sizeof(int) + 2 * n * sizeof(int));
+    int* h_src = h_counts + n + 2;
     for (int i = 0; i < n; ++i) {
         h_src[2 * i] = src_hs[i];
         h_src[2 * i + 1] = src_ws[i];
     }
     B200_CUDA_CHECK(cudaMemcpyAsync(d_src, h_src, 2 * n * sizeof(int), cudaMemcpyHostToDevice, st));
-    B200_CUDA_CHECK(cudaStreamSynchronize(st));
-    launches += 10;
-    int64_t total_pts = h_counts[n];
-    if (total_pts >= (1 << 20) * (int64_t)64) throw std::runtime_error("bad argument: contour point pool overflow");
-    uint64_t* keys = (uint64_t*)W.keys.get((size_t)(total_pts + 1) * sizeof(uint64_t));
-    int* ipool = (int*)W.ipool.get((size_t)(2 * total_pts + 2 * (int64_t)nt + 2) * sizeof(int));
-    float* fpool = (float*)W.fpool.get((size_t)(5 * total_pts + 5) * sizeof(float));
-    float* box1 = (float*)W.box1.get((size_t)nt * 8 * sizeof(float));
-    uint8_t* valid = (uint8_t*)W.valid.get((size_t)nt);
-    double* score = (double*)W.score.get((size_t)nt * sizeof(double));
-    int* res_box = (int*)W.res_box.get((size_t)nt * 8 * sizeof(int));
-    contour_box_kernel<<<(unsigned)ceil_div(nt, 64), 64, 0, st>>>(bm, cand, counts, npts, offs, keys, ipool, fpool, box1, valid,
-                                                                   n, h, w, maxc, (float)p.min_size);
-    score_kernel<<<nt, 128, 0, st>>>(d_prob, box1, valid, score, h, w, maxc, p.box_thresh);
-    unclip_kernel<<<(unsigned)ceil_div(nt, 32), 32, 0, st>>>(box1, valid, res_box, d_src, n, h, w, maxc, p.unclip_ratio,
-                                                              (float)(p.min_size + 2));
-    launches += 3;
+    {
+        static bool attr_set = false;
+        size_t smem = kWarpSmem * kWarpsPerBlock;
+        if (!attr_set) {
+            B200_CUDA_CHECK(cudaFuncSetAttribute(contour_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        contour_warp_kernel<<<(unsigned)ceil_div(nt, kWarpsPerBlock), 32 * kWarpsPerBlock, smem, st>>>(
+            bm, cand, counts, box1, valid, d_flagged, n, h, w, maxc, (float)p.min_size);
+    }
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_counts, counts, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_counts + n, d_flagged, sizeof(int), cudaMemcpyDeviceToHost, st));
+    launches += 11;
+    auto run_tail = [&]() {
+        score_kernel<<<nt, 128, 0, st>>>(d_prob, box1, valid, score, h, w, maxc, p.box_thresh);
+        unclip_kernel<<<(unsigned)ceil_div(nt, 32), 32, 0, st>>>(box1, valid, res_box, d_src, n, h, w, maxc, p.unclip_ratio,
+                                                                  (float)(p.min_size + 2));
+        launches += 2;
+    };
+    run_tail();
     B200_CUDA_CHECK(cudaGetLastError());
     // results -> host
     size_t res_bytes = (size_t)nt * (8 * sizeof(int) + sizeof(double) + 1);
@@ -394,6 +527,30 @@ void Stages::db_postprocess_device(const float* d_prob, int n, int h, int w, con
     B200_CUDA_CHECK(cudaMemcpyAsync(hs, score, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaMemcpyAsync(hv, valid, (size_t)nt, cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h_counts[n] > 0) {
+        // rare: some contour exceeded the shared-memory capacity of the warp kernel -> generic two-pass path for those
+        trace_count_kernel<<<(unsigned)ceil_div(nt, 64), 64, 0, st>>>(bm, cand, counts, valid, npts, n, h, w, maxc);
+        B200_CUDA_CHECK(cudaMemsetAsync(npts + nt, 0, sizeof(int), st));
+        size_t tmp2 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp2, npts, offs, nt + 1, st);
+        void* tmpb = W.scan_tmp.get(std::max(tmp_bytes, tmp2) + 256);
+        cub::DeviceScan::ExclusiveSum(tmpb, tmp2, npts, offs, nt + 1, st);
+        B200_CUDA_CHECK(cudaMemcpyAsync(h_counts + n + 1, offs + nt, sizeof(int), cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        int64_t total_pts = h_counts[n + 1];
+        if (total_pts >= (1 << 20) * (int64_t)64) throw std::runtime_error("bad argument: contour point pool overflow");
+        uint64_t* keys = (uint64_t*)W.keys.get((size_t)(total_pts + 1) * sizeof(uint64_t));
+        int* ipool = (int*)W.ipool.get((size_t)(2 * total_pts + 2 * (int64_t)nt + 2) * sizeof(int));
+        float* fpool = (float*)W.fpool.get((size_t)(5 * total_pts + 5) * sizeof(float));
+        contour_box_kernel<<<(unsigned)ceil_div(nt, 64), 64, 0, st>>>(bm, cand, counts, npts, offs, keys, ipool, fpool, box1, valid,
+                                                                       n, h, w, maxc, (float)p.min_size);
+        launches += 4;
+        run_tail();
+        B200_CUDA_CHECK(cudaMemcpyAsync(hb, res_box, (size_t)nt * 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaMemcpyAsync(hs, score, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaMemcpyAsync(hv, valid, (size_t)nt, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
     boxes->clear();
     scores->clear();
     counts_out->assign(n, 0);
@@ -401,7 +558,7 @@ void Stages::db_postprocess_device(const float* d_prob, int n, int h, int w, con
         int c = h_counts[pg];
         for (int r = 0; r < c; ++r) {
             size_t t = (size_t)pg * maxc + r;
-            if (!hv[t]) continue;
+            if (hv[t] != 1) continue;
             boxes->insert(boxes->end(), hb + t * 8, hb + t * 8 + 8);
             scores->push_back(hs[t]);
             (*counts_out)[pg]++;
