@@ -608,15 +608,20 @@ void Model::build_steps(Plan& p) {
                 cost_bytes = vbytes(in) + vbytes(out);
                 emit("dwconv " + c.name, [=](cudaStream_t st) {
                     if (std::is_same<T, bf16>::value && wb16 && dp.CP % 8 == 0 && dp.kh == dp.kw && (dp.kw == 3 || dp.kw == 5) &&
-                        (dp.sw == 1 || dp.sw == 2)) {
-                        int64_t strips = (int64_t)dp.N * dp.Ho * ceil_div(dp.Wo, 4) * (dp.CP / 8);
+                        (dp.sw == 1 || dp.sw == 2) && (dp.sh == 1 || dp.sh == 2)) {
                         const bf16* xi = (const bf16*)pp->ptr(in);
                         bf16* yo = (bf16*)pp->ptr(out);
-                        int g = grid_for(strips);
-                        if (dp.kw == 3 && dp.sw == 1) dwconv_strip_kernel<3, 1><<<g, 256, 0, st>>>(xi, wb16, bptr, yo, dp);
-                        else if (dp.kw == 3) dwconv_strip_kernel<3, 2><<<g, 256, 0, st>>>(xi, wb16, bptr, yo, dp);
-                        else if (dp.sw == 1) dwconv_strip_kernel<5, 1><<<g, 256, 0, st>>>(xi, wb16, bptr, yo, dp);
-                        else dwconv_strip_kernel<5, 2><<<g, 256, 0, st>>>(xi, wb16, bptr, yo, dp);
+                        int key = dp.kw * 100 + dp.sh * 10 + dp.sw;
+                        switch (key) {
+                            case 311: launch_dwconv_tile<3, 1, 1>(xi, wb16, bptr, yo, dp, st); break;
+                            case 312: launch_dwconv_tile<3, 1, 2>(xi, wb16, bptr, yo, dp, st); break;
+                            case 321: launch_dwconv_tile<3, 2, 1>(xi, wb16, bptr, yo, dp, st); break;
+                            case 322: launch_dwconv_tile<3, 2, 2>(xi, wb16, bptr, yo, dp, st); break;
+                            case 511: launch_dwconv_tile<5, 1, 1>(xi, wb16, bptr, yo, dp, st); break;
+                            case 512: launch_dwconv_tile<5, 1, 2>(xi, wb16, bptr, yo, dp, st); break;
+                            case 521: launch_dwconv_tile<5, 2, 1>(xi, wb16, bptr, yo, dp, st); break;
+                            default: launch_dwconv_tile<5, 2, 2>(xi, wb16, bptr, yo, dp, st); break;
+                        }
                         return;
                     }
                     dwconv_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)pp->ptr(in), wptr, bptr, (T*)pp->ptr(out), dp);

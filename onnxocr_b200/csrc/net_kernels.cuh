@@ -347,6 +347,128 @@ __global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restric
     }
 }
 
+// Depthwise convolution with the input tile (halo included) staged in shared memory by coalesced 16-byte loads; each
+// thread owns one 8-channel group and walks the pixels of the 16 x 8 output tile assigned to it.  3x3 weights live in
+// registers (packed bf16), 5x5 weights in shared memory.  HBM traffic = input + output once; the k^2 re-reads hit smem.
+// CC = channels per block (16 / 32 / 64), chosen on the host to minimise channel padding.
+template <int K, int SH, int SW, int CC>
+__global__ void __launch_bounds__(256) dwconv_tile_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                           const float* __restrict__ bias, bf16* __restrict__ y, const DwP p,
+                                                           int tiles_x, int tiles_y) {
+    constexpr int TW = 16, TH = 8, G = CC / 8;
+    constexpr int IR = (TH - 1) * SH + K, IC = (TW - 1) * SW + K;
+    constexpr int SLOTS = 256 / G;                // pixels handled per pass
+    constexpr int PASSES = (TW * TH) / SLOTS;
+    constexpr bool W_SMEM = K > 3;
+    extern __shared__ uint4 tile[];               // [IR][IC][G] (+ [K*K][G] weights when W_SMEM)
+    uint4* wsm = tile + IR * IC * G;
+    int t = blockIdx.x;
+    const int tx = t % tiles_x;
+    t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int n = t / tiles_y;
+    const int x0 = tx * TW, y0 = ty * TH;
+    const int c0 = blockIdx.y * CC;
+    const int iy0 = y0 * SH - p.pt, ix0 = x0 * SW - p.pl;
+    for (int i = threadIdx.x; i < IR * IC * G; i += 256) {
+        int gi = i % G, pix = i / G;
+        int ic = pix % IC, ir = pix / IC;
+        int iy = iy0 + ir, ix = ix0 + ic, ch = c0 + gi * 8;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W && ch < p.CP)
+            v = *reinterpret_cast<const uint4*>(x + (((int64_t)n * p.H + iy) * p.W + ix) * p.CP + ch);
+        tile[i] = v;
+    }
+    const int g = threadIdx.x % G, slot = threadIdx.x / G;
+    const int c = c0 + g * 8;
+    const bool active = c < p.CP;
+    uint4 wreg[W_SMEM ? 1 : K * K];
+    if (W_SMEM) {
+        for (int i = threadIdx.x; i < K * K * G; i += 256) {
+            int gi = i % G, k = i / G;
+            int ch = c0 + gi * 8;
+            wsm[i] = ch < p.CP ? *reinterpret_cast<const uint4*>(w + (int64_t)k * p.CP + ch) : make_uint4(0, 0, 0, 0);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K * K; ++k)
+            wreg[k] = active ? *reinterpret_cast<const uint4*>(w + (int64_t)k * p.CP + c) : make_uint4(0, 0, 0, 0);
+    }
+    float bb[8];
+    {
+        float4 b0 = active ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0, 0, 0, 0);
+        float4 b1 = active ? *reinterpret_cast<const float4*>(bias + c + 4) : make_float4(0, 0, 0, 0);
+        bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+    }
+    __syncthreads();
+    if (!active) return;
+#pragma unroll
+    for (int it = 0; it < PASSES; ++it) {
+        int pixel = slot + it * SLOTS;
+        int py = pixel / TW, px = pixel % TW;
+        int oy = y0 + py, ox = x0 + px;
+        if (oy >= p.Ho || ox >= p.Wo) continue;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = bb[j];
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                uint4 v = tile[((py * SH + ky) * IC + (px * SW + kx)) * G + g];
+                uint4 ww = W_SMEM ? wsm[(ky * K + kx) * G + g] : wreg[W_SMEM ? 0 : ky * K + kx];
+                acc[0] = fmaf(__uint_as_float(v.x << 16), __uint_as_float(ww.x << 16), acc[0]);
+                acc[1] = fmaf(__uint_as_float(v.x & 0xffff0000u), __uint_as_float(ww.x & 0xffff0000u), acc[1]);
+                acc[2] = fmaf(__uint_as_float(v.y << 16), __uint_as_float(ww.y << 16), acc[2]);
+                acc[3] = fmaf(__uint_as_float(v.y & 0xffff0000u), __uint_as_float(ww.y & 0xffff0000u), acc[3]);
+                acc[4] = fmaf(__uint_as_float(v.z << 16), __uint_as_float(ww.z << 16), acc[4]);
+                acc[5] = fmaf(__uint_as_float(v.z & 0xffff0000u), __uint_as_float(ww.z & 0xffff0000u), acc[5]);
+                acc[6] = fmaf(__uint_as_float(v.w << 16), __uint_as_float(ww.w << 16), acc[6]);
+                acc[7] = fmaf(__uint_as_float(v.w & 0xffff0000u), __uint_as_float(ww.w & 0xffff0000u), acc[7]);
+            }
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (c + j < p.C) ? epi_apply(acc[j], p.epi) : 0.f;
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(o[0], o[1]);
+        __nv_bfloat162 t1 = __floats2bfloat162_rn(o[2], o[3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(o[4], o[5]);
+        __nv_bfloat162 t3 = __floats2bfloat162_rn(o[6], o[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0);
+        pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2);
+        pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(y + (((int64_t)n * p.Ho + oy) * p.Wo + ox) * p.CP + c) = pk;
+    }
+}
+
+template <int K, int SH, int SW, int CC>
+inline void launch_dwconv_tile_cc(const bf16* x, const bf16* w, const float* bias, bf16* y, const DwP& p, cudaStream_t st) {
+    constexpr int TW = 16, TH = 8, G = CC / 8;
+    constexpr int IR = (TH - 1) * SH + K, IC = (TW - 1) * SW + K;
+    constexpr size_t smem = ((size_t)IR * IC * G + (K > 3 ? K * K * G : 0)) * 16;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(dwconv_tile_kernel<K, SH, SW, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
+    dim3 grid((unsigned)(tiles_x * tiles_y * p.N), (unsigned)((p.CP + CC - 1) / CC));
+    dwconv_tile_kernel<K, SH, SW, CC><<<grid, 256, smem, st>>>(x, w, bias, y, p, tiles_x, tiles_y);
+}
+
+template <int K, int SH, int SW>
+inline void launch_dwconv_tile(const bf16* x, const bf16* w, const float* bias, bf16* y, const DwP& p, cudaStream_t st) {
+    // channels per block: the candidate with the least channel padding, larger preferred; 16 only for narrow tensors
+    auto padded = [&](int cc) { return (p.CP + cc - 1) / cc * cc; };
+    int cc = 64;
+    if (padded(32) < padded(cc)) cc = 32;
+    if (p.CP <= 48 && padded(16) < padded(cc)) cc = 16;
+    if (cc == 64) launch_dwconv_tile_cc<K, SH, SW, 64>(x, w, bias, y, p, st);
+    else if (cc == 32) launch_dwconv_tile_cc<K, SH, SW, 32>(x, w, bias, y, p, st);
+    else launch_dwconv_tile_cc<K, SH, SW, 16>(x, w, bias, y, p, st);
+}
+
 // ----------------------------------------------------------------------------------------
 // global average pool (deterministic two-stage) + squeeze-excite
 // ----------------------------------------------------------------------------------------
