@@ -1,0 +1,55 @@
+"""Page sharding across GPUs: one process (one engine, one stream) per GPU, page i -> rank i mod world, host-side gather
+by page index.  Mirrors how the reference back-fills `pdf_text[i]` from its thread pool (ocr_images_pdfs.py:154-158).
+Pages are independent through det -> crop -> cls -> rec (predict_system.py:35-72), so no collective touches the data
+path; torch.distributed (NCCL on GPUs, gloo in the CPU tests) only carries the small result objects to rank 0.
+"""
+import os
+
+
+def rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def shard_indices(n_items, rank, world):
+    """Indices of the pages rank `rank` processes (round-robin keeps mixed-size pages balanced)."""
+    return list(range(rank, n_items, world))
+
+
+def process_shard(pages, fn, rank, world):
+    """Runs fn(page) on this rank's pages; returns [(page_index, result), ...]."""
+    return [(i, fn(pages[i])) for i in shard_indices(len(pages), rank, world)]
+
+
+def gather_by_page(local, n_items, group=None):
+    """All ranks call this; rank 0 receives the results in page order (others get None)."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        out = [None] * n_items
+        for i, r in local:
+            out[i] = r
+        return out
+    world = dist.get_world_size(group)
+    bucket = [None] * world if dist.get_rank(group) == 0 else None
+    dist.gather_object(local, bucket, dst=0, group=group)
+    if dist.get_rank(group) != 0:
+        return None
+    out = [None] * n_items
+    for part in bucket:
+        for i, r in part:
+            if out[i] is not None:
+                raise RuntimeError("page %d was processed by two ranks" % i)
+            out[i] = r
+    missing = [i for i, r in enumerate(out) if r is None]
+    if missing:
+        raise RuntimeError("pages %s were not processed by any rank" % missing[:8])
+    return out
+
+
+def ocr_pages_sharded(pages, fn, group=None):
+    """fn(page) -> result on every rank's shard, gathered on rank 0 in page order."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    return gather_by_page(process_shard(pages, fn, rank, world), len(pages), group)

