@@ -126,6 +126,40 @@ int b200ocr_rec_crops(b200ocr_engine* e, const uint8_t* const* crops, const int*
                       int batch_num, const uint8_t* rotate180, int32_t* ids_out, int max_len, int* lens_out,
                       float* scores_out);
 
+/* session.run on the rec graph fused with `preds.argmax(axis=2)` / `preds.max(axis=2)` (predict_rec.py:316,
+ * rec_postprocess.py:100-101): for the NCHW float32 batch `nchw` [dims] writes, per sample and time step, the class
+ * index and its softmax probability (idx_out / prob_out: [dims[0]][T], T returned in *steps_out).  The
+ * [n, T, classes] probability tensor is never materialised in bf16 mode (tcgen05 GEMM with an online
+ * softmax / argmax epilogue).  Call with idx_out == NULL to query T. */
+int b200ocr_rec_argmax(b200ocr_engine* e, const float* nchw, const int64_t dims[4], int32_t* idx_out, float* prob_out,
+                       int capacity, int* steps_out);
+
+/* ---- fused end to end (Level C) --------------------------------------------------------- */
+typedef struct b200ocr_ocr_params {
+    b200ocr_det_params det;
+    int use_angle_cls;        /* args.use_angle_cls (predict_system.py:20,57): run the classifier and rotate flagged crops */
+    float cls_thresh;         /* args.cls_thresh 0.9: rotate when '180' in label and score > cls_thresh (predict_cls.py:85) */
+    unsigned cls_rot_label_mask; /* bit i set <=> '180' in label_list[i]  (label_list ['0','180'] -> 0x2)  utils.py:351 */
+    int rec_batch_num;        /* args.rec_batch_num 6: fixes each crop's padded width imgW exactly as the reference's
+                                 per-page batches do (predict_rec.py:290-300); device batches are formed across pages */
+    int rec_width_bucket;     /* 0: imgW exactly as the reference; k > 0: imgW rounded up to a multiple of k (fewer,
+                                 larger device batches; results then differ from the reference like a different
+                                 rec_batch_num would) */
+} b200ocr_ocr_params;
+
+void b200ocr_ocr_params_default(b200ocr_ocr_params* p);
+
+/* TextSystem.__call__ (predict_system.py:35-72) for a batch of pages, device resident between the stages:
+ * det -> filter_tag_det_res -> sorted_boxes -> get_rotate_crop_image (every crop of every page in one launch) ->
+ * [cls -> rotate 180] -> rec -> CTC decode.  Lines are returned page after page in sorted_boxes order:
+ * n_boxes_out[i] lines for page i; boxes_out float32 [line_cap][4][2]; ids_out int32 [line_cap][max_len] with
+ * lens_out[l] valid entries; scores_out float32 [line_cap] (the caller applies drop_score, predict_system.py:66-70);
+ * cls_labels_out / cls_scores_out (optional) [line_cap].  Needs the det and rec models (and cls when use_angle_cls). */
+int b200ocr_ocr_pages(b200ocr_engine* e, const uint8_t* const* pages, const int* hs, const int* ws, const int* strides,
+                      int n, const b200ocr_ocr_params* p, float* boxes_out, int line_cap, int* n_boxes_out,
+                      int32_t* ids_out, int max_len, int* lens_out, float* scores_out, int32_t* cls_labels_out,
+                      float* cls_scores_out);
+
 /* ---- diagnostics ------------------------------------------------------------------------ */
 /* Text dump of the canonical graph of a loaded model (for tests / INTEGRATION.md). */
 int b200ocr_describe(b200ocr_engine* e, int kind, char* buf, size_t cap);
@@ -148,6 +182,9 @@ int64_t b200ocr_launch_count(const b200ocr_engine* e);
 /* Device time (ms, CUDA events on the engine stream) of the stages of the last fused call:
  * [0] preprocess  [1] network  [2] post-process  [3] total. */
 int b200ocr_stage_times(b200ocr_engine* e, float ms_out[4]);
+/* Host wall-clock split of the last b200ocr_ocr_pages call (ms): page upload enqueue, det incl. box read-back,
+ * host box sorting / crop planning, warp + cls enqueue, rec enqueue, final drain. */
+int b200ocr_ocr_stage_times(b200ocr_engine* e, float ms_out[6]);
 
 /* ---- device-resident benchmarking hooks (bench.py `value`: inputs already in HBM) ------- */
 /* Uploads pages once; b200ocr_det_resident_run then repeats preprocess -> DBNet -> DBPostProcess

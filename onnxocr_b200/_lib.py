@@ -25,6 +25,11 @@ class DetParams(C.Structure):
                 ("box_thresh", C.c_double), ("unclip_ratio", C.c_double)]
 
 
+class OcrParams(C.Structure):
+    _fields_ = [("det", DetParams), ("use_angle_cls", C.c_int), ("cls_thresh", C.c_float),
+                ("cls_rot_label_mask", C.c_uint), ("rec_batch_num", C.c_int), ("rec_width_bucket", C.c_int)]
+
+
 _LIMIT_TYPES = {"max": 0, "min": 1, "resize_long": 2}
 
 
@@ -32,6 +37,16 @@ def det_params(limit_side_len=960, limit_type="max", thresh=0.3, box_thresh=0.6,
                max_candidates=1000, min_size=3, use_dilation=False):
     return DetParams(float(limit_side_len), _LIMIT_TYPES[limit_type], float(thresh), int(max_candidates),
                      int(min_size), int(bool(use_dilation)), float(box_thresh), float(unclip_ratio))
+
+
+def ocr_params(det=None, use_angle_cls=False, cls_thresh=0.9, label_list=("0", "180"), rec_batch_num=6,
+               rec_width_bucket=0):
+    mask = 0
+    for i, lab in enumerate(label_list):
+        if "180" in lab:
+            mask |= 1 << i
+    return OcrParams(det or det_params(), int(bool(use_angle_cls)), float(cls_thresh), mask, int(rec_batch_num),
+                     int(rec_width_bucket))
 
 
 def lib():
@@ -65,6 +80,10 @@ def lib():
         L.b200ocr_crop_boxes.argtypes = [vp, vp, i, i, i, vp, i, vp, sz, pi]
         L.b200ocr_cls_crops.argtypes = [vp, C.POINTER(vp), pi, pi, i, i, vp, vp]
         L.b200ocr_rec_crops.argtypes = [vp, C.POINTER(vp), pi, pi, i, i, vp, vp, i, pi, vp]
+        L.b200ocr_rec_argmax.argtypes = [vp, vp, pi64, vp, vp, i, pi]
+        L.b200ocr_ocr_params_default.argtypes = [C.POINTER(OcrParams)]
+        L.b200ocr_ocr_params_default.restype = None
+        L.b200ocr_ocr_pages.argtypes = [vp, C.POINTER(vp), pi, pi, pi, i, C.POINTER(OcrParams), vp, i, pi, vp, i, vp, vp, vp, vp]
         L.b200ocr_describe.argtypes = [vp, i, C.c_char_p, sz]
         L.b200ocr_plan_stats.argtypes = [vp, i, i, i, i, pd, pi, pd]
         L.b200ocr_profile_plan.argtypes = [vp, i, i, i, i, i, pf, pd, pd, i, C.c_char_p, sz]
@@ -76,6 +95,7 @@ def lib():
         L.b200ocr_launch_count.argtypes = [vp]
         L.b200ocr_launch_count.restype = C.c_int64
         L.b200ocr_stage_times.argtypes = [vp, pf]
+        L.b200ocr_ocr_stage_times.argtypes = [vp, pf]
         L.b200ocr_det_resident_upload.argtypes = [vp, C.POINTER(vp), pi, pi, pi, i]
         L.b200ocr_det_resident_run.argtypes = [vp, C.POINTER(DetParams), i, pf, pi, pf]
         _lib = L
@@ -147,6 +167,17 @@ class Engine(object):
         self._check(self._L.b200ocr_session_run(self._h, kind, _ptr(x), dims, _ptr(out), out.size, od, C.byref(r)))
         return out
 
+    def rec_argmax(self, x):
+        """rec session.run fused with argmax/max over the classes: float32 NCHW -> (int32 [n,T], float32 [n,T])."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        dims = (C.c_int64 * 4)(*x.shape)
+        t = C.c_int()
+        self._check(self._L.b200ocr_rec_argmax(self._h, _ptr(x), dims, None, None, 0, C.byref(t)))
+        idx = np.zeros((x.shape[0], t.value), np.int32)
+        prob = np.zeros((x.shape[0], t.value), np.float32)
+        self._check(self._L.b200ocr_rec_argmax(self._h, _ptr(x), dims, _ptr(idx), _ptr(prob), idx.size, C.byref(t)))
+        return idx, prob
+
     def describe(self, kind):
         buf = C.create_string_buffer(1 << 20)
         self._check(self._L.b200ocr_describe(self._h, kind, buf, len(buf)))
@@ -192,6 +223,11 @@ class Engine(object):
         return list(ms)
 
     # ---- Level B -----------------------------------------------------------------
+    def ocr_stage_times(self):
+        ms = (C.c_float * 6)()
+        self._check(self._L.b200ocr_ocr_stage_times(self._h, ms))
+        return dict(zip(["upload", "det", "host_plan", "warp_cls", "rec", "drain"], [float(v) for v in ms]))
+
     def det_preprocess(self, img, params=None):
         """-> (chw float32 [1,3,H,W], shape float64[4]) like transform(data, ops) in predict_det.py:98."""
         params = params or det_params()
@@ -300,6 +336,48 @@ class Engine(object):
             self._check(self._L.b200ocr_rec_crops(self._h, ptrs, hs, ws, n, batch_num, _ptr(rot) if rot is not None else None,
                                                   _ptr(ids), max_len, lens, _ptr(scores)))
         return [ids[i, :lens[i]].copy() for i in range(n)], scores[:n]
+
+    def ocr_pages(self, pages, params=None, line_cap=None, max_len=160):
+        """TextSystem.__call__ for a batch of pages in one call (Level C).  -> per page a dict with
+        boxes float32 [m,4,2] (sorted_boxes order), ids (list of int32 arrays), scores float32 [m],
+        cls_labels int32 [m], cls_scores float32 [m] (zeros when the classifier is off)."""
+        params = params or ocr_params()
+        pages = [np.ascontiguousarray(p, dtype=np.uint8) for p in pages]
+        n = len(pages)
+        if n == 0:
+            return []
+        ptrs = (C.c_void_p * n)(*[p.ctypes.data for p in pages])
+        hs, ws = _int_arr([p.shape[0] for p in pages]), _int_arr([p.shape[1] for p in pages])
+        st = _int_arr([p.strides[0] for p in pages])
+        cap = int(line_cap or max(1000, 300 * n))
+        while True:
+            boxes = np.zeros((cap, 4, 2), np.float32)
+            ids = np.zeros((cap, max_len), np.int32)
+            lens = np.zeros((cap,), np.int32)
+            scores = np.zeros((cap,), np.float32)
+            cl = np.zeros((cap,), np.int32)
+            cs = np.zeros((cap,), np.float32)
+            counts = (C.c_int * n)()
+            rc = self._L.b200ocr_ocr_pages(self._h, ptrs, hs, ws, st, n, C.byref(params), _ptr(boxes), cap, counts, _ptr(ids),
+                                           max_len, _ptr(lens), _ptr(scores), _ptr(cl), _ptr(cs))
+            if rc == -4 and cap < 1000 * n:            # B200OCR_E_CAPACITY: more lines than assumed
+                cap = 1000 * n
+                continue
+            self._check(rc)
+            total = sum(counts[i] for i in range(n))
+            longest = int(lens[:total].max()) if total else 0
+            if longest > max_len:                       # a line longer than the id buffer: rerun with room for it
+                max_len = longest + 8
+                continue
+            break
+        out, off = [], 0
+        for i in range(n):
+            m = counts[i]
+            sl = slice(off, off + m)
+            out.append({"boxes": boxes[sl].copy(), "ids": [ids[off + k, :lens[off + k]].copy() for k in range(m)],
+                        "scores": scores[sl].copy(), "cls_labels": cl[sl].copy(), "cls_scores": cs[sl].copy()})
+            off += m
+        return out
 
     def det_resident_upload(self, pages):
         pages = [np.ascontiguousarray(p, dtype=np.uint8) for p in pages]

@@ -233,6 +233,46 @@ int b200ocr_rec_crops(b200ocr_engine* e, const uint8_t* const* crops, const int*
     });
 }
 
+int b200ocr_rec_argmax(b200ocr_engine* e, const float* nchw, const int64_t dims[4], int32_t* idx_out, float* prob_out,
+                       int capacity, int* steps_out) {
+    return guarded(e, [&]() {
+        if (!nchw || !dims) throw std::runtime_error("bad argument to rec_argmax");
+        Model* m = need(e, B200OCR_REC);
+        std::lock_guard<std::mutex> lk(e->mu);
+        e->stages->rec_argmax_host(m, nchw, (int)dims[0], (int)dims[1], (int)dims[2], (int)dims[3], idx_out, prob_out, capacity,
+                                   steps_out);
+        return B200OCR_OK;
+    });
+}
+
+void b200ocr_ocr_params_default(b200ocr_ocr_params* p) {
+    if (!p) return;
+    b200ocr_det_params_default(&p->det);
+    p->use_angle_cls = 0;
+    p->cls_thresh = 0.9f;
+    p->cls_rot_label_mask = 0x2u;
+    p->rec_batch_num = 6;
+    p->rec_width_bucket = 0;
+}
+
+int b200ocr_ocr_pages(b200ocr_engine* e, const uint8_t* const* pages, const int* hs, const int* ws, const int* strides,
+                      int n, const b200ocr_ocr_params* p, float* boxes_out, int line_cap, int* n_boxes_out,
+                      int32_t* ids_out, int max_len, int* lens_out, float* scores_out, int32_t* cls_labels_out,
+                      float* cls_scores_out) {
+    return guarded(e, [&]() {
+        if (!pages || !hs || !ws || !p || n < 0 || !boxes_out || !n_boxes_out || !ids_out || !lens_out || !scores_out ||
+            line_cap <= 0 || max_len <= 0)
+            throw std::runtime_error("bad argument to ocr_pages");
+        Model* det = need(e, B200OCR_DET);
+        Model* rec = need(e, B200OCR_REC);
+        Model* cls = p->use_angle_cls ? need(e, B200OCR_CLS) : nullptr;
+        std::lock_guard<std::mutex> lk(e->mu);
+        e->stages->ocr_pages(det, cls, rec, pages, hs, ws, strides, n, *p, boxes_out, line_cap, n_boxes_out, ids_out, max_len,
+                             lens_out, scores_out, cls_labels_out, cls_scores_out);
+        return B200OCR_OK;
+    });
+}
+
 int b200ocr_describe(b200ocr_engine* e, int kind, char* buf, size_t cap) {
     return guarded(e, [&]() {
         Model* m = need(e, kind);
@@ -306,6 +346,13 @@ int64_t b200ocr_launch_count(const b200ocr_engine* e) { return e && e->stages ? 
 int b200ocr_stage_times(b200ocr_engine* e, float ms_out[4]) {
     return guarded(e, [&]() {
         for (int i = 0; i < 4; ++i) ms_out[i] = e->stages->stage_ms[i];
+        return B200OCR_OK;
+    });
+}
+
+int b200ocr_ocr_stage_times(b200ocr_engine* e, float ms_out[6]) {
+    return guarded(e, [&]() {
+        for (int i = 0; i < 6; ++i) ms_out[i] = e->stages->ocr_ms[i];
         return B200OCR_OK;
     });
 }

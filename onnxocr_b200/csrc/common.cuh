@@ -81,4 +81,18 @@ __device__ __forceinline__ float epi_apply(float v, const Epilogue& e) {
     return v;
 }
 
+// Compiled epilogue with the activation fixed at compile time (ACT < 0: interpret the chain).
+template <int ACT>
+__device__ __forceinline__ float epi_fast(float v, const Epilogue& e) {
+    if (ACT < 0) return epi_apply(v, e);                 // generic (interpreted) chain
+    v = fmaf(v, e.a0, e.b0);
+    if (ACT == EPI_RELU) v = fmaxf(v, 0.f);
+    else if (ACT == EPI_HSWISH) v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * 0.16666667f;
+    else if (ACT == EPI_SIGMOID) v = __fdividef(1.f, 1.f + __expf(-v));
+    else if (ACT == EPI_SWISH) v = __fdividef(v, 1.f + __expf(-v));
+    else if (ACT == EPI_HSIGMOID) v = fminf(fmaxf(fmaf(v, e.pa, e.pb), 0.f), 1.f);
+    else if (ACT == EPI_CLIP) v = fminf(fmaxf(v, e.pa), e.pb);
+    return fmaf(v, e.a1, e.b1);
+}
+
 }  // namespace b200ocr

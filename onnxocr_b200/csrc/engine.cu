@@ -84,6 +84,15 @@ static bool tc_enabled() {
     return v == 1;
 }
 
+static bool dw_strip_enabled() {          // B200OCR_DW=tile selects the previous depthwise kernel (A/B measurements)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200OCR_DW");
+        v = (e && std::string(e) == "tile") ? 0 : 1;
+    }
+    return v == 1;
+}
+
 struct TcState {            // per conv step: tensor maps, re-encoded when the activation slab moves
     CUtensorMap map_a, map_b;
     const void* a_ptr = nullptr;
@@ -153,6 +162,11 @@ Model::Model(const std::string& path, int precision) : prec_(precision) {
             std::vector<float> tb(rows + 128, 0.f);
             for (int co = 0; co < cw.cout; ++co) tb[co] = cw.bias[co];
             d.tc_bias = upload(tb);
+            if (taps == 1 && bn == 128 && kchunks <= 4) {             // candidate CTC head (Linear with >= 65 outputs)
+                std::vector<float> hb(rows + 128, -1.0e30f);
+                for (int co = 0; co < cw.cout; ++co) hb[co] = cw.bias[co];
+                d.head_bias = upload(hb);
+            }
             d.tc_bn = bn;
             d.tc_rows = rows;
             d.tc_k = (int)K;
@@ -197,6 +211,7 @@ Model::~Model() {
         if (d.w) cudaFree(d.w);
         if (d.bias) cudaFree(d.bias);
         if (d.w_bf16) cudaFree(d.w_bf16);
+        if (d.head_bias) cudaFree(d.head_bias);
         if (d.tc_bias) cudaFree(d.tc_bias);
     }
     for (auto& v : dvec_) {
@@ -301,19 +316,23 @@ struct Arena {
 };
 }  // namespace
 
-Plan* Model::plan_for(int n, int h, int w) {
-    std::vector<int> key{n, h, w};
+Plan* Model::plan_for(int n, int h, int w, bool head) {
+    std::vector<int> key{n, h, w, head ? 1 : 0};
     auto it = plans_.find(key);
     if (it != plans_.end()) return it->second.get();
-    if (plans_.size() >= 96) plans_.clear();            // bounded cache (dynamic rec widths)
-    std::unique_ptr<Plan> p = build_plan(n, h, w);
+    if (plans_.size() >= 768) {                         // bounded cache (dynamic rec widths x batch sizes)
+        B200_CUDA_CHECK(cudaDeviceSynchronize());
+        plans_.clear();
+    }
+    std::unique_ptr<Plan> p = build_plan(n, h, w, head);
     Plan* raw = p.get();
     plans_[key] = std::move(p);
     return raw;
 }
 
-std::unique_ptr<Plan> Model::build_plan(int n, int h, int w) {
+std::unique_ptr<Plan> Model::build_plan(int n, int h, int w, bool head) {
     std::unique_ptr<Plan> p(new Plan());
+    p->head_mode = head;
     p->model_arena = &arena_;
     p->n = n;
     p->h = h;
@@ -483,6 +502,68 @@ void Model::build_steps(Plan& p) {
                 bool same = !convt && c.sh == 1 && c.sw == 1 && Ho == iv.h && Wo == iv.w;
                 bool pointwise = same && c.kh == 1 && c.kw == 1;
                 bool tc_ct = convt && cp.CoutP % 8 == 0;
+                // ---- fused CTC head: Linear -> Softmax (graph output) -> argmax / max, logits never materialised
+                if (p.head_mode && std::is_same<T, bf16>::value && tc_enabled() && c.is_linear && c.epi.n == 0 && dw.head_bias &&
+                    iv.cp % 8 == 0 && (iv.cp + tc::BK - 1) / tc::BK <= tc::HEAD_MAX_KB && ni + 1 < g.nodes.size() &&
+                    g.nodes[ni + 1].kind == C_SOFTMAX && g.nodes[ni + 1].in[0] == c.out && nuse[c.out] == 1 &&
+                    g.nodes[ni + 1].out == g.output_name && (iv.form == F_NSC || iv.form == F_NHWC)) {
+                    int rows = iv.n * iv.h * iv.w;
+                    int n_tiles = dw.tc_rows / tc::HEAD_BN;
+                    int m_tiles = (int)ceil_div(rows, tc::BM);
+                    int splits = std::max(1, std::min({16, n_tiles, (int)ceil_div(2 * 148, m_tiles)}));
+                    int per = (int)ceil_div(n_tiles, splits);
+                    splits = (int)ceil_div(n_tiles, per);
+                    int kblocks = (iv.cp + tc::BK - 1) / tc::BK;
+                    int b_pmax = new_buf((size_t)splits * rows * 4), b_pidx = new_buf((size_t)splits * rows * 4),
+                        b_psum = new_buf((size_t)splits * rows * 4);
+                    p.head_idx_buf = new_buf((size_t)rows * 4);
+                    p.head_prob_buf = new_buf((size_t)rows * 4);
+                    for (int b : {b_pmax, b_pidx, b_psum, p.head_idx_buf, p.head_prob_buf}) buf_last[b] = (int)g.nodes.size();
+                    p.head_rows = rows;
+                    p.head_T = iv.h * iv.w;
+                    std::shared_ptr<TcState> ts(new TcState());
+                    {
+                        uint64_t dims[2] = {(uint64_t)dw.tc_k, (uint64_t)dw.tc_rows};
+                        uint64_t str[1] = {(uint64_t)dw.tc_k * 2};
+                        uint32_t box[2] = {(uint32_t)tc::BK, (uint32_t)tc::HEAD_BN};
+                        make_tmap(&ts->map_b, dw.w_bf16, 2, dims, str, box);
+                    }
+                    tc::HeadParams hp;
+                    hp.rows = rows; hp.n_tiles = n_tiles; hp.tiles_per_split = per; hp.kblocks = kblocks;
+                    const float* hbias = dw.head_bias;
+                    int icp = iv.cp, ib_idx = p.head_idx_buf, ib_prob = p.head_prob_buf;
+                    size_t smem = tc::head_smem_bytes(kblocks);
+                    cost_flops = 2.0 * rows * (double)c.cout * c.cin;
+                    cost_bytes = vbytes(in) + (double)c.cout * c.cin * esz + (double)rows * 8;
+                    p.flops += cost_flops;
+                    use(in);
+                    emit("ctc_head " + c.name, [=](cudaStream_t st) {
+                        const void* x = pp->ptr(in);
+                        if (ts->a_ptr != x) {
+                            uint64_t dims[2] = {(uint64_t)icp, (uint64_t)rows};
+                            uint64_t str[1] = {(uint64_t)icp * 2};
+                            uint32_t box[2] = {(uint32_t)tc::BK, (uint32_t)tc::BM};
+                            make_tmap(&ts->map_a, x, 2, dims, str, box);
+                            ts->a_ptr = x;
+                        }
+                        cudaFuncSetAttribute(tc::ctc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        tc::ctc_head_kernel<<<dim3(m_tiles, splits), tc::kThreads, smem, st>>>(
+                            ts->map_a, ts->map_b, hbias, (float*)pp->bufptr(b_pmax), (int*)pp->bufptr(b_pidx),
+                            (float*)pp->bufptr(b_psum), hp);
+                    });
+                    emit("ctc_head_merge " + c.name, [=](cudaStream_t st) {
+                        tc::ctc_head_merge_kernel<<<(unsigned)ceil_div(rows, 128), 128, 0, st>>>(
+                            (const float*)pp->bufptr(b_pmax), (const int*)pp->bufptr(b_pidx), (const float*)pp->bufptr(b_psum),
+                            splits, rows, (int*)pp->bufptr(ib_idx), (float*)pp->bufptr(ib_prob));
+                    });
+                    PVal ov = iv;                           // logical [n, T, classes]; lives only as idx / prob
+                    ov.c = c.cout; ov.cp = cpad_of(c.cout); ov.root = -1; ov.form = iv.form;
+                    p.vals.push_back(ov);
+                    vid[g.nodes[ni + 1].out] = (int)p.vals.size() - 1;
+                    p.out_written_dense = true;
+                    skip[ni + 1] = 1;
+                    break;
+                }
                 if (std::is_same<T, bf16>::value && tc_enabled() && (same || tc_ct) && iv.cp % 8 == 0 && cp.CoutP % 8 == 0 && dw.w_bf16) {
                     tc::Params tp;
                     memset(&tp, 0, sizeof(tp));
@@ -612,6 +693,19 @@ void Model::build_steps(Plan& p) {
                         const bf16* xi = (const bf16*)pp->ptr(in);
                         bf16* yo = (bf16*)pp->ptr(out);
                         int key = dp.kw * 100 + dp.sh * 10 + dp.sw;
+                        if (dw_strip_enabled()) {
+                            switch (key) {
+                                case 311: launch_dwconv_strip<3, 1, 1>(xi, wptr, bptr, yo, dp, st); break;
+                                case 312: launch_dwconv_strip<3, 1, 2>(xi, wptr, bptr, yo, dp, st); break;
+                                case 321: launch_dwconv_strip<3, 2, 1>(xi, wptr, bptr, yo, dp, st); break;
+                                case 322: launch_dwconv_strip<3, 2, 2>(xi, wptr, bptr, yo, dp, st); break;
+                                case 511: launch_dwconv_strip<5, 1, 1>(xi, wptr, bptr, yo, dp, st); break;
+                                case 512: launch_dwconv_strip<5, 1, 2>(xi, wptr, bptr, yo, dp, st); break;
+                                case 521: launch_dwconv_strip<5, 2, 1>(xi, wptr, bptr, yo, dp, st); break;
+                                default: launch_dwconv_strip<5, 2, 2>(xi, wptr, bptr, yo, dp, st); break;
+                            }
+                            return;
+                        }
                         switch (key) {
                             case 311: launch_dwconv_tile<3, 1, 1>(xi, wb16, bptr, yo, dp, st); break;
                             case 312: launch_dwconv_tile<3, 1, 2>(xi, wb16, bptr, yo, dp, st); break;
@@ -1033,7 +1127,8 @@ void Model::build_steps(Plan& p) {
             to_dense_f32_kernel<T><<<grid_for(tot), 256, 0, st>>>((const T*)pp->ptr(ov), pp->out_dense, N, C, H, W, CP, to_nchw);
         });
     }
-    B200_CUDA_CHECK(cudaMalloc(&p.out_dense, std::max<size_t>(1, p.out_dense_elems) * sizeof(float)));
+    if (p.head_rows == 0)
+        B200_CUDA_CHECK(cudaMalloc(&p.out_dense, std::max<size_t>(1, p.out_dense_elems) * sizeof(float)));
 
     // ---- liveness-based offsets
     size_t nb = buf_bytes.size();
@@ -1052,8 +1147,65 @@ void Model::build_steps(Plan& p) {
     p.launches = (int)p.steps.size();
 }
 
+static bool graphs_enabled() {            // B200OCR_NO_GRAPH=1: launch every kernel individually (A/B measurements)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200OCR_NO_GRAPH");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// The first launch of a plan runs its kernels one by one (this also performs the lazy one-time work inside the step
+// closures: tensor-map encoding, shared-memory attributes).  The second launch records the same sequence into a CUDA
+// graph; from then on a plan is ONE cudaGraphLaunch, which removes the per-kernel launch latency that dominates the
+// small rec / cls / single-page det batches.  A graph bakes in the activation-slab address, so it is re-recorded when
+// the model's slab has been re-allocated (arena_version).
 void Plan::launch(cudaStream_t st) {
+    if (!graphs_enabled() || steps.size() < 8) {
+        for (auto& s : steps) s(st);
+        return;
+    }
+    if (graph_exec && graph_arena == *model_arena) {
+        if (cudaGraphLaunch(graph_exec, st) == cudaSuccess) return;
+        cudaGetLastError();
+        cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+    }
+    if (graph_exec) {
+        cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+    }
+    if (warm_launches < 1 || warm_arena != *model_arena) {
+        for (auto& s : steps) s(st);
+        warm_launches = 1;
+        warm_arena = *model_arena;
+        return;
+    }
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        for (auto& s : steps) s(st);
+        return;
+    }
     for (auto& s : steps) s(st);
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (e != cudaSuccess || !g) {
+        cudaGetLastError();
+        if (g) cudaGraphDestroy(g);
+        for (auto& s : steps) s(st);              // capture was discarded: nothing has run yet
+        return;
+    }
+    e = cudaGraphInstantiate(&graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        graph_exec = nullptr;
+        for (auto& s : steps) s(st);
+        return;
+    }
+    graph_arena = *model_arena;
+    B200_CUDA_CHECK(cudaGraphLaunch(graph_exec, st));
 }
 
 void Model::profile(int n, int h, int w, int iters, cudaStream_t st, std::vector<float>* ms) {
@@ -1080,11 +1232,9 @@ void Model::profile(int n, int h, int w, int iters, cudaStream_t st, std::vector
     B200_CUDA_CHECK(cudaGetLastError());
 }
 
-void Model::run_host(const float* nchw, int n, int c, int h, int w, std::vector<int64_t>* out_shape, float* out,
-                     size_t out_capacity, cudaStream_t st) {
-    std::lock_guard<std::mutex> lk(mu_);
+Plan* Model::launch_host_input(const float* nchw, int n, int c, int h, int w, cudaStream_t st, bool head) {
     if (c != in_c_) throw std::runtime_error("input has " + std::to_string(c) + " channels, model expects " + std::to_string(in_c_));
-    Plan* p = plan_for(n, h, w);
+    Plan* p = plan_for(n, h, w, head);
     size_t in_bytes = (size_t)n * c * h * w * sizeof(float);
     if (in_bytes > stage_in_bytes_) {
         if (stage_in_) cudaFree(stage_in_);
@@ -1101,6 +1251,13 @@ void Model::run_host(const float* nchw, int n, int c, int h, int w, std::vector<
         nchw_to_nhwc_kernel<float><<<grid_for(tot), 256, 0, st>>>(stage_in_, (float*)p->in_ptr(), n, c, h, w, cp);
     p->launch(st);
     B200_CUDA_CHECK(cudaGetLastError());
+    return p;
+}
+
+void Model::run_host(const float* nchw, int n, int c, int h, int w, std::vector<int64_t>* out_shape, float* out,
+                     size_t out_capacity, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(mu_);
+    Plan* p = launch_host_input(nchw, n, c, h, w, st, false);
     if (out_shape) *out_shape = p->out_shape;
     if (out) {
         if (p->out_dense_elems > out_capacity)

@@ -41,6 +41,7 @@ struct DevWeights {
     float* bias = nullptr;         // [ColsW]
     void* w_bf16 = nullptr;        // tcgen05 operand pack: bf16 [tc_rows][tc_k], K-major (bf16 models only)
     float* tc_bias = nullptr;
+    float* head_bias = nullptr;    // CTC head: bias with -1e30 beyond the last class (padding never wins the argmax)
     int tc_bn = 0, tc_rows = 0, tc_k = 0;
     int K = 0, Kpad = 0, ColsW = 0;
 };
@@ -55,6 +56,11 @@ struct Plan {
     std::vector<std::string> step_names;
     std::vector<double> step_flops, step_bytes;   // algorithmic work per launch (unique in+out+weight bytes)
     int in_val = -1, out_val = -1;
+    // fused CTC head (bf16 rec plans built with head = true): per (b, t) row the argmax class and its softmax value
+    bool head_mode = false;
+    int head_rows = 0, head_T = 0, head_idx_buf = -1, head_prob_buf = -1;
+    const int* head_idx() const { return (const int*)bufptr(head_idx_buf); }
+    const float* head_prob() const { return (const float*)bufptr(head_prob_buf); }
     float* out_dense = nullptr;    // dense fp32 logical output (device)
     size_t out_dense_elems = 0;
     bool out_written_dense = false;
@@ -62,6 +68,9 @@ struct Plan {
     double flops = 0;              // 2*MACs of Conv/ConvT/MatMul at this shape
     int launches = 0;
     cudaGraphExec_t graph_exec = nullptr;
+    const char* graph_arena = nullptr;   // slab address the graph was recorded against
+    const char* warm_arena = nullptr;
+    int warm_launches = 0;
     void* ptr(int v) const { return *model_arena + buf_off[vals[v].root]; }
     void* bufptr(int b) const { return *model_arena + buf_off[b]; }
     void* in_ptr() const { return ptr(in_val); }
@@ -81,7 +90,10 @@ public:
     // Host NCHW fp32 in -> logical fp32 out (the onnxruntime-compatible seam).
     void run_host(const float* nchw, int n, int c, int h, int w, std::vector<int64_t>* out_shape,
                   float* out, size_t out_capacity, cudaStream_t st);
-    Plan* plan_for(int n, int h, int w);
+    // head = true: the final Linear + Softmax run as the fused CTC head (no dense output; see Plan::head_*)
+    Plan* plan_for(int n, int h, int w, bool head = false);
+    // Host NCHW fp32 in -> plan launched on `st` (no synchronisation); head selects the fused CTC head variant.
+    Plan* launch_host_input(const float* nchw, int n, int c, int h, int w, cudaStream_t st, bool head);
     // Per-step device time (ms, averaged over iters) measured with CUDA events between launches.
     void profile(int n, int h, int w, int iters, cudaStream_t st, std::vector<float>* ms);
     size_t elem_size() const { return prec_ == PREC_BF16 ? 2 : 4; }
@@ -91,7 +103,7 @@ public:
     std::string describe() const;
 
 private:
-    std::unique_ptr<Plan> build_plan(int n, int h, int w);
+    std::unique_ptr<Plan> build_plan(int n, int h, int w, bool head);
     template <typename T> void build_steps(Plan& p);
     std::unique_ptr<CGraph> g_;
     int prec_;

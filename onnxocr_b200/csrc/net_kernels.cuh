@@ -469,6 +469,158 @@ inline void launch_dwconv_tile(const bf16* x, const bf16* w, const float* bias, 
     else launch_dwconv_tile_cc<K, SH, SW, 16>(x, w, bias, y, p, st);
 }
 
+// Depthwise convolution, register-sliding form.  The input tile (halo included) is staged in shared memory with
+// 16-byte cp.async copies (zero-filled outside the image); each thread owns ONE 32-bit word (two bf16 channels) of ONE
+// output column and walks down the tile's rows: every input row costs K conflict-free LDS.32 and feeds the K (or
+// ceil(K/SH)) output rows in flight, so the k x k window is read K times instead of K*K times.  The two channels of a
+// word are kept as one packed fp32x2 register pair and accumulated with FFMA2 (fma.rn.f32x2, sm_100): K*K packed FMAs
+// per output pair, weights unpacked once into registers (fp32 — they are never rounded to bf16).
+//   WPP = words per pixel handled by a block (8 / 16 / 32 -> 16 / 32 / 64 channels); TX = 256 / WPP output columns.
+//   PS  = shared-memory pixel stride in words; padded 1.5x for SW == 2 with WPP < 32 so that the lanes of a warp
+//         (which then read every second pixel) still hit 32 distinct banks.
+typedef unsigned long long f32x2_t;             // two fp32 lanes in one 64-bit register pair
+
+__device__ __forceinline__ f32x2_t pack_f32x2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(f32x2_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t bf16x2_to_f32x2(uint32_t u) {
+    return pack_f32x2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ void ffma2(f32x2_t& acc, f32x2_t a, f32x2_t b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
+template <int K, int SH, int SW, int WPP, int TY, int ACT>
+__device__ __forceinline__ void dw_strip_rows(const uint32_t* __restrict__ col, const f32x2_t (&wf)[K * K], f32x2_t bb,
+                                              bf16* __restrict__ yo, int64_t ystride, int rows_in, bool live0, bool live1,
+                                              const Epilogue& epi) {
+    constexpr int TX = 256 / WPP;
+    constexpr int IR = (TY - 1) * SH + K, IC = (TX - 1) * SW + K;
+    constexpr int PS = (SW == 2 && WPP < 32) ? WPP * 3 / 2 : WPP;
+    f32x2_t acc[TY];
+#pragma unroll
+    for (int r = 0; r < IR; ++r) {
+        if (r >= rows_in) break;                  // block-uniform
+        f32x2_t in[K];
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) in[kx] = bf16x2_to_f32x2(col[(r * IC + kx) * PS]);
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            if (r - ky < 0 || (r - ky) % SH != 0 || (r - ky) / SH >= TY) continue;
+            const int oy = (r - ky) / SH;
+            if (ky == 0) acc[oy] = bb;                               // first row that touches this output
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) ffma2(acc[oy], in[kx], wf[ky * K + kx]);
+            if (ky == K - 1) {                                       // last row: output complete
+                float a0, a1;
+                unpack_f32x2(acc[oy], a0, a1);
+                float o0 = live0 ? epi_fast<ACT>(a0, epi) : 0.f;
+                float o1 = live1 ? epi_fast<ACT>(a1, epi) : 0.f;
+                __nv_bfloat162 pk = __floats2bfloat162_rn(o0, o1);
+                *reinterpret_cast<uint32_t*>(yo + (int64_t)oy * ystride) = *reinterpret_cast<uint32_t*>(&pk);
+            }
+        }
+    }
+}
+
+template <int K, int SH, int SW, int WPP, int TY>
+__global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, bf16* __restrict__ y, const DwP p,
+                                                            int tiles_x, int tiles_y) {
+    constexpr int TX = 256 / WPP;
+    constexpr int IR = (TY - 1) * SH + K, IC = (TX - 1) * SW + K;
+    constexpr int PS = (SW == 2 && WPP < 32) ? WPP * 3 / 2 : WPP;
+    constexpr int G = WPP / 4;                    // 16-byte chunks per pixel
+    extern __shared__ uint32_t dw_tile[];         // [IR][IC][PS]
+    int t = blockIdx.x;
+    const int tx = t % tiles_x;
+    t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int n = t / tiles_y;
+    const int x0 = tx * TX, y0 = ty * TY;
+    const int c0 = blockIdx.y * (2 * WPP);
+    const int iy0 = y0 * SH - p.pt, ix0 = x0 * SW - p.pl;
+    const int rows_out = min(TY, p.Ho - y0);
+    const int rows_in = (rows_out - 1) * SH + K;
+    {
+        // thread -> (pixel column block, 16-byte chunk); rows advance by a fixed step so the index math is hoisted
+        const int gi = threadIdx.x % G;
+        const int ch = c0 + gi * 8;
+        const bool ch_ok = ch < p.CP;
+        for (int pix = threadIdx.x / G; pix < rows_in * IC; pix += 256 / G) {
+            int ic = pix % IC, ir = pix / IC;
+            int iy = iy0 + ir, ix = ix0 + ic;
+            bool ok = ch_ok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+            const bf16* src = ok ? x + (((int64_t)n * p.H + iy) * p.W + ix) * p.CP + ch : x;
+            cp_async16_zfill(dw_tile + pix * PS + gi * 4, src, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const int wl = threadIdx.x % WPP, tc = threadIdx.x / WPP;
+    const int c = c0 + 2 * wl;
+    const bool active = c < p.CP && x0 + tc < p.Wo;
+    f32x2_t wf[K * K];
+    f32x2_t bb = 0;
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < K * K; ++k) wf[k] = *reinterpret_cast<const f32x2_t*>(w + (int64_t)k * p.CP + c);
+        bb = *reinterpret_cast<const f32x2_t*>(bias + c);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (!active) return;
+    const bool live0 = c < p.C, live1 = c + 1 < p.C;
+    const uint32_t* col = dw_tile + (tc * SW) * PS + wl;
+    bf16* yo = y + (((int64_t)n * p.Ho + y0) * p.Wo + (x0 + tc)) * p.CP + c;
+    const int64_t ystride = (int64_t)p.Wo * p.CP;
+    // the activation is a launch constant: branch once, run a body compiled for it
+    switch (p.epi.fast ? p.epi.act : -1) {
+        case 0: dw_strip_rows<K, SH, SW, WPP, TY, 0>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi); break;
+        case EPI_RELU: dw_strip_rows<K, SH, SW, WPP, TY, EPI_RELU>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi); break;
+        case EPI_HSWISH: dw_strip_rows<K, SH, SW, WPP, TY, EPI_HSWISH>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi); break;
+        default: dw_strip_rows<K, SH, SW, WPP, TY, -1>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi); break;
+    }
+}
+
+template <int K, int SH, int SW, int WPP>
+inline void launch_dwconv_strip_w(const bf16* x, const float* w, const float* bias, bf16* y, const DwP& p, cudaStream_t st) {
+    constexpr int TY = SH == 2 ? 8 : 16;
+    constexpr int TX = 256 / WPP;
+    constexpr int IR = (TY - 1) * SH + K, IC = (TX - 1) * SW + K;
+    constexpr int PS = (SW == 2 && WPP < 32) ? WPP * 3 / 2 : WPP;
+    constexpr size_t smem = (size_t)IR * IC * PS * 4;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(dwconv_strip_kernel<K, SH, SW, WPP, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    int tiles_x = (p.Wo + TX - 1) / TX, tiles_y = (p.Ho + TY - 1) / TY;
+    dim3 grid((unsigned)(tiles_x * tiles_y * p.N), (unsigned)((p.CP + 2 * WPP - 1) / (2 * WPP)));
+    dwconv_strip_kernel<K, SH, SW, WPP, TY><<<grid, 256, smem, st>>>(x, w, bias, y, p, tiles_x, tiles_y);
+}
+
+template <int K, int SH, int SW>
+inline void launch_dwconv_strip(const bf16* x, const float* w, const float* bias, bf16* y, const DwP& p, cudaStream_t st) {
+    // channels per block: the candidate with the least channel padding, larger preferred
+    auto padded = [&](int cc) { return (p.CP + cc - 1) / cc * cc; };
+    int cc = 64;
+    if (padded(32) < padded(cc)) cc = 32;
+    if (padded(16) < padded(cc)) cc = 16;
+    if (cc == 64) launch_dwconv_strip_w<K, SH, SW, 32>(x, w, bias, y, p, st);
+    else if (cc == 32) launch_dwconv_strip_w<K, SH, SW, 16>(x, w, bias, y, p, st);
+    else launch_dwconv_strip_w<K, SH, SW, 8>(x, w, bias, y, p, st);
+}
+
 // ----------------------------------------------------------------------------------------
 // global average pool (deterministic two-stage) + squeeze-excite
 // ----------------------------------------------------------------------------------------

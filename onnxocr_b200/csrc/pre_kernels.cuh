@@ -123,18 +123,21 @@ __global__ void __launch_bounds__(256) resize_norm_kernel(const ResizeJob* __res
 // ---------------------------------------------------------------------------------------------
 struct WarpJob {
     double mi[9];            // inverse perspective matrix (dst -> src), row major
+    const uint8_t* img;      // source page (HWC u8, device) — crops of several pages share one launch
+    int h, w, stride;        // source size / bytes per row
     int cw, ch;              // warp output size before rotation
     int rot90;               // 1: store np.rot90(dst) (counter-clockwise), output is [cw][ch]
     size_t out_off;          // byte offset of this crop in the pool
 };
 
-__global__ void __launch_bounds__(256) warp_cubic_kernel(const uint8_t* __restrict__ img, int h, int w, int stride,
-                                                          const WarpJob* __restrict__ jobs,
-                                                          const short* __restrict__ tab, uint8_t* __restrict__ pool) {
+__global__ void __launch_bounds__(256) warp_cubic_kernel(const WarpJob* __restrict__ jobs, const short* __restrict__ tab,
+                                                          uint8_t* __restrict__ pool) {
     const WarpJob& j = jobs[blockIdx.z];
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= j.cw || y >= j.ch) return;
+    const uint8_t* __restrict__ img = j.img;
+    const int h = j.h, w = j.w, stride = j.stride;
     double X0 = __dadd_rn(__dmul_rn(j.mi[0], (double)x), __dadd_rn(__dmul_rn(j.mi[1], (double)y), j.mi[2]));
     double Y0 = __dadd_rn(__dmul_rn(j.mi[3], (double)x), __dadd_rn(__dmul_rn(j.mi[4], (double)y), j.mi[5]));
     double W0 = __dadd_rn(__dmul_rn(j.mi[6], (double)x), __dadd_rn(__dmul_rn(j.mi[7], (double)y), j.mi[8]));
@@ -164,6 +167,30 @@ __global__ void __launch_bounds__(256) warp_cubic_kernel(const uint8_t* __restri
     else o = pool + j.out_off + ((size_t)y * j.cw + x) * 3;
 #pragma unroll
     for (int c = 0; c < 3; ++c) o[c] = (uint8_t)min(max((acc[c] + (1 << 14)) >> 15, 0), 255);
+}
+
+// ClsPostProcess (cls_postprocess.py:24-26): argmax over the class probabilities, first maximum wins.
+__global__ void cls_argmax_kernel(const float* __restrict__ probs, int b, int ncls, const int* __restrict__ slots,
+                                  int* __restrict__ labels, float* __restrict__ scores) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= b) return;
+    const float* r = probs + (size_t)k * ncls;
+    int best = 0;
+    for (int c = 1; c < ncls; ++c)
+        if (r[c] > r[best]) best = c;
+    labels[slots[k]] = best;
+    scores[slots[k]] = r[best];
+}
+
+// predict_cls.py:85-88: crops whose label contains '180' with score > cls_thresh are rotated before recognition;
+// the rotation is folded into the rec sampler (SrcView::rot180) instead of rewriting the crop.
+__global__ void rot_patch_kernel(ResizeJob* __restrict__ jobs, const int* __restrict__ slots, int n,
+                                 const int* __restrict__ labels, const float* __restrict__ scores, unsigned rot_mask,
+                                 float thresh) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int i = slots[k];
+    jobs[k].src.rot180 = (((rot_mask >> labels[i]) & 1u) && scores[i] > thresh) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -241,7 +268,7 @@ __global__ void ctc_collapse_kernel(const int* __restrict__ idx, const float* __
             ++n;
         }
     }
-    lens_out[slot] = min(n, max_len);
+    lens_out[slot] = n;                         // untruncated: callers detect n > max_len and retry with room
     scores_out[slot] = n ? __fdiv_rn(np_pairwise_sum(keep, n), (float)n) : 0.f;
 }
 

@@ -1,6 +1,7 @@
 #include "stages.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -280,12 +281,13 @@ void Stages::crop_boxes_host(const uint8_t* bgr, int h, int w, int row_stride, c
     size_t img_bytes = (size_t)h * row_stride;
     uint8_t* d_img = (uint8_t*)d_img_.get(img_bytes);
     B200_CUDA_CHECK(cudaMemcpyAsync(d_img, bgr, img_bytes, cudaMemcpyHostToDevice, st_));
+    for (auto& j : jobs) { j.img = d_img; j.h = h; j.w = w; j.stride = row_stride; }
     WarpJob* d_jobs = (WarpJob*)d_misc_.get(sizeof(WarpJob) * n);
     B200_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(WarpJob) * n, cudaMemcpyHostToDevice, st_));
     uint8_t* d_pool = (uint8_t*)d_crops_.get(off);
     dim3 block(32, 8);
     dim3 grid((unsigned)ceil_div(max_w, 32), (unsigned)ceil_div(max_h, 8), n);
-    warp_cubic_kernel<<<grid, block, 0, st_>>>(d_img, h, w, row_stride, d_jobs, cubic_tab_device(), d_pool);
+    warp_cubic_kernel<<<grid, block, 0, st_>>>(d_jobs, cubic_tab_device(), d_pool);
     launches += 1;
     B200_CUDA_CHECK(cudaGetLastError());
     B200_CUDA_CHECK(cudaMemcpyAsync(crops_out, d_pool, off, cudaMemcpyDeviceToHost, st_));
@@ -376,6 +378,69 @@ void Stages::cls_crops(Model* cls, const uint8_t* const* crops, const int* hs, c
     }
 }
 
+// One device batch of the recogniser: resize/normalise/pad -> SVTR_LCNet -> greedy CTC decode into the slots.
+void Stages::rec_batch(Model* rec, const ResizeJob* d_jobs, const int* d_slots, int b, int img_h, int W, int max_len,
+                       int* d_ids, int* d_lens, float* d_scores) {
+    Plan* p = rec->plan_for(b, img_h, W, /*head=*/true);
+    dim3 grid((unsigned)ceil_div(W, 256), img_h, b);
+    if (rec->precision() == PREC_BF16)
+        resize_norm_kernel<bf16><<<grid, 256, 0, st_>>>(d_jobs, img_h, W, p->in_ptr(), 0, rec_norm());
+    else
+        resize_norm_kernel<float><<<grid, 256, 0, st_>>>(d_jobs, img_h, W, p->in_ptr(), 0, rec_norm());
+    p->launch(st_);
+    if (p->out_shape.size() != 3) throw std::runtime_error("rec model output must be [B, T, classes]");
+    int T = (int)p->out_shape[1], C = (int)p->out_shape[2];
+    int rows = b * T;
+    int* d_idx = (int*)d_batch_.get((size_t)rows * (sizeof(int) + 2 * sizeof(float)));
+    float* d_mx = (float*)(d_idx + rows);
+    float* d_scr = d_mx + rows;
+    if (p->head_rows > 0) {                      // fused CTC head: argmax / max came out of the GEMM epilogue
+        ctc_collapse_kernel<<<(unsigned)ceil_div(b, 64), 64, 0, st_>>>(p->head_idx(), p->head_prob(), b, T, d_slots, max_len,
+                                                                        d_ids, d_lens, d_scores, d_scr);
+        launches += p->launches + 2;
+        B200_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
+    ctc_argmax_kernel<<<rows, 256, 0, st_>>>(p->out_dense, C, d_idx, d_mx);
+    ctc_collapse_kernel<<<(unsigned)ceil_div(b, 64), 64, 0, st_>>>(d_idx, d_mx, b, T, d_slots, max_len, d_ids, d_lens,
+                                                                    d_scores, d_scr);
+    launches += p->launches + 3;
+    B200_CUDA_CHECK(cudaGetLastError());
+}
+
+// session.run + `preds.argmax(axis=2)` / `preds.max(axis=2)` (predict_rec.py:316, rec_postprocess.py:100-101) for a
+// caller-provided NCHW tensor: the per-step class index and its probability, without the [n, T, classes] tensor.
+void Stages::rec_argmax_host(Model* rec, const float* nchw, int n, int c, int h, int w, int32_t* idx_out, float* prob_out,
+                             int capacity, int* T_out) {
+    Plan* p = rec->launch_host_input(nchw, n, c, h, w, st_, /*head=*/true);
+    if (p->out_shape.size() != 3) throw std::runtime_error("rec model output must be [B, T, classes]");
+    int T = (int)p->out_shape[1], C = (int)p->out_shape[2];
+    int rows = n * T;
+    if (T_out) *T_out = T;
+    launches += p->launches + 1;
+    if (!idx_out || !prob_out) {
+        B200_CUDA_CHECK(cudaStreamSynchronize(st_));
+        return;
+    }
+    if (rows > capacity) throw std::runtime_error("output buffer too small: need " + std::to_string(rows) + " rows");
+    const int* d_idx;
+    const float* d_mx;
+    if (p->head_rows > 0) {
+        d_idx = p->head_idx();
+        d_mx = p->head_prob();
+    } else {
+        int* di = (int*)d_batch_.get((size_t)rows * (sizeof(int) + sizeof(float)));
+        float* dm = (float*)(di + rows);
+        ctc_argmax_kernel<<<rows, 256, 0, st_>>>(p->out_dense, C, di, dm);
+        launches += 1;
+        d_idx = di;
+        d_mx = dm;
+    }
+    B200_CUDA_CHECK(cudaMemcpyAsync(idx_out, d_idx, (size_t)rows * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    B200_CUDA_CHECK(cudaMemcpyAsync(prob_out, d_mx, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost, st_));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st_));
+}
+
 void Stages::rec_crops(Model* rec, const uint8_t* const* crops, const int* hs, const int* ws, int n, int batch_num,
                        const uint8_t* rotate180, int32_t* ids_out, int max_len, int* lens_out, float* scores_out) {
     if (n == 0) return;
@@ -413,24 +478,7 @@ void Stages::rec_crops(Model* rec, const uint8_t* const* crops, const int* hs, c
         int end = beg;
         while (end < n && imgw[end] == imgw[beg] && end - beg < max_batch) ++end;
         int b = end - beg, W = imgw[beg];
-        Plan* p = rec->plan_for(b, img_h, W);
-        dim3 grid((unsigned)ceil_div(W, 256), img_h, b);
-        if (rec->precision() == PREC_BF16)
-            resize_norm_kernel<bf16><<<grid, 256, 0, st_>>>(d_jobs + beg, img_h, W, p->in_ptr(), 0, rec_norm());
-        else
-            resize_norm_kernel<float><<<grid, 256, 0, st_>>>(d_jobs + beg, img_h, W, p->in_ptr(), 0, rec_norm());
-        p->launch(st_);
-        if (p->out_shape.size() != 3) throw std::runtime_error("rec model output must be [B, T, classes]");
-        int T = (int)p->out_shape[1], C = (int)p->out_shape[2];
-        int rows = b * T;
-        int* d_idx = (int*)d_batch_.get((size_t)rows * (sizeof(int) + 2 * sizeof(float)));
-        float* d_mx = (float*)(d_idx + rows);
-        float* d_scr = d_mx + rows;
-        ctc_argmax_kernel<<<rows, 256, 0, st_>>>(p->out_dense, C, d_idx, d_mx);
-        ctc_collapse_kernel<<<(unsigned)ceil_div(b, 64), 64, 0, st_>>>(d_idx, d_mx, b, T, d_slots + beg, max_len, d_ids, d_lens,
-                                                                        d_scores, d_scr);
-        launches += p->launches + 3;
-        B200_CUDA_CHECK(cudaGetLastError());
+        rec_batch(rec, d_jobs + beg, d_slots + beg, b, img_h, W, max_len, d_ids, d_lens, d_scores);
         beg = end;
     }
     B200_CUDA_CHECK(cudaMemcpyAsync(ids_out, d_ids, (size_t)n * max_len * sizeof(int), cudaMemcpyDeviceToHost, st_));
@@ -440,8 +488,8 @@ void Stages::rec_crops(Model* rec, const uint8_t* const* crops, const int* hs, c
 }
 
 // ------------------------------------------------------------------------------- det pages
-// filter_tag_det_res (predict_det.py:67-81) on int32 boxes in cv2 order -> float32 boxes
-static int filter_boxes(const int32_t* in, int n, int img_h, int img_w, float* out, int max_boxes) {
+// filter_tag_det_res (predict_det.py:67-81) on int32 boxes in cv2 order -> float32 boxes appended to `out`
+static int filter_boxes(const int32_t* in, int n, int img_h, int img_w, std::vector<float>* out) {
     int m = 0;
     for (int i = 0; i < n; ++i) {
         float pts[4][2];
@@ -485,19 +533,37 @@ static int filter_boxes(const int32_t* in, int n, int img_h, int img_w, float* o
         };
         int rw = (int)norm(0, 1), rh = (int)norm(0, 3);
         if (rw <= 3 || rh <= 3) continue;
-        if (m >= max_boxes) throw std::runtime_error("box capacity too small");
-        memcpy(out + (size_t)m * 8, rect, sizeof(rect));
+        out->insert(out->end(), &rect[0][0], &rect[0][0] + 8);
         ++m;
     }
     return m;
 }
 
-void Stages::det_pages(Model* det, const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n,
-                       const b200ocr_det_params& p, float* boxes_out, int max_boxes, int* n_boxes_out, float* probmap_out,
-                       size_t probmap_capacity, int* probmap_dims_out) {
-    if (n == 0) return;
+// All pages of a call go to the device once and stay there until their crops are cut (the warp samples the
+// full-resolution original, predict_system.py:36,51).
+void Stages::upload_pages(const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n, PagePool* pool) {
+    pool->off.assign(n, 0);
+    pool->stride.assign(n, 0);
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!pages[i] || hs[i] <= 0 || ws[i] <= 0) throw std::runtime_error("bad argument: empty page at index " + std::to_string(i));
+        pool->stride[i] = strides && strides[i] > 0 ? strides[i] : ws[i] * 3;
+        if (pool->stride[i] < ws[i] * 3) throw std::runtime_error("bad argument: row stride smaller than a row at page " + std::to_string(i));
+        pool->off[i] = total;
+        total += ((size_t)hs[i] * pool->stride[i] + 255) & ~(size_t)255;
+    }
+    pool->base = (uint8_t*)d_img_.get(total);
+    for (int i = 0; i < n; ++i)
+        B200_CUDA_CHECK(cudaMemcpyAsync(pool->base + pool->off[i], pages[i], (size_t)hs[i] * pool->stride[i], cudaMemcpyHostToDevice, st_));
+}
+
+// TextDetector.__call__ for device-resident pages: equal-shaped pages run as one batch (<= 16);
+// boxes[i] receives page i's filtered float32 quads (cv2 contour order), 8 floats each.
+void Stages::det_on_pool(Model* det, const PagePool& pool, const int* hs, const int* ws, int n, const b200ocr_det_params& p,
+                         std::vector<std::vector<float>>* boxes_pp, float* probmap_out, size_t probmap_capacity,
+                         int* probmap_dims_out) {
+    boxes_pp->assign(n, {});
     cudaEventRecord(ev_[0], st_);
-    // group pages by (src shape) so equal-shaped pages run as one batch
     std::vector<int> idx(n);
     std::iota(idx.begin(), idx.end(), 0);
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
@@ -522,24 +588,12 @@ void Stages::det_pages(Model* det, const uint8_t* const* pages, const int* hs, c
         int b = g1 - g0;
         const DetGeom& g = geo[idx[g0]];
         int h = hs[idx[g0]], w = ws[idx[g0]];
-        // upload
         std::vector<ResizeJob> jobs(b);
-        size_t total = 0;
-        std::vector<size_t> off(b);
         for (int k = 0; k < b; ++k) {
             int i = idx[g0 + k];
-            int stride = strides && strides[i] > 0 ? strides[i] : w * 3;
-            off[k] = total;
-            total += ((size_t)h * stride + 255) & ~(size_t)255;
+            jobs[k] = make_job(pool.base + pool.off[i], h, w, pool.stride[i], g.pad_h, g.pad_w, g.dst_h, g.dst_w, 0);
         }
-        uint8_t* d_img = (uint8_t*)d_img_.get(total);
-        for (int k = 0; k < b; ++k) {
-            int i = idx[g0 + k];
-            int stride = strides && strides[i] > 0 ? strides[i] : w * 3;
-            B200_CUDA_CHECK(cudaMemcpyAsync(d_img + off[k], pages[i], (size_t)h * stride, cudaMemcpyHostToDevice, st_));
-            jobs[k] = make_job(d_img + off[k], h, w, stride, g.pad_h, g.pad_w, g.dst_h, g.dst_w, 0);
-        }
-        ResizeJob* d_jobs = (ResizeJob*)d_misc_.get(sizeof(ResizeJob) * b);
+        ResizeJob* d_jobs = (ResizeJob*)d_misc_.get(sizeof(ResizeJob) * max_batch);
         B200_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(ResizeJob) * b, cudaMemcpyHostToDevice, st_));
         Plan* pl = det->plan_for(b, g.dst_h, g.dst_w);
         cudaEventRecord(ev_[1], st_);
@@ -570,16 +624,241 @@ void Stages::det_pages(Model* det, const uint8_t* const* pages, const int* hs, c
         size_t bo = 0;
         for (int k = 0; k < b; ++k) {
             int i = idx[g0 + k];
-            n_boxes_out[i] = filter_boxes(boxes.data() + bo * 8, counts[k], h, w, boxes_out + (size_t)i * max_boxes * 8, max_boxes);
+            filter_boxes(boxes.data() + bo * 8, counts[k], h, w, &(*boxes_pp)[i]);
             bo += counts[k];
         }
         g0 = g1;
     }
-    B200_CUDA_CHECK(cudaStreamSynchronize(st_));
     stage_ms[0] = t_pre;
     stage_ms[1] = t_net;
     stage_ms[2] = t_post;
     stage_ms[3] = t_pre + t_net + t_post;
+}
+
+void Stages::det_pages(Model* det, const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n,
+                       const b200ocr_det_params& p, float* boxes_out, int max_boxes, int* n_boxes_out, float* probmap_out,
+                       size_t probmap_capacity, int* probmap_dims_out) {
+    if (n == 0) return;
+    PagePool pool;
+    upload_pages(pages, hs, ws, strides, n, &pool);
+    std::vector<std::vector<float>> boxes;
+    det_on_pool(det, pool, hs, ws, n, p, &boxes, probmap_out, probmap_capacity, probmap_dims_out);
+    B200_CUDA_CHECK(cudaStreamSynchronize(st_));
+    for (int i = 0; i < n; ++i) {
+        int m = (int)(boxes[i].size() / 8);
+        if (m > max_boxes) throw std::runtime_error("box capacity too small: page " + std::to_string(i) + " has " + std::to_string(m));
+        n_boxes_out[i] = m;
+        if (m) memcpy(boxes_out + (size_t)i * max_boxes * 8, boxes[i].data(), boxes[i].size() * sizeof(float));
+    }
+}
+
+// ------------------------------------------------------------------------------- fused end-to-end (Level C)
+// sorted_boxes (predict_system.py:75-97): Python's stable sort on (y0, x0), then the non-transitive adjacent-swap pass.
+static void sorted_boxes(std::vector<float>* boxes) {
+    int n = (int)(boxes->size() / 8);
+    if (n < 2) return;
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    const float* b = boxes->data();
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) {
+        if (b[a * 8 + 1] != b[c * 8 + 1]) return b[a * 8 + 1] < b[c * 8 + 1];
+        return b[a * 8] < b[c * 8];
+    });
+    std::vector<float> t(boxes->size());
+    for (int i = 0; i < n; ++i) memcpy(&t[(size_t)i * 8], b + (size_t)order[i] * 8, 8 * sizeof(float));
+    for (int i = 0; i < n - 1; ++i)
+        for (int j = i; j >= 0; --j) {
+            float* lo = &t[(size_t)j * 8];
+            float* hi = &t[(size_t)(j + 1) * 8];
+            if (std::fabs(hi[1] - lo[1]) < 10.f && hi[0] < lo[0]) {
+                float tmp[8];
+                memcpy(tmp, lo, sizeof(tmp)); memcpy(lo, hi, sizeof(tmp)); memcpy(hi, tmp, sizeof(tmp));
+            } else {
+                break;
+            }
+        }
+    boxes->swap(t);
+}
+
+static bool make_warp_job(const float* b, WarpJob* j) {
+    auto norm = [&](int a, int c) {
+        float dx = b[2 * a] - b[2 * c], dy = b[2 * a + 1] - b[2 * c + 1];
+        float s = dx * dx;                       // np.linalg.norm on float32
+        s += dy * dy;
+        return std::sqrt(s);
+    };
+    int cw = (int)std::max(norm(0, 1), norm(2, 3));
+    int ch = (int)std::max(norm(0, 3), norm(1, 2));
+    j->cw = cw;
+    j->ch = ch;
+    j->rot90 = (cw > 0 && ch > 0 && (ch * 1.0 / cw) >= 1.5) ? 1 : 0;
+    if (cw <= 0 || ch <= 0) return false;
+    perspective_inverse(b, cw, ch, j->mi);
+    return true;
+}
+
+// TextSystem.__call__ (predict_system.py:35-72) for a batch of pages without leaving the device between stages:
+// det -> boxes (host: filter + sorted_boxes, a few microseconds) -> one warp launch for every crop of every page ->
+// cls over all crops -> rotation flags patched into the rec jobs on the device -> rec batches (the reference's per-page
+// batch plan decides each crop's imgW; crops of all pages with equal imgW share a launch) -> CTC decode.
+void Stages::ocr_pages(Model* det, Model* cls, Model* rec, const uint8_t* const* pages, const int* hs, const int* ws,
+                       const int* strides, int n, const b200ocr_ocr_params& op, float* boxes_out, int line_cap,
+                       int* n_boxes_out, int32_t* ids_out, int max_len, int* lens_out, float* scores_out,
+                       int32_t* cls_labels_out, float* cls_scores_out) {
+    if (n == 0) return;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<float, std::milli>(now() - t0).count(); };
+    auto t0 = now();
+    PagePool pool;
+    upload_pages(pages, hs, ws, strides, n, &pool);
+    ocr_ms[0] = ms_since(t0); t0 = now();
+    std::vector<std::vector<float>> boxes;
+    det_on_pool(det, pool, hs, ws, n, op.det, &boxes, nullptr, 0, nullptr);
+    ocr_ms[1] = ms_since(t0); t0 = now();
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        sorted_boxes(&boxes[i]);
+        n_boxes_out[i] = (int)(boxes[i].size() / 8);
+        total += n_boxes_out[i];
+    }
+    if (total > line_cap) throw std::runtime_error("line capacity too small: need " + std::to_string(total));
+    if (total == 0) {
+        B200_CUDA_CHECK(cudaStreamSynchronize(st_));
+        return;
+    }
+    // ---- crops: get_rotate_crop_image for every box of every page in one launch
+    std::vector<WarpJob> wj(total);
+    std::vector<int> ch(total), cw(total), first_line(n + 1, 0);
+    std::vector<size_t> coff(total + 1, 0);
+    int max_w = 1, max_h = 1, li = 0;
+    for (int i = 0; i < n; ++i) {
+        first_line[i] = li;
+        for (int k = 0; k < n_boxes_out[i]; ++k, ++li) {
+            const float* b = &boxes[i][(size_t)k * 8];
+            memcpy(boxes_out + (size_t)li * 8, b, 8 * sizeof(float));
+            WarpJob& j = wj[li];
+            if (!make_warp_job(b, &j)) throw std::runtime_error("degenerate box (zero-size crop) on page " + std::to_string(i));
+            j.img = pool.base + pool.off[i];
+            j.h = hs[i]; j.w = ws[i]; j.stride = pool.stride[i];
+            j.out_off = coff[li];
+            coff[li + 1] = coff[li] + (((size_t)j.cw * j.ch * 3 + 15) & ~(size_t)15);
+            ch[li] = j.rot90 ? j.cw : j.ch;
+            cw[li] = j.rot90 ? j.ch : j.cw;
+            max_w = std::max(max_w, j.cw);
+            max_h = std::max(max_h, j.ch);
+        }
+    }
+    first_line[n] = li;
+    ocr_ms[2] = ms_since(t0); t0 = now();
+    const bool use_cls = op.use_angle_cls && cls != nullptr;
+    // one device block for every job table of this call
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o_wj = 0, o_cj = o_wj + al(sizeof(WarpJob) * total), o_rj = o_cj + al(sizeof(ResizeJob) * total),
+           o_cs = o_rj + al(sizeof(ResizeJob) * total), o_rs = o_cs + al(sizeof(int) * total),
+           o_cl = o_rs + al(sizeof(int) * total), o_cc = o_cl + al(sizeof(int) * total), o_end = o_cc + al(sizeof(float) * total);
+    char* d_tab = (char*)d_jobs_.get(o_end);
+    WarpJob* d_wj = (WarpJob*)(d_tab + o_wj);
+    ResizeJob* d_cj = (ResizeJob*)(d_tab + o_cj);
+    ResizeJob* d_rj = (ResizeJob*)(d_tab + o_rj);
+    int* d_cslot = (int*)(d_tab + o_cs);
+    int* d_rslot = (int*)(d_tab + o_rs);
+    int* d_clabel = (int*)(d_tab + o_cl);
+    float* d_cscore = (float*)(d_tab + o_cc);
+    uint8_t* d_pool = (uint8_t*)d_crops_.get(coff[total] + 16);
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_wj, wj.data(), sizeof(WarpJob) * total, cudaMemcpyHostToDevice, st_));
+    {
+        dim3 block(32, 8);
+        dim3 grid((unsigned)ceil_div(max_w, 32), (unsigned)ceil_div(max_h, 8), total);
+        warp_cubic_kernel<<<grid, block, 0, st_>>>(d_wj, cubic_tab_device(), d_pool);
+        launches += 1;
+        B200_CUDA_CHECK(cudaGetLastError());
+    }
+    // ---- cls: every batch has the same 48 x 192 canvas, so all crops of all pages form one device batch
+    if (use_cls) {
+        const int img_h = 48, img_w = 192;
+        std::vector<int> order = aspect_order(ch.data(), cw.data(), total);
+        std::vector<ResizeJob> jobs(total);
+        for (int k = 0; k < total; ++k) {
+            int i = order[k];
+            int rw = resized_w_rule(ch[i], cw[i], img_h, img_w);
+            jobs[k] = make_job(d_pool + coff[i], ch[i], cw[i], cw[i] * 3, ch[i], cw[i], img_h, rw, 0);
+        }
+        B200_CUDA_CHECK(cudaMemcpyAsync(d_cj, jobs.data(), sizeof(ResizeJob) * total, cudaMemcpyHostToDevice, st_));
+        B200_CUDA_CHECK(cudaMemcpyAsync(d_cslot, order.data(), sizeof(int) * total, cudaMemcpyHostToDevice, st_));
+        const int chunk = 512;
+        for (int beg = 0; beg < total; beg += chunk) {
+            int b = std::min(chunk, total - beg);
+            Plan* p = cls->plan_for(b, img_h, img_w);
+            dim3 grid((unsigned)ceil_div(img_w, 256), img_h, b);
+            if (cls->precision() == PREC_BF16)
+                resize_norm_kernel<bf16><<<grid, 256, 0, st_>>>(d_cj + beg, img_h, img_w, p->in_ptr(), 0, rec_norm());
+            else
+                resize_norm_kernel<float><<<grid, 256, 0, st_>>>(d_cj + beg, img_h, img_w, p->in_ptr(), 0, rec_norm());
+            p->launch(st_);
+            int ncls = (int)(p->out_dense_elems / b);
+            cls_argmax_kernel<<<(unsigned)ceil_div(b, 128), 128, 0, st_>>>(p->out_dense, b, ncls, d_cslot + beg, d_clabel, d_cscore);
+            launches += p->launches + 2;
+            B200_CUDA_CHECK(cudaGetLastError());
+        }
+    }
+    ocr_ms[3] = ms_since(t0); t0 = now();
+    // ---- rec: the reference's plan per page (aspect order, groups of rec_batch_num, imgW = int(48 * max ratio))
+    const int img_h = 48, img_w0 = 320;
+    int batch_num = op.rec_batch_num > 0 ? op.rec_batch_num : 6;
+    std::vector<int> imgw(total);
+    for (int pg = 0; pg < n; ++pg) {
+        int l0 = first_line[pg], m = first_line[pg + 1] - l0;
+        if (m == 0) continue;
+        std::vector<int> order = aspect_order(ch.data() + l0, cw.data() + l0, m);
+        for (int beg = 0; beg < m; beg += batch_num) {
+            int end = std::min(m, beg + batch_num);
+            double max_wh = img_w0 / (double)img_h;
+            for (int k = beg; k < end; ++k) max_wh = std::max(max_wh, cw[l0 + order[k]] * 1.0 / ch[l0 + order[k]]);
+            int W = (int)(img_h * max_wh);
+            if (op.rec_width_bucket > 0) W = (int)ceil_div(W, op.rec_width_bucket) * op.rec_width_bucket;
+            for (int k = beg; k < end; ++k) imgw[l0 + order[k]] = W;
+        }
+    }
+    std::vector<int> rorder(total);
+    std::iota(rorder.begin(), rorder.end(), 0);
+    std::stable_sort(rorder.begin(), rorder.end(), [&](int a, int b) { return imgw[a] < imgw[b]; });
+    {
+        std::vector<ResizeJob> jobs(total);
+        for (int k = 0; k < total; ++k) {
+            int i = rorder[k];
+            int rw = resized_w_rule(ch[i], cw[i], img_h, imgw[i]);
+            jobs[k] = make_job(d_pool + coff[i], ch[i], cw[i], cw[i] * 3, ch[i], cw[i], img_h, rw, 0);
+        }
+        B200_CUDA_CHECK(cudaMemcpyAsync(d_rj, jobs.data(), sizeof(ResizeJob) * total, cudaMemcpyHostToDevice, st_));
+        B200_CUDA_CHECK(cudaMemcpyAsync(d_rslot, rorder.data(), sizeof(int) * total, cudaMemcpyHostToDevice, st_));
+    }
+    if (use_cls) {                                // predict_cls.py:85-88: '180' in label and score > cls_thresh
+        rot_patch_kernel<<<(unsigned)ceil_div(total, 128), 128, 0, st_>>>(d_rj, d_rslot, total, d_clabel, d_cscore,
+                                                                         (unsigned)op.cls_rot_label_mask, op.cls_thresh);
+        launches += 1;
+    }
+    int* d_ids = (int*)d_boxes_.get(((size_t)total * max_len + 2 * (size_t)total) * sizeof(int));
+    int* d_lens = d_ids + (size_t)total * max_len;
+    float* d_scores = (float*)(d_lens + total);
+    B200_CUDA_CHECK(cudaMemsetAsync(d_ids, 0, (size_t)total * max_len * sizeof(int), st_));
+    const int max_batch = 256;
+    for (int beg = 0; beg < total;) {
+        int end = beg;
+        while (end < total && imgw[rorder[end]] == imgw[rorder[beg]] && end - beg < max_batch) ++end;
+        int b = end - beg, W = imgw[rorder[beg]];
+        rec_batch(rec, d_rj + beg, d_rslot + beg, b, img_h, W, max_len, d_ids, d_lens, d_scores);
+        beg = end;
+    }
+    ocr_ms[4] = ms_since(t0); t0 = now();
+    B200_CUDA_CHECK(cudaMemcpyAsync(ids_out, d_ids, (size_t)total * max_len * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    B200_CUDA_CHECK(cudaMemcpyAsync(lens_out, d_lens, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    B200_CUDA_CHECK(cudaMemcpyAsync(scores_out, d_scores, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, st_));
+    if (use_cls && cls_labels_out)
+        B200_CUDA_CHECK(cudaMemcpyAsync(cls_labels_out, d_clabel, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, st_));
+    if (use_cls && cls_scores_out)
+        B200_CUDA_CHECK(cudaMemcpyAsync(cls_scores_out, d_cscore, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, st_));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st_));
+    ocr_ms[5] = ms_since(t0);
 }
 
 void Stages::db_postprocess_host(const float* prob, int h, int w, int src_h, int src_w, const b200ocr_det_params& p,

@@ -33,7 +33,8 @@ struct PinBuf {
     ~PinBuf();
 };
 
-struct DbWork;              // device scratch of DBPostProcess (dbpost.cu)
+struct DbWork;
+struct ResizeJob;              // device scratch of DBPostProcess (dbpost.cu)
 void db_free(DbWork* w);
 
 class Stages {
@@ -54,6 +55,13 @@ public:
                    int32_t* labels_out, float* scores_out);
     void rec_crops(Model* rec, const uint8_t* const* crops, const int* hs, const int* ws, int n, int batch_num,
                    const uint8_t* rotate180, int32_t* ids_out, int max_len, int* lens_out, float* scores_out);
+    // Level C: TextSystem.__call__ for a batch of pages, device resident between stages (flat line-major outputs)
+    void ocr_pages(Model* det, Model* cls, Model* rec, const uint8_t* const* pages, const int* hs, const int* ws,
+                   const int* strides, int n, const b200ocr_ocr_params& op, float* boxes_out, int line_cap, int* n_boxes_out,
+                   int32_t* ids_out, int max_len, int* lens_out, float* scores_out, int32_t* cls_labels_out,
+                   float* cls_scores_out);
+    void rec_argmax_host(Model* rec, const float* nchw, int n, int c, int h, int w, int32_t* idx_out, float* prob_out,
+                         int capacity, int* T_out);
     void resident_upload(const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n);
     void resident_run(Model* det, const b200ocr_det_params& p, int iters, float* ms_total, int* n_boxes_total,
                       float* net_ms_total);
@@ -62,15 +70,29 @@ public:
 
     int64_t launches = 0;
     float stage_ms[4] = {0, 0, 0, 0};
+    // host wall clock of the last ocr_pages call: upload enqueue, det (incl. box read-back), host box/crop planning,
+    // warp + cls enqueue, rec enqueue, final drain
+    float ocr_ms[6] = {0, 0, 0, 0, 0, 0};
 
 private:
+    struct PagePool {
+        uint8_t* base = nullptr;
+        std::vector<size_t> off;
+        std::vector<int> stride;
+    };
+    void upload_pages(const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n, PagePool* pool);
+    void det_on_pool(Model* det, const PagePool& pool, const int* hs, const int* ws, int n, const b200ocr_det_params& p,
+                     std::vector<std::vector<float>>* boxes_pp, float* probmap_out, size_t probmap_capacity,
+                     int* probmap_dims_out);
+    void rec_batch(Model* rec, const struct ResizeJob* d_jobs, const int* d_slots, int b, int img_h, int W, int max_len,
+                   int* d_ids, int* d_lens, float* d_scores);
     // device-side DBPostProcess on a device-resident fp32 probability map [n][h][w]; results on the host
     void db_postprocess_device(const float* d_prob, int n, int h, int w, const int* src_hs, const int* src_ws,
                                const b200ocr_det_params& p, int capacity, std::vector<int32_t>* boxes,
                                std::vector<double>* scores, std::vector<int>* counts);
     cudaStream_t st_;
     cudaEvent_t ev_[4];
-    DevBuf d_img_, d_chw_, d_prob_, d_boxes_, d_crops_, d_misc_, d_batch_;
+    DevBuf d_img_, d_chw_, d_prob_, d_boxes_, d_crops_, d_misc_, d_batch_, d_jobs_;
     PinBuf h_pin_, h_pin2_;
     DbWork* db_ = nullptr;
     // resident pages

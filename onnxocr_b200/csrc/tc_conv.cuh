@@ -117,19 +117,6 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int ACT>
-__device__ __forceinline__ float epi_fast(float v, const Epilogue& e) {
-    if (ACT < 0) return epi_apply(v, e);                 // generic (interpreted) chain
-    v = fmaf(v, e.a0, e.b0);
-    if (ACT == EPI_RELU) v = fmaxf(v, 0.f);
-    else if (ACT == EPI_HSWISH) v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * 0.16666667f;
-    else if (ACT == EPI_SIGMOID) v = __fdividef(1.f, 1.f + __expf(-v));
-    else if (ACT == EPI_SWISH) v = __fdividef(v, 1.f + __expf(-v));
-    else if (ACT == EPI_HSIGMOID) v = fminf(fmaxf(fmaf(v, e.pa, e.pb), 0.f), 1.f);
-    else if (ACT == EPI_CLIP) v = fminf(fmaxf(v, e.pa), e.pb);
-    return fmaf(v, e.a1, e.b1);
-}
-
 // One accumulator row (this thread's pixel) -> bias, activation chain, bf16, 16-byte NHWC stores.
 template <int BN, int ACT>
 __device__ __forceinline__ void epilogue_row(uint32_t trow, const float* __restrict__ bias, bf16* __restrict__ dst, bool valid,
@@ -348,6 +335,211 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CTC head: logits = A[rows][K] * W[classes][K]^T + bias, softmax over the classes and
+// CTCLabelDecode's argmax / max (rec_postprocess.py:98-104) in ONE kernel — the [rows][classes] logits (753 MB at
+// 256 x 40 x 18385 fp32) never exist in HBM.  A CTA owns one 128-row tile and a contiguous range of 128-class tiles:
+// the A tile is loaded once and stays in shared memory, weight tiles stream through a TMA ring, tcgen05.mma fills two
+// TMEM accumulators alternately, and each epilogue thread (one row) keeps a running (max, first argmax, sum of
+// exp(v - max)) in registers.  grid = (row tiles, class splits); partial results of the splits are merged by
+// ctc_head_merge_kernel (max prob = 1 / sum exp(v - max)).
+struct HeadParams {
+    int rows;                    // B * T
+    int n_tiles;                 // ceil(classes / 128)
+    int tiles_per_split;
+    int kblocks;                 // ceil(K / 64)  (<= 4)
+};
+
+constexpr int HEAD_BN = 128;
+constexpr int HEAD_STAGES = 4;
+constexpr int HEAD_MAX_KB = 4;
+
+inline size_t head_smem_bytes(int kblocks) {
+    return (size_t)kblocks * (BM * BK * 2) + (size_t)HEAD_STAGES * kblocks * (HEAD_BN * BK * 2) + 2 * HEAD_BN * 4 + 1024 + 256;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads) ctc_head_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                            const __grid_constant__ CUtensorMap map_b,
+                                                            const float* __restrict__ bias /* -1e30 beyond the last class */,
+                                                            float* __restrict__ pmax, int* __restrict__ pidx,
+                                                            float* __restrict__ psum, const HeadParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int A_KB_BYTES = BM * BK * 2, B_KB_BYTES = HEAD_BN * BK * 2;
+    const int KB = p.kblocks;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_base = base;
+    const uint32_t b_base = a_base + KB * A_KB_BYTES;
+    const uint32_t bias_base = b_base + HEAD_STAGES * KB * B_KB_BYTES;
+    const uint32_t bar_base = bias_base + 2 * HEAD_BN * 4;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (HEAD_STAGES + s); };
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * HEAD_STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * HEAD_STAGES + 2 + a); };
+    const uint32_t a_bar = bar_base + 8u * (2 * HEAD_STAGES + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * HEAD_STAGES + 5);
+    uint32_t* tmem_slot_ptr = (uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    float* bias_sm = (float*)(smem_raw + (bias_base - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM;
+    const int t_begin = blockIdx.y * p.tiles_per_split;
+    const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < HEAD_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full_bar(a), 1);
+            mbar_init(tmem_empty_bar(a), 4);
+        }
+        mbar_init(a_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * HEAD_BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(a_bar, KB * A_KB_BYTES);
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(a_base + kb * A_KB_BYTES, &map_a, a_bar, kb * BK, m0);
+            uint32_t it = 0;
+            for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+                int s = it % HEAD_STAGES;
+                uint32_t ph = (it / HEAD_STAGES) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_expect_tx(full_bar(s), KB * B_KB_BYTES);
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(b_base + (s * KB + kb) * B_KB_BYTES, &map_b, full_bar(s), kb * BK, tile * HEAD_BN);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(HEAD_BN);
+            mbar_wait(a_bar, 0);
+            uint32_t it = 0;
+            for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+                int acc = it & 1;
+                uint32_t aph = (it >> 1) & 1;
+                mbar_wait(tmem_empty_bar(acc), aph ^ 1);
+                int s = it % HEAD_STAGES;
+                uint32_t ph = (it / HEAD_STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t tmem_d = tmem_base + (uint32_t)(acc * HEAD_BN);
+                for (int kb = 0; kb < KB; ++kb) {
+                    uint64_t adesc = make_smem_desc(a_base + kb * A_KB_BYTES);
+                    uint64_t bdesc = make_smem_desc(b_base + (s * KB + kb) * B_KB_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                }
+                umma_commit(empty_bar(s));
+                umma_commit(tmem_full_bar(acc));
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int et = threadIdx.x - 64;                 // 0..127 among the epilogue threads
+        float run_max = -3.0e38f, run_sum = 0.f;
+        int run_idx = 0;
+        uint32_t it = 0;
+        for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+            int acc = it & 1;
+            uint32_t aph = (it >> 1) & 1;
+            bias_sm[acc * HEAD_BN + et] = bias[tile * HEAD_BN + et];
+            named_bar_sync(1, 128);                      // bias tile visible; also fences the reuse of the other buffer
+            mbar_wait(tmem_full_bar(acc), aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t trow = tmem_base + (uint32_t)(acc * HEAD_BN) + ((uint32_t)(q * 32) << 16);
+            const float* bs = bias_sm + acc * HEAD_BN;
+#pragma unroll 1
+            for (int c = 0; c < HEAD_BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld8(trow + (uint32_t)c, v);
+                tmem_ld8(trow + (uint32_t)c + 8, v + 8);
+                tmem_ld8(trow + (uint32_t)c + 16, v + 16);
+                tmem_ld8(trow + (uint32_t)c + 24, v + 24);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float f[32];
+                float cmax = -3.0e38f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 b4 = *reinterpret_cast<const float4*>(bs + c + j);
+                    f[j] = __uint_as_float(v[j]) + b4.x;
+                    f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+                    f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+                    cmax = fmaxf(cmax, fmaxf(fmaxf(f[j], f[j + 1]), fmaxf(f[j + 2], f[j + 3])));
+                }
+                if (cmax > run_max) {                     // strictly greater: the earliest maximum keeps its index
+                    int ci = 0;
+#pragma unroll
+                    for (int j = 31; j >= 0; --j)
+                        if (f[j] == cmax) ci = j;
+                    run_sum *= __expf(run_max - cmax);
+                    run_max = cmax;
+                    run_idx = tile * HEAD_BN + c + ci;
+                }
+                float ssum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ssum += __expf(f[j] - run_max);
+                run_sum += ssum;
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        }
+        if (m0 + row < p.rows) {
+            size_t o = (size_t)blockIdx.y * p.rows + m0 + row;
+            pmax[o] = run_max;
+            pidx[o] = run_idx;
+            psum[o] = run_sum;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * HEAD_BN)) : "memory");
+    }
+}
+
+// Merges the class splits of ctc_head_kernel: idx = first index of the global maximum, prob = softmax value there.
+__global__ void ctc_head_merge_kernel(const float* __restrict__ pmax, const int* __restrict__ pidx,
+                                      const float* __restrict__ psum, int splits, int rows, int* __restrict__ idx,
+                                      float* __restrict__ prob) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float m = pmax[r];
+    int bi = pidx[r];
+    for (int s = 1; s < splits; ++s) {
+        float v = pmax[(size_t)s * rows + r];
+        int i = pidx[(size_t)s * rows + r];
+        if (v > m || (v == m && i < bi)) { m = v; bi = i; }
+    }
+    float sum = 0.f;
+    for (int s = 0; s < splits; ++s) sum += psum[(size_t)s * rows + r] * __expf(pmax[(size_t)s * rows + r] - m);
+    idx[r] = bi;
+    prob[r] = 1.f / sum;
 }
 
 }  // namespace tc

@@ -20,7 +20,7 @@ def default_args(**kwargs):
              rec_batch_num=6, rec_char_dict_path=os.path.join(assets, "ppocrv5_dict.txt"), use_space_char=True,
              drop_score=0.5, use_angle_cls=False, cls_model_dir=os.path.join(assets, "ppocrv5_cls.onnx"),
              cls_image_shape="3, 48, 192", label_list=["0", "180"], cls_batch_num=6, cls_thresh=0.9,
-             save_crop_res=False, precision="fp32")
+             save_crop_res=False, precision="fp32", fused=True, rec_width_bucket=0)
     d.update(kwargs)
     if d["det_model_dir"] is None or d["rec_model_dir"] is None:
         paths = synth_graphs.ensure_models()
@@ -127,7 +127,10 @@ def sorted_boxes(dt_boxes):
 
 
 class TextSystem(object):
-    """predict_system.py:10-72"""
+    """predict_system.py:10-72.  `__call__` keeps the reference's signature; by default it runs as ONE fused device
+    pipeline (`b200ocr_ocr_pages`: det -> crops -> cls -> rec without leaving the GPU).  `fused=False` in the args runs
+    the stage objects one after the other exactly like the reference does (same results, more PCIe round trips);
+    `batch(imgs)` is the Level-C throughput entry for many pages per call."""
 
     def __init__(self, args):
         self.text_detector = TextDetector(args)
@@ -138,8 +141,30 @@ class TextSystem(object):
             self.text_classifier = TextClassifier(args)
         self.args = args
         self.engine = _engine_for(args)
+        self.fused = bool(getattr(args, "fused", True))
+        self.rec_width_bucket = int(getattr(args, "rec_width_bucket", 0) or 0)
+
+    def _ocr_params(self, cls):
+        a = self.args
+        return _lib.ocr_params(self.text_detector.params, self.use_angle_cls and cls, a.cls_thresh, a.label_list,
+                               a.rec_batch_num, self.rec_width_bucket)
+
+    def batch(self, imgs, cls=True):
+        """[(filter_boxes, filter_rec_res), ...] for a list of pages; one library call."""
+        decode = self.text_recognizer.postprocess_op.text
+        out = []
+        for page in self.engine.ocr_pages(list(imgs), self._ocr_params(cls)):
+            fb, fr = [], []
+            for box, ids, score in zip(page["boxes"], page["ids"], page["scores"]):
+                if score >= self.drop_score:
+                    fb.append(box)
+                    fr.append((decode(ids), float(score)))
+            out.append((fb, fr))
+        return out
 
     def __call__(self, img, cls=True):
+        if self.fused:
+            return self.batch([img], cls)[0]
         dt_boxes = self.text_detector(img)
         if dt_boxes is None:
             return None, None
@@ -179,3 +204,7 @@ class ONNXPaddleOcr(TextSystem):
         if not rec:
             return cls_res
         return [rec_res]
+
+    def ocr_batch(self, imgs, cls=True):
+        """`ocr(img)` for a list of pages in one fused call: [[[box, (text, score)], ...], ...] (one entry per page)."""
+        return [[[box.tolist(), res] for box, res in zip(b, r)] for b, r in self.batch(imgs, cls)]

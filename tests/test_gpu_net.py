@@ -91,3 +91,37 @@ def test_unsupported_op_is_a_load_error(lib_built, tmp_path):
     with pytest.raises(RuntimeError, match="unsupported op: Erf"):
         e.load_onnx(_lib.DET, str(p))
     e.close()
+
+
+@pytest.mark.parametrize("shape", [(5, 3, 48, 320), (2, 3, 48, 1000), (1, 3, 48, 48)])
+def test_rec_fused_ctc_head_bf16(engine_bf16, torch_graphs, shape):
+    """K19: the tcgen05 Linear + online softmax/argmax epilogue against the dense path of the same engine
+    (Linear -> Softmax tensor -> argmax) and against the fp32 oracle."""
+    n, _, h, w = shape
+    crops = synth_pages.rec_crops_c3(n, seed=13, w=w)
+    x = np.stack([restate_pre.resize_norm_img(c, w) for c in crops]).astype(np.float32)
+    idx, prob = engine_bf16.rec_argmax(x)
+    dense = engine_bf16.session_run(_lib.REC, x)
+    assert idx.shape == dense.shape[:2]
+    # the dense path rounds the logits to bf16 before the softmax, the fused head keeps them in fp32: compare where
+    # the dense path's winner is clear, and the probabilities within the bf16 tolerance
+    d_idx, d_prob = dense.argmax(2), dense.max(2)
+    srt = np.sort(dense, axis=2)
+    clear = (srt[:, :, -1] - srt[:, :, -2]) > 0.05
+    assert clear.mean() > 0.5
+    assert (idx[clear] == d_idx[clear]).all()
+    assert np.abs(prob - d_prob)[clear].max() < 3e-2
+    ref = torch_graphs("rec").run(None, {"x": x})[0]
+    assert (idx == ref.argmax(2)).mean() > 0.9
+    r_clear = (np.sort(ref, axis=2)[:, :, -1] - np.sort(ref, axis=2)[:, :, -2]) > 0.1
+    assert (idx[r_clear] == ref.argmax(2)[r_clear]).all()
+    assert np.abs(prob - ref.max(2))[r_clear].max() < 5e-2
+
+
+def test_rec_argmax_fp32_equals_dense(engine_fp32):
+    crops = synth_pages.rec_crops_c3(3, seed=14, w=200)
+    x = np.stack([restate_pre.resize_norm_img(c, 200) for c in crops]).astype(np.float32)
+    idx, prob = engine_fp32.rec_argmax(x)
+    dense = engine_fp32.session_run(_lib.REC, x)
+    assert np.array_equal(idx, dense.argmax(2))
+    assert np.array_equal(prob, dense.max(2))

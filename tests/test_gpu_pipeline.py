@@ -63,6 +63,34 @@ def test_ocr_fp32_matches_oracle(system_fp32, oracle):
     assert n_lines >= 12
 
 
+def test_ocr_staged_equals_fused(system_fp32, model_paths):
+    """The stage-by-stage path (reference call sequence) and the fused device pipeline give identical results."""
+    staged = pipeline.ONNXPaddleOcr(use_angle_cls=True, det_model_dir=model_paths["det"], rec_model_dir=model_paths["rec"],
+                                    cls_model_dir=model_paths["cls"], rec_char_dict_path=model_paths["dict"], precision="fp32",
+                                    fused=False)
+    staged.engine = system_fp32.engine
+    for seed in (73, 74):
+        page = synth_pages.render_page(512, 704, 11, seed=seed, rot180_frac=0.3)[0]
+        a = staged.ocr(page.copy())[0]
+        b = system_fp32.ocr(page.copy())[0]
+        assert len(a) == len(b) and len(a) >= 5
+        for (ab, (at, asc)), (bb, (bt, bsc)) in zip(a, b):
+            assert ab == bb and at == bt and abs(asc - bsc) < 1e-6
+
+
+def test_ocr_batch_mixed_pages_matches_single(system_fp32):
+    """Level C: many pages of different sizes in one call == one call per page (page order kept, empty page included)."""
+    pages = [synth_pages.render_page(480, 640, 8, seed=90)[0], np.zeros((64, 64, 3), np.uint8),
+             synth_pages.render_page(384, 800, 6, seed=91, rot180_frac=0.5)[0], synth_pages.render_page(480, 640, 7, seed=92)[0]]
+    got = system_fp32.ocr_batch(pages)
+    assert len(got) == len(pages) and got[1] == []
+    for page, g in zip(pages, got):
+        single = system_fp32.ocr(page)[0]
+        assert [x[0] for x in g] == [x[0] for x in single]
+        assert [x[1][0] for x in g] == [x[1][0] for x in single]
+        assert np.allclose([x[1][1] for x in g], [x[1][1] for x in single], atol=1e-6)
+
+
 def test_ocr_warmup_image_has_no_boxes(system_fp32):
     """app/engine.py:149-164 warms the model with a 64x64 zero image."""
     assert system_fp32.ocr(np.zeros((64, 64, 3), np.uint8)) == [[]]
