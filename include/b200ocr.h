@@ -173,6 +173,9 @@ int b200ocr_plan_stats(b200ocr_engine* e, int kind, int n, int h, int w, double*
 int b200ocr_profile_plan(b200ocr_engine* e, int kind, int n, int h, int w, int iters, float* ms_out, double* flops_out,
                          double* bytes_out, int capacity, char* names_buf, size_t names_cap);
 /* Writes a buffer larger than L2 (256 MiB) on the engine stream: an L2 flush between timed iterations. */
+/* Average device time (ms, CUDA events on the engine stream) of `iters` back-to-back launches of one plan, the way
+ * the stages launch it (CUDA-graph replay); head != 0 selects the rec plan with the fused CTC head. */
+int b200ocr_time_plan(b200ocr_engine* e, int kind, int n, int h, int w, int head, int iters, float* ms_avg);
 int b200ocr_l2_flush(b200ocr_engine* e);
 /* Page-locked host memory for callers that want the H2D copies of their page buffers to be truly async. */
 void* b200ocr_host_alloc(size_t bytes);

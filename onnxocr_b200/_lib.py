@@ -87,6 +87,7 @@ def lib():
         L.b200ocr_describe.argtypes = [vp, i, C.c_char_p, sz]
         L.b200ocr_plan_stats.argtypes = [vp, i, i, i, i, pd, pi, pd]
         L.b200ocr_profile_plan.argtypes = [vp, i, i, i, i, i, pf, pd, pd, i, C.c_char_p, sz]
+        L.b200ocr_time_plan.argtypes = [vp, i, i, i, i, i, i, pf]
         L.b200ocr_l2_flush.argtypes = [vp]
         L.b200ocr_host_alloc.argtypes = [sz]
         L.b200ocr_host_alloc.restype = vp
@@ -199,6 +200,11 @@ class Engine(object):
         ns = self._check(self._L.b200ocr_profile_plan(self._h, kind, n, h, w, iters, ms, fl, by, cap, names, len(names)))
         parts = names.raw.split(b"\0")
         return [{"name": parts[k].decode(), "ms": ms[k], "flops": fl[k], "bytes": by[k]} for k in range(ns)]
+
+    def time_plan(self, kind, n, h, w, head=False, iters=10):
+        ms = C.c_float()
+        self._check(self._L.b200ocr_time_plan(self._h, kind, n, h, w, int(head), iters, C.byref(ms)))
+        return ms.value
 
     def l2_flush(self):
         self._check(self._L.b200ocr_l2_flush(self._h))

@@ -11,6 +11,7 @@
 #include "../../include/b200ocr.h"
 #include "engine.h"
 #include "stages.h"
+#include "common.cuh"
 
 using namespace b200ocr;
 
@@ -320,6 +321,30 @@ int b200ocr_profile_plan(b200ocr_engine* e, int kind, int n, int h, int w, int i
         }
         e->stages->launches += (int64_t)ns * (iters < 1 ? 1 : iters);
         return ns;
+    });
+}
+
+int b200ocr_time_plan(b200ocr_engine* e, int kind, int n, int h, int w, int head, int iters, float* ms_avg) {
+    return guarded(e, [&]() {
+        Model* m = need(e, kind);
+        if (!ms_avg || iters < 1) throw std::runtime_error("bad argument to time_plan");
+        std::lock_guard<std::mutex> lk(e->mu);
+        Plan* p = m->plan_for(n, h, w, head != 0);
+        for (int i = 0; i < 3; ++i) p->launch(e->stream);          // warm: lazy init, graph capture
+        cudaEvent_t a, b;
+        B200_CUDA_CHECK(cudaEventCreate(&a));
+        B200_CUDA_CHECK(cudaEventCreate(&b));
+        B200_CUDA_CHECK(cudaEventRecord(a, e->stream));
+        for (int i = 0; i < iters; ++i) p->launch(e->stream);
+        B200_CUDA_CHECK(cudaEventRecord(b, e->stream));
+        B200_CUDA_CHECK(cudaEventSynchronize(b));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        *ms_avg = ms / iters;
+        e->stages->launches += (int64_t)p->launches * (iters + 3);
+        return B200OCR_OK;
     });
 }
 

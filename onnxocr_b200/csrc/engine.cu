@@ -23,6 +23,7 @@ std::vector<int64_t> PVal::logical() const {
 }
 
 Plan::~Plan() {
+    if (own_arena) cudaFree(own_arena);
     if (out_dense) cudaFree(out_dense);
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
 }
@@ -84,6 +85,15 @@ static bool tc_enabled() {
     return v == 1;
 }
 
+static bool tc_ws_enabled() {             // B200OCR_TC=stream selects the A+B streaming kernel (A/B measurements)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200OCR_TC");
+        v = (e && std::string(e) == "stream") ? 0 : 1;
+    }
+    return v == 1;
+}
+
 static bool dw_strip_enabled() {          // B200OCR_DW=tile selects the previous depthwise kernel (A/B measurements)
     static int v = -1;
     if (v < 0) {
@@ -104,7 +114,8 @@ Model::Model(const std::string& path, int precision) : prec_(precision) {
     g_ = build_cgraph(m);
     if (g_->input_shape.size() == 4 && g_->input_shape[1] > 0) in_c_ = (int)g_->input_shape[1];
     dw_.resize(g_->weights.size());
-    auto pack_dense = [&](int wid, bool convt) {
+    // pre = (a0, b0) of the node's compiled epilogue: folded into the tensor-core operand pack (W * a0, bias * a0 + b0)
+    auto pack_dense = [&](int wid, bool convt, float pre_a = 1.f, float pre_b = 0.f) {
         const ConvWeights& cw = g_->weights[wid];
         DevWeights& d = dw_[wid];
         int cinp = cpad_of(cw.cin), coutp = cpad_of(cw.cout);
@@ -136,8 +147,8 @@ Model::Model(const std::string& path, int precision) : prec_(precision) {
             for (int t = 0; t < taps; ++t)
                 for (int co = 0; co < cw.cout; ++co) {
                     for (int ci = 0; ci < cw.cin; ++ci)
-                        wb[(size_t)(t * coutp + co) * K + ci] = __float2bfloat16(cw.w[((size_t)t * cw.cin + ci) * cw.cout + co]);
-                    tb[t * coutp + co] = cw.bias[co];
+                        wb[(size_t)(t * coutp + co) * K + ci] = __float2bfloat16(pre_a * cw.w[((size_t)t * cw.cin + ci) * cw.cout + co]);
+                    tb[t * coutp + co] = cw.bias[co] * pre_a + pre_b;
                 }
             B200_CUDA_CHECK(cudaMalloc(&d.w_bf16, wb.size() * sizeof(bf16)));
             B200_CUDA_CHECK(cudaMemcpy(d.w_bf16, wb.data(), wb.size() * sizeof(bf16), cudaMemcpyHostToDevice));
@@ -156,11 +167,11 @@ Model::Model(const std::string& path, int precision) : prec_(precision) {
             for (int t = 0; t < taps; ++t)
                 for (int ci = 0; ci < cw.cin; ++ci)
                     for (int co = 0; co < cw.cout; ++co)
-                        wb[(size_t)co * K + (size_t)t * kchunks * 64 + ci] = __float2bfloat16(cw.w[((size_t)t * cw.cin + ci) * cw.cout + co]);
+                        wb[(size_t)co * K + (size_t)t * kchunks * 64 + ci] = __float2bfloat16(pre_a * cw.w[((size_t)t * cw.cin + ci) * cw.cout + co]);
             B200_CUDA_CHECK(cudaMalloc(&d.w_bf16, wb.size() * sizeof(bf16)));
             B200_CUDA_CHECK(cudaMemcpy(d.w_bf16, wb.data(), wb.size() * sizeof(bf16), cudaMemcpyHostToDevice));
             std::vector<float> tb(rows + 128, 0.f);
-            for (int co = 0; co < cw.cout; ++co) tb[co] = cw.bias[co];
+            for (int co = 0; co < cw.cout; ++co) tb[co] = cw.bias[co] * pre_a + pre_b;
             d.tc_bias = upload(tb);
             if (taps == 1 && bn == 128 && kchunks <= 4) {             // candidate CTC head (Linear with >= 65 outputs)
                 std::vector<float> hb(rows + 128, -1.0e30f);
@@ -173,8 +184,11 @@ Model::Model(const std::string& path, int precision) : prec_(precision) {
         }
     };
     for (auto& c : g_->nodes) {
-        if (c.kind == C_CONV) pack_dense(c.weight_id, false);
-        else if (c.kind == C_CONVT) pack_dense(c.weight_id, true);
+        const bool fold = prec_ == PREC_BF16 && c.epi.n > 0 && c.epi.fast && (c.epi.a0 != 1.f || c.epi.b0 != 0.f);
+        if (c.kind == C_CONV || c.kind == C_CONVT) {
+            pack_dense(c.weight_id, c.kind == C_CONVT, fold ? c.epi.a0 : 1.f, fold ? c.epi.b0 : 0.f);
+            dw_[c.weight_id].tc_prefolded = fold;
+        }
         else if (c.kind == C_SE) {
             pack_dense(c.se_w1, false);
             pack_dense(c.se_w2, false);
@@ -316,21 +330,22 @@ struct Arena {
 };
 }  // namespace
 
-Plan* Model::plan_for(int n, int h, int w, bool head) {
-    std::vector<int> key{n, h, w, head ? 1 : 0};
+Plan* Model::plan_for(int n, int h, int w, bool head, bool own_arena) {
+    std::vector<int> key{n, h, w, head ? 1 : 0, own_arena ? 1 : 0};
     auto it = plans_.find(key);
     if (it != plans_.end()) return it->second.get();
     if (plans_.size() >= 768) {                         // bounded cache (dynamic rec widths x batch sizes)
         B200_CUDA_CHECK(cudaDeviceSynchronize());
         plans_.clear();
+        private_bytes_ = 0;
     }
-    std::unique_ptr<Plan> p = build_plan(n, h, w, head);
+    std::unique_ptr<Plan> p = build_plan(n, h, w, head, own_arena);
     Plan* raw = p.get();
     plans_[key] = std::move(p);
     return raw;
 }
 
-std::unique_ptr<Plan> Model::build_plan(int n, int h, int w, bool head) {
+std::unique_ptr<Plan> Model::build_plan(int n, int h, int w, bool head, bool own_arena) {
     std::unique_ptr<Plan> p(new Plan());
     p->head_mode = head;
     p->model_arena = &arena_;
@@ -339,6 +354,13 @@ std::unique_ptr<Plan> Model::build_plan(int n, int h, int w, bool head) {
     p->w = w;
     if (prec_ == PREC_BF16) build_steps<bf16>(*p);
     else build_steps<float>(*p);
+    constexpr size_t kPrivateMax = (size_t)192 << 20, kPrivateBudget = (size_t)24 << 30;
+    if (own_arena && p->arena_bytes <= kPrivateMax && private_bytes_ + p->arena_bytes <= kPrivateBudget) {
+        B200_CUDA_CHECK(cudaMalloc(&p->own_arena, p->arena_bytes));
+        p->model_arena = &p->own_arena;
+        private_bytes_ += p->arena_bytes;
+        return p;
+    }
     if (p->arena_bytes > arena_cap_) {
         B200_CUDA_CHECK(cudaDeviceSynchronize());
         if (arena_) cudaFree(arena_);
@@ -580,6 +602,32 @@ void Model::build_steps(Plan& p) {
                         tp.Cout = tp.CoutP = 4 * cp.CoutP;
                     }
                     tp.epi = c.epi;
+                    if (dw.tc_prefolded) { tp.epi.a0 = 1.f; tp.epi.b0 = 0.f; }   // already inside the packed weights / bias
+                    // DB head tail: ConvT -> ConvT(-> <= 1 channel) [-> activation] == graph output, fused into this epilogue
+                    bool ct2 = false;
+                    std::shared_ptr<float> ct2_w;
+                    if (tc_ct && ni + 1 < g.nodes.size() && cp.CoutP <= tc::CT2_MAX_C && c.epi.fast) {
+                        const CNode& nx = g.nodes[ni + 1];
+                        if (nx.kind == C_CONVT && nx.in[0] == c.out && nuse[c.out] == 1 && nx.out == g.output_name && nx.cout == 1 &&
+                            nx.cin == c.cout) {
+                            const ConvWeights& w2 = g.weights[nx.weight_id];
+                            std::vector<float> hw((size_t)4 * cp.CoutP + 1, 0.f);
+                            for (int t2 = 0; t2 < 4; ++t2)
+                                for (int ci = 0; ci < nx.cin; ++ci) hw[(size_t)t2 * cp.CoutP + ci] = w2.w[((size_t)t2 * w2.cin + ci) * w2.cout];
+                            hw[(size_t)4 * cp.CoutP] = w2.bias[0];
+                            float* dptr = nullptr;
+                            B200_CUDA_CHECK(cudaMalloc(&dptr, hw.size() * sizeof(float)));
+                            B200_CUDA_CHECK(cudaMemcpy(dptr, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice));
+                            ct2_w.reset(dptr, [](float* q) { cudaFree(q); });
+                            ct2 = true;
+                            tp.ct2 = 1;
+                            tp.ct2_w = dptr;
+                            tp.epi2 = nx.epi;
+                            p.flops += 2.0 * (4.0 * cp.M) * 4.0 * nx.cin;
+                            cost_flops += 2.0 * (4.0 * cp.M) * 4.0 * nx.cin;
+                            cost_bytes = vbytes(in) + 16.0 * cp.M * 4.0 + (double)c.cout * c.cin * 4 * esz;
+                        }
+                    }
                     tp.TW = 128; tp.TH = 1;
                     if (tp.mode == 1) {
                         int64_t best = -1;
@@ -592,6 +640,16 @@ void Model::build_steps(Plan& p) {
                     tp.tiles_x = (int)ceil_div(iv.w, tp.TW);
                     tp.tiles_y = (int)ceil_div(iv.h, tp.TH);
                     int bn = dw.tc_bn;
+                    // weight-stationary kernel whenever the layer's weight slab fits in shared memory
+                    const int nkb = tp.taps * tp.kchunks;
+                    // k x k convolutions re-read the activation tile once per tap, which dominates: they keep the streaming
+                    // kernel (2 CTAs per SM); 1x1 / linear / transposed convolutions run weight-stationary
+                    const int ws_bn = (tc_ws_enabled() && tp.mode == 0) ? tc::ws_pick_bn(tp.CoutP, nkb) : 0;
+                    if (ws_bn) {
+                        bn = ws_bn;
+                        tp.ws_bn = ws_bn;
+                        tp.ws_stages = tc::ws_pick_stages(ws_bn, nkb);
+                    }
                     std::shared_ptr<TcState> ts(new TcState());
                     {
                         uint64_t dims[2] = {(uint64_t)dw.tc_k, (uint64_t)dw.tc_rows};
@@ -601,7 +659,11 @@ void Model::build_steps(Plan& p) {
                     }
                     const float* tbias = dw.tc_bias;
                     int icp = iv.cp, iN = iv.n, iH = iv.h, iW = iv.w;
-                    emit(std::string(tc_ct ? "tcconvT " : c.is_linear ? "tclinear " : "tcconv ") + c.name, [=](cudaStream_t st) {
+                    const tc::Params tp0 = tp;
+                    emit(std::string(ct2 ? "tcconvT2 " : tc_ct ? "tcconvT " : c.is_linear ? "tclinear " : "tcconv ") + c.name, [=](cudaStream_t st) {
+                        (void)ct2_w;                                    // keeps the second-stage weights alive with the plan
+                        tc::Params tp = tp0;
+                        tp.ct2_out = pp->out_dense;
                         const void* x = pp->ptr(in);
                         if (ts->a_ptr != x) {
                             if (tp.mode == 0) {
@@ -618,6 +680,15 @@ void Model::build_steps(Plan& p) {
                             ts->a_ptr = x;
                         }
                         int m_tiles = tp.mode == 0 ? (int)ceil_div(tp.M, tc::BM) : tp.tiles_x * tp.tiles_y * tp.N;
+                        if (ws_bn) {
+                            int n_tiles = (int)ceil_div(tp.CoutP, ws_bn);
+                            int m_groups = std::max(1, std::min(m_tiles, 148 / n_tiles));
+                            size_t smem = tc::ws_smem_bytes(ws_bn, nkb, tp.ws_stages);
+                            cudaFuncSetAttribute(tc::conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::WS_SMEM_LIMIT);
+                            tc::conv_tc_ws_kernel<<<dim3((unsigned)(n_tiles * m_groups)), tc::kWsThreads, smem, st>>>(
+                                ts->map_a, ts->map_b, tbias, (bf16*)pp->ptr(out), tp);
+                            return;
+                        }
                         int total_tiles = m_tiles * (int)ceil_div(tp.CoutP, bn);
                         int per_sm = bn == 128 ? 1 : 2;                     // shared-memory footprint per CTA
                         dim3 grid((unsigned)std::min(total_tiles, 148 * per_sm));
@@ -633,6 +704,16 @@ void Model::build_steps(Plan& p) {
                             tc::conv_tc_kernel<128><<<grid, tc::kThreads, tc::smem_bytes<128>(), st>>>(ts->map_a, ts->map_b, tbias, yo, tp);
                         }
                     });
+                    if (ct2) {                                          // the dense fp32 graph output was written directly
+                        const CNode& nx = g.nodes[ni + 1];
+                        PVal ov = p.vals[out];
+                        ov.h = 4 * iv.h; ov.w = 4 * iv.w; ov.c = 1; ov.cp = 1; ov.root = -1;
+                        p.vals.push_back(ov);
+                        vid[nx.out] = (int)p.vals.size() - 1;
+                        p.out_written_dense = true;
+                        skip[ni + 1] = 1;
+                        break;
+                    }
                     vid[c.out] = out;
                     break;
                 }
@@ -730,7 +811,7 @@ void Model::build_steps(Plan& p) {
                 if (iv.form != F_NCHW) throw std::runtime_error("GlobalAveragePool input is not NCHW-shaped: " + c.name);
                 if (iv.cp > 1024 || iv.cp < 4) throw std::runtime_error("GlobalAveragePool channel count unsupported: " + c.name);
                 int HW = iv.h * iv.w;
-                int chunks = std::max(1, std::min(64, HW / 2048));
+                int chunks = std::max(1, std::min(64, HW / 256));   // depends on HW only: per-sample sums do not depend on the batch
                 int partial = new_buf((size_t)iv.n * chunks * iv.cp * sizeof(float));
                 int rows = std::max(1, 256 / (iv.cp / 4));
                 size_t smem = (size_t)rows * iv.cp * sizeof(float);
@@ -768,9 +849,9 @@ void Model::build_steps(Plan& p) {
                 const DevWeights &w1 = dw_[c.se_w1], &w2 = dw_[c.se_w2];
                 int mid = c.se_mid;
                 float alpha = c.scale, beta = c.eps;
-                size_t smem2 = (size_t)(iv.cp + mid) * sizeof(float);
+                size_t smem2 = (size_t)(iv.cp + mid + kSeThreads) * sizeof(float);
                 emit("se_fc " + c.name, [=](cudaStream_t st) {
-                    se_fc_kernel<<<N, 256, smem2, st>>>((const float*)pp->bufptr(partial), chunks, HW, C, CP, mid, w1.w, w1.ColsW,
+                    se_fc_kernel<<<N, kSeThreads, smem2, st>>>((const float*)pp->bufptr(partial), chunks, HW, C, CP, mid, w1.w, w1.ColsW,
                                                          w1.bias, w2.w, w2.ColsW, w2.bias, alpha, beta, (float*)pp->bufptr(scale));
                 });
                 int64_t total4 = (int64_t)iv.n * HW * (iv.cp / 4);

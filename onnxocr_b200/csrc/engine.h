@@ -41,6 +41,7 @@ struct DevWeights {
     float* bias = nullptr;         // [ColsW]
     void* w_bf16 = nullptr;        // tcgen05 operand pack: bf16 [tc_rows][tc_k], K-major (bf16 models only)
     float* tc_bias = nullptr;
+    bool tc_prefolded = false;     // the epilogue's leading affine (a0, b0) is folded into w_bf16 / tc_bias
     float* head_bias = nullptr;    // CTC head: bias with -1e30 beyond the last class (padding never wins the argmax)
     int tc_bn = 0, tc_rows = 0, tc_k = 0;
     int K = 0, Kpad = 0, ColsW = 0;
@@ -51,7 +52,8 @@ struct Plan {
     std::vector<PVal> vals;
     std::vector<size_t> buf_off, buf_bytes;
     size_t arena_bytes = 0;
-    char** model_arena = nullptr;  // the owning Model's activation slab (shared by all of its plans)
+    char** model_arena = nullptr;  // the owning Model's activation slab (shared by all of its plans) or &own_arena
+    char* own_arena = nullptr;     // private slab: lets this plan run concurrently with other plans on another stream
     std::vector<std::function<void(cudaStream_t)>> steps;
     std::vector<std::string> step_names;
     std::vector<double> step_flops, step_bytes;   // algorithmic work per launch (unique in+out+weight bytes)
@@ -91,7 +93,9 @@ public:
     void run_host(const float* nchw, int n, int c, int h, int w, std::vector<int64_t>* out_shape,
                   float* out, size_t out_capacity, cudaStream_t st);
     // head = true: the final Linear + Softmax run as the fused CTC head (no dense output; see Plan::head_*)
-    Plan* plan_for(int n, int h, int w, bool head = false);
+    // own_arena = true: give the plan a private activation slab when it is small (so independent small batches can
+    // overlap on several streams); falls back to the shared slab when the private budget is exhausted.
+    Plan* plan_for(int n, int h, int w, bool head = false, bool own_arena = false);
     // Host NCHW fp32 in -> plan launched on `st` (no synchronisation); head selects the fused CTC head variant.
     Plan* launch_host_input(const float* nchw, int n, int c, int h, int w, cudaStream_t st, bool head);
     // Per-step device time (ms, averaged over iters) measured with CUDA events between launches.
@@ -103,7 +107,8 @@ public:
     std::string describe() const;
 
 private:
-    std::unique_ptr<Plan> build_plan(int n, int h, int w, bool head);
+    std::unique_ptr<Plan> build_plan(int n, int h, int w, bool head, bool own_arena);
+    size_t private_bytes_ = 0;
     template <typename T> void build_steps(Plan& p);
     std::unique_ptr<CGraph> g_;
     int prec_;

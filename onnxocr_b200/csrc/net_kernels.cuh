@@ -664,35 +664,67 @@ __global__ void gap_finish_kernel(const float* __restrict__ partial, T* __restri
     }
 }
 
-// scale[n][c] = hsigmoid(W2 relu(W1 mean + b1) + b2).  One block per image.
-// w1: [C][mid] (rows padded as stored: K index = ci, ColsW stride), w2: [mid][C].
-__global__ void se_fc_kernel(const float* __restrict__ partial, int chunks, int HW, int C, int CP, int mid,
-                             const float* __restrict__ w1, int w1_ld, const float* __restrict__ b1,
-                             const float* __restrict__ w2, int w2_ld, const float* __restrict__ b2, float alpha,
-                             float beta, float* __restrict__ scale) {
-    extern __shared__ float sm[];                   // mean[CP] + hidden[mid]
+// scale[n][c] = hsigmoid(W2 relu(W1 mean + b1) + b2).  One block of 1024 threads per image; both small matrix-vector
+// products are split over thread slices (coalesced weight reads along the output index, partial sums through shared
+// memory) so the dependent-load chains stay short — the kernel is pure latency.
+// w1: [C][mid] (row stride w1_ld), w2: [mid][C] (row stride w2_ld).
+constexpr int kSeThreads = 1024;
+__global__ void __launch_bounds__(kSeThreads) se_fc_kernel(const float* __restrict__ partial, int chunks, int HW, int C, int CP,
+                                                           int mid, const float* __restrict__ w1, int w1_ld,
+                                                           const float* __restrict__ b1, const float* __restrict__ w2, int w2_ld,
+                                                           const float* __restrict__ b2, float alpha, float beta,
+                                                           float* __restrict__ scale) {
+    extern __shared__ float sm[];                   // mean[CP] + hidden[mid] + part[kSeThreads]
     float* mean = sm;
     float* hid = sm + CP;
-    int n = blockIdx.x;
-    for (int c = threadIdx.x; c < CP; c += blockDim.x) {
+    float* part = hid + mid;
+    const int n = blockIdx.x, tid = threadIdx.x;
+    {   // mean over the pixels: slices of the chunk list per channel
+        const int S = max(1, min(chunks, kSeThreads / CP));
+        const int c = tid % CP, sl = tid / CP;
         float s = 0.f;
-        for (int k = 0; k < chunks; ++k) s += partial[((int64_t)n * chunks + k) * CP + c];
-        mean[c] = c < C ? s / (float)HW : 0.f;
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < mid; j += blockDim.x) {
-        float s = 0.f;
-        for (int c = 0; c < C; ++c) s = fmaf(mean[c], w1[(int64_t)c * w1_ld + j], s);
-        hid[j] = fmaxf(s + b1[j], 0.f);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < CP; c += blockDim.x) {
-        float s = 0.f;
-        if (c < C) {
-            for (int j = 0; j < mid; ++j) s = fmaf(hid[j], w2[(int64_t)j * w2_ld + c], s);
-            s = fminf(fmaxf(fmaf(s + b2[c], alpha, beta), 0.f), 1.f);
+        if (sl < S)
+            for (int k = sl; k < chunks; k += S) s += partial[((int64_t)n * chunks + k) * CP + c];
+        if (sl < S) part[sl * CP + c] = s;
+        __syncthreads();
+        if (tid < CP) {
+            float t = 0.f;
+            for (int q = 0; q < S; ++q) t += part[q * CP + tid];
+            mean[tid] = tid < C ? t / (float)HW : 0.f;
         }
-        scale[(int64_t)n * CP + c] = s;
+        __syncthreads();
+    }
+    {   // hidden = relu(W1^T mean + b1)
+        const int S = max(1, kSeThreads / mid);
+        const int j = tid % mid, sl = tid / mid;
+        float s = 0.f;
+        if (sl < S)
+            for (int c = sl; c < C; c += S) s = fmaf(mean[c], w1[(int64_t)c * w1_ld + j], s);
+        if (sl < S) part[sl * mid + j] = s;
+        __syncthreads();
+        if (tid < mid) {
+            float t = 0.f;
+            for (int q = 0; q < S; ++q) t += part[q * mid + tid];
+            hid[tid] = fmaxf(t + b1[tid], 0.f);
+        }
+        __syncthreads();
+    }
+    {   // scale = hsigmoid(W2^T hidden + b2)
+        const int S = max(1, min(mid, kSeThreads / CP));
+        const int c = tid % CP, sl = tid / CP;
+        float s = 0.f;
+        if (sl < S && c < C)
+            for (int j = sl; j < mid; j += S) s = fmaf(hid[j], w2[(int64_t)j * w2_ld + c], s);
+        if (sl < S) part[sl * CP + c] = s;
+        __syncthreads();
+        if (tid < CP) {
+            float t = 0.f;
+            if (tid < C) {
+                for (int q = 0; q < S; ++q) t += part[q * CP + tid];
+                t = fminf(fmaxf(fmaf(t + b2[tid], alpha, beta), 0.f), 1.f);
+            }
+            scale[(int64_t)n * CP + tid] = t;
+        }
     }
 }
 

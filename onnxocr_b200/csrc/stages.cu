@@ -187,10 +187,16 @@ static short* g_cubic_tab[16] = {nullptr};
 
 Stages::Stages(cudaStream_t st) : st_(st) {
     for (auto& e : ev_) B200_CUDA_CHECK(cudaEventCreate(&e));
+    for (auto& a : aux_) B200_CUDA_CHECK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+    for (auto& e : ev_join_) B200_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     db_ = nullptr;
 }
 
 Stages::~Stages() {
+    for (auto& a : aux_) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+    cudaEventDestroy(ev_fork_);
+    for (auto& e : ev_join_) cudaEventDestroy(e);
     for (auto& e : ev_) cudaEventDestroy(e);
     db_free(db_);
 }
@@ -379,33 +385,80 @@ void Stages::cls_crops(Model* cls, const uint8_t* const* crops, const int* hs, c
 }
 
 // One device batch of the recogniser: resize/normalise/pad -> SVTR_LCNet -> greedy CTC decode into the slots.
+// `lane` selects the stream (0 = the engine stream, 1.. = auxiliary streams): small batches get a plan with a private
+// activation slab, so independent batches overlap on the GPU instead of queueing behind each other.
 void Stages::rec_batch(Model* rec, const ResizeJob* d_jobs, const int* d_slots, int b, int img_h, int W, int max_len,
-                       int* d_ids, int* d_lens, float* d_scores) {
-    Plan* p = rec->plan_for(b, img_h, W, /*head=*/true);
+                       int* d_ids, int* d_lens, float* d_scores, int lane) {
+    cudaStream_t st = lane == 0 ? st_ : aux_[lane - 1];
+    Plan* p = rec->plan_for(b, img_h, W, /*head=*/true, /*own_arena=*/lane != 0);
+    if (lane != 0 && !p->own_arena) {            // private budget exhausted: this batch must run on the engine stream
+        lane = 0;
+        st = st_;
+    }
     dim3 grid((unsigned)ceil_div(W, 256), img_h, b);
     if (rec->precision() == PREC_BF16)
-        resize_norm_kernel<bf16><<<grid, 256, 0, st_>>>(d_jobs, img_h, W, p->in_ptr(), 0, rec_norm());
+        resize_norm_kernel<bf16><<<grid, 256, 0, st>>>(d_jobs, img_h, W, p->in_ptr(), 0, rec_norm());
     else
-        resize_norm_kernel<float><<<grid, 256, 0, st_>>>(d_jobs, img_h, W, p->in_ptr(), 0, rec_norm());
-    p->launch(st_);
+        resize_norm_kernel<float><<<grid, 256, 0, st>>>(d_jobs, img_h, W, p->in_ptr(), 0, rec_norm());
+    p->launch(st);
     if (p->out_shape.size() != 3) throw std::runtime_error("rec model output must be [B, T, classes]");
     int T = (int)p->out_shape[1], C = (int)p->out_shape[2];
     int rows = b * T;
-    int* d_idx = (int*)d_batch_.get((size_t)rows * (sizeof(int) + 2 * sizeof(float)));
+    int* d_idx = (int*)d_lane_[lane].get((size_t)rows * (sizeof(int) + 2 * sizeof(float)));
     float* d_mx = (float*)(d_idx + rows);
     float* d_scr = d_mx + rows;
     if (p->head_rows > 0) {                      // fused CTC head: argmax / max came out of the GEMM epilogue
-        ctc_collapse_kernel<<<(unsigned)ceil_div(b, 64), 64, 0, st_>>>(p->head_idx(), p->head_prob(), b, T, d_slots, max_len,
-                                                                        d_ids, d_lens, d_scores, d_scr);
+        ctc_collapse_kernel<<<(unsigned)ceil_div(b, 64), 64, 0, st>>>(p->head_idx(), p->head_prob(), b, T, d_slots, max_len,
+                                                                       d_ids, d_lens, d_scores, d_scr);
         launches += p->launches + 2;
         B200_CUDA_CHECK(cudaGetLastError());
         return;
     }
-    ctc_argmax_kernel<<<rows, 256, 0, st_>>>(p->out_dense, C, d_idx, d_mx);
-    ctc_collapse_kernel<<<(unsigned)ceil_div(b, 64), 64, 0, st_>>>(d_idx, d_mx, b, T, d_slots, max_len, d_ids, d_lens,
-                                                                    d_scores, d_scr);
+    ctc_argmax_kernel<<<rows, 256, 0, st>>>(p->out_dense, C, d_idx, d_mx);
+    ctc_collapse_kernel<<<(unsigned)ceil_div(b, 64), 64, 0, st>>>(d_idx, d_mx, b, T, d_slots, max_len, d_ids, d_lens,
+                                                                   d_scores, d_scr);
     launches += p->launches + 3;
     B200_CUDA_CHECK(cudaGetLastError());
+}
+
+// Runs the rec batches [beg, end) of equal imgW (given in `imgw_sorted`) and spreads small ones over the auxiliary
+// streams.  Everything enqueued on the engine stream so far is visible to the auxiliary streams, and the engine stream
+// continues only after all of them have finished.
+void Stages::rec_batches(Model* rec, const ResizeJob* d_jobs, const int* d_slots, const std::vector<int>& imgw_sorted,
+                         int img_h, int max_len, int* d_ids, int* d_lens, float* d_scores) {
+    const int total = (int)imgw_sorted.size();
+    const int max_batch = 256, small_batch = 48;
+    std::vector<std::pair<int, int>> batches;
+    for (int beg = 0; beg < total;) {
+        int end = beg;
+        while (end < total && imgw_sorted[end] == imgw_sorted[beg] && end - beg < max_batch) ++end;
+        batches.push_back({beg, end});
+        beg = end;
+    }
+    int n_small = 0;
+    for (auto& be : batches) n_small += (be.second - be.first) <= small_batch;
+    const bool fan_out = n_small >= 2 && kAux > 0;
+    if (fan_out) {
+        B200_CUDA_CHECK(cudaEventRecord(ev_fork_, st_));
+        for (int a = 0; a < kAux; ++a) B200_CUDA_CHECK(cudaStreamWaitEvent(aux_[a], ev_fork_, 0));
+    }
+    int rr = 0;
+    std::vector<char> used(kAux, 0);
+    for (auto& be : batches) {
+        int b = be.second - be.first, W = imgw_sorted[be.first];
+        int lane = 0;
+        if (fan_out && b <= small_batch) {
+            lane = 1 + (rr++ % kAux);
+            used[lane - 1] = 1;
+        }
+        rec_batch(rec, d_jobs + be.first, d_slots + be.first, b, img_h, W, max_len, d_ids, d_lens, d_scores, lane);
+    }
+    if (fan_out)
+        for (int a = 0; a < kAux; ++a)
+            if (used[a]) {
+                B200_CUDA_CHECK(cudaEventRecord(ev_join_[a], aux_[a]));
+                B200_CUDA_CHECK(cudaStreamWaitEvent(st_, ev_join_[a], 0));
+            }
 }
 
 // session.run + `preds.argmax(axis=2)` / `preds.max(axis=2)` (predict_rec.py:316, rec_postprocess.py:100-101) for a
@@ -473,14 +526,7 @@ void Stages::rec_crops(Model* rec, const uint8_t* const* crops, const int* hs, c
     int* d_lens = d_ids + (size_t)n * max_len;
     float* d_scores = (float*)(d_lens + n);
     B200_CUDA_CHECK(cudaMemsetAsync(d_ids, 0, (size_t)n * max_len * sizeof(int), st_));
-    const int max_batch = 256;
-    for (int beg = 0; beg < n;) {
-        int end = beg;
-        while (end < n && imgw[end] == imgw[beg] && end - beg < max_batch) ++end;
-        int b = end - beg, W = imgw[beg];
-        rec_batch(rec, d_jobs + beg, d_slots + beg, b, img_h, W, max_len, d_ids, d_lens, d_scores);
-        beg = end;
-    }
+    rec_batches(rec, d_jobs, d_slots, imgw, img_h, max_len, d_ids, d_lens, d_scores);
     B200_CUDA_CHECK(cudaMemcpyAsync(ids_out, d_ids, (size_t)n * max_len * sizeof(int), cudaMemcpyDeviceToHost, st_));
     B200_CUDA_CHECK(cudaMemcpyAsync(lens_out, d_lens, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st_));
     B200_CUDA_CHECK(cudaMemcpyAsync(scores_out, d_scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st_));
@@ -841,13 +887,10 @@ void Stages::ocr_pages(Model* det, Model* cls, Model* rec, const uint8_t* const*
     int* d_lens = d_ids + (size_t)total * max_len;
     float* d_scores = (float*)(d_lens + total);
     B200_CUDA_CHECK(cudaMemsetAsync(d_ids, 0, (size_t)total * max_len * sizeof(int), st_));
-    const int max_batch = 256;
-    for (int beg = 0; beg < total;) {
-        int end = beg;
-        while (end < total && imgw[rorder[end]] == imgw[rorder[beg]] && end - beg < max_batch) ++end;
-        int b = end - beg, W = imgw[rorder[beg]];
-        rec_batch(rec, d_rj + beg, d_rslot + beg, b, img_h, W, max_len, d_ids, d_lens, d_scores);
-        beg = end;
+    {
+        std::vector<int> imgw_sorted(total);
+        for (int k = 0; k < total; ++k) imgw_sorted[k] = imgw[rorder[k]];
+        rec_batches(rec, d_rj, d_rslot, imgw_sorted, img_h, max_len, d_ids, d_lens, d_scores);
     }
     ocr_ms[4] = ms_since(t0); t0 = now();
     B200_CUDA_CHECK(cudaMemcpyAsync(ids_out, d_ids, (size_t)total * max_len * sizeof(int), cudaMemcpyDeviceToHost, st_));

@@ -85,7 +85,13 @@ private:
                      std::vector<std::vector<float>>* boxes_pp, float* probmap_out, size_t probmap_capacity,
                      int* probmap_dims_out);
     void rec_batch(Model* rec, const struct ResizeJob* d_jobs, const int* d_slots, int b, int img_h, int W, int max_len,
-                   int* d_ids, int* d_lens, float* d_scores);
+                   int* d_ids, int* d_lens, float* d_scores, int lane);
+    void rec_batches(Model* rec, const struct ResizeJob* d_jobs, const int* d_slots, const std::vector<int>& imgw_sorted,
+                     int img_h, int max_len, int* d_ids, int* d_lens, float* d_scores);
+    static constexpr int kAux = 8;              // auxiliary streams for independent small rec batches
+    cudaStream_t aux_[kAux];
+    cudaEvent_t ev_fork_, ev_join_[kAux];
+    DevBuf d_lane_[kAux + 1];                   // per-stream CTC scratch
     // device-side DBPostProcess on a device-resident fp32 probability map [n][h][w]; results on the host
     void db_postprocess_device(const float* d_prob, int n, int h, int w, const int* src_hs, const int* src_ws,
                                const b200ocr_det_params& p, int capacity, std::vector<int32_t>* boxes,

@@ -12,6 +12,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace b200ocr {
@@ -33,6 +35,13 @@ struct Params {
     int convT;                   // 1: column = tap * ctC + co, stored pixel-shuffled to (2y + dy, 2x + dx)
     int ctC, ctCout;             // convT: padded / real output channels
     Epilogue epi;
+    // convT -> convT(2x2, stride 2, <= 1 output channel) -> activation fused into the epilogue (the DB head's tail):
+    // ct2_w = [4 taps][ctC] second-stage weights followed by its bias; ct2_out = dense fp32 [N][4H][4W]
+    int ws_bn, ws_stages;        // weight-stationary kernel: output-channel tile width and activation ring depth
+    int ct2;
+    const float* ct2_w;
+    float* ct2_out;
+    Epilogue epi2;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,9 +117,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                  : "r"(taddr));
 }
 
+constexpr int CT2_MAX_C = 32;     // fused second transposed conv: 4 * ctC columns must fit one 128-column tile
 template <int BN>
 constexpr size_t smem_bytes() {
-    return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*alignment slack*/ + 256 /*barriers*/ +
+           (4 * CT2_MAX_C + 4) * 4 /*second-stage convT weights*/;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -162,6 +173,49 @@ __device__ __forceinline__ void epilogue_row(uint32_t trow, const float* __restr
     }
 }
 
+// DB head tail: this thread's accumulator row holds the first transposed conv's 4 taps x ctC channels for input pixel
+// (n, yy, xx).  Bias + activation give the 2x2 block of mid-resolution pixels; each of them goes through the second
+// transposed conv (ctC -> 1 channel, 2x2) and its activation, yielding a 4x4 block of the final map, stored as four
+// 16-byte rows of the dense fp32 output.  The mid-resolution tensor never reaches HBM.
+template <int ACT>
+__device__ __forceinline__ void epilogue_row_ct2(uint32_t trow, const float* __restrict__ bias, const float* __restrict__ w2s,
+                                                 bool valid, int m, const Params& p) {
+    float res[4][4];
+    const float b2 = w2s[4 * p.ctC];
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+        float a[4] = {b2, b2, b2, b2};
+#pragma unroll 1
+        for (int cc = 0; cc < p.ctC; cc += 8) {
+            uint32_t v[8];
+            tmem_ld8(trow + (uint32_t)(tap * p.ctC + cc), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const float* bp = bias + tap * p.ctC + cc;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float f = (cc + j < p.ctCout) ? epi_fast<ACT>(__uint_as_float(v[j]) + bp[j], p.epi) : 0.f;
+#pragma unroll
+                for (int t2 = 0; t2 < 4; ++t2) a[t2] = fmaf(f, w2s[t2 * p.ctC + cc + j], a[t2]);
+            }
+        }
+#pragma unroll
+        for (int t2 = 0; t2 < 4; ++t2) res[tap][t2] = epi_apply(a[t2], p.epi2);
+    }
+    if (!valid) return;
+    int xx = m % p.W;
+    int r = m / p.W;
+    int yy = r % p.H;
+    int nn = r / p.H;
+    const int64_t OW = 4 * (int64_t)p.W;
+    float* dst = p.ct2_out + ((int64_t)nn * (4 * p.H) + 4 * yy) * OW + 4 * xx;
+#pragma unroll
+    for (int r4 = 0; r4 < 4; ++r4) {
+        const int dy = r4 >> 1, ey = r4 & 1;
+        float4 o = make_float4(res[dy * 2][ey * 2], res[dy * 2][ey * 2 + 1], res[dy * 2 + 1][ey * 2], res[dy * 2 + 1][ey * 2 + 1]);
+        *reinterpret_cast<float4*>(dst + r4 * OW) = o;
+    }
+}
+
 // Persistent kernel: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA ring runs ahead across tile
 // boundaries and two TMEM accumulators let the MMA of tile t+1 overlap the epilogue of tile t.
 template <int BN>
@@ -179,6 +233,9 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
     uint32_t* tmem_slot_ptr = (uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    float* w2s = (float*)(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
+    if (p.ct2)
+        for (int i = threadIdx.x; i < 4 * p.ctC + 1; i += kThreads) w2s[i] = p.ct2_w[i];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.taps * p.kchunks;
@@ -314,6 +371,14 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
                 ctb = ((((int64_t)nn * (2 * p.H) + 2 * yy) * (2 * p.W)) + 2 * xx) * p.ctC;
                 dst = y;
             }
+            if (p.ct2) {
+                const int m = m0 + row;
+                switch (act_code) {
+                    case EPI_RELU: epilogue_row_ct2<EPI_RELU>(trow, bias, w2s, valid, m, p); break;
+                    case EPI_HSWISH: epilogue_row_ct2<EPI_HSWISH>(trow, bias, w2s, valid, m, p); break;
+                    default: epilogue_row_ct2<-1>(trow, bias, w2s, valid, m, p); break;
+                }
+            } else
             switch (act_code) {
                 case 0: epilogue_row<BN, 0>(trow, bias, dst, valid, n0, p, ctb); break;
                 case EPI_RELU: epilogue_row<BN, EPI_RELU>(trow, bias, dst, valid, n0, p, ctb); break;
@@ -334,6 +399,470 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weight-stationary variant (the default): the layers of these mobile networks have small weight matrices, so a CTA
+// fixes its output-channel tile, loads that tile's WHOLE weight slab (all taps x K chunks) into shared memory once and
+// then streams only activation tiles through the TMA ring.  Compared with streaming A and B together this halves the
+// L2 -> SM traffic per tile (the per-SM L2 bandwidth was the limiter) and frees ring space for more A stages in flight.
+// BN (32..256) is a run-time parameter chosen so that the slab fits; with BN = 256 a 240-channel layer reads its
+// activations exactly once.  Eight epilogue warps (two per TMEM lane quarter, each taking half of the columns) drain
+// the double-buffered accumulators.
+constexpr int kWsThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int WS_MAX_STAGES = 12;
+constexpr int WS_A_BYTES = BM * BK * 2;
+constexpr size_t WS_SMEM_LIMIT = 225 * 1024;
+
+inline size_t ws_tail_bytes() { return 1024 /*alignment*/ + 512 /*barriers*/ + (4 * CT2_MAX_C + 4) * 4 + 64 + 256 * 4 /*bias slice*/; }
+// epilogue staging: 8 warps x 32 rows x (BN/2 columns bf16 + 16 bytes of padding against bank conflicts)
+inline size_t ws_stage_row_bytes(int bn) { return (size_t)bn + 16; }
+inline size_t ws_staging_bytes(int bn) { return 8 * 32 * ws_stage_row_bytes(bn); }
+inline size_t ws_slab_bytes(int bn, int nkb) { return (size_t)nkb * bn * BK * 2 + ws_staging_bytes(bn); }
+// largest BN whose slab leaves room for at least 3 activation stages; 0 when none fits
+inline int ws_pick_bn(int coutp, int nkb) {
+    int want = coutp <= 32 ? 32 : (coutp <= 64 ? 64 : (coutp <= 128 ? 128 : 256));
+    for (int bn = want; bn >= 32; bn >>= 1)
+        if (ws_slab_bytes(bn, nkb) + 3 * WS_A_BYTES + ws_tail_bytes() <= WS_SMEM_LIMIT) return bn;
+    return 0;
+}
+inline int ws_pick_stages(int bn, int nkb) {
+    size_t left = WS_SMEM_LIMIT - ws_slab_bytes(bn, nkb) - ws_tail_bytes();
+    return (int)std::min<size_t>(WS_MAX_STAGES, left / WS_A_BYTES);
+}
+inline size_t ws_smem_bytes(int bn, int nkb, int stages) { return ws_slab_bytes(bn, nkb) + (size_t)stages * WS_A_BYTES + ws_tail_bytes(); }
+
+
+// columns [c_begin, c_end) of this thread's accumulator row -> bias, activation chain, bf16, 16-byte NHWC stores
+template <int ACT>
+__device__ __forceinline__ void epilogue_cols(uint32_t trow, const float* __restrict__ bias, bf16* __restrict__ dst, bool valid,
+                                              int n0, int c_begin, int c_end, const Params& p, int64_t ct_base) {
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 16) {
+        uint32_t v[16];
+        tmem_ld8(trow + (uint32_t)c, v);
+        tmem_ld8(trow + (uint32_t)c + 8, v + 8);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int col = n0 + c + 8 * h;
+            if (valid && col < p.CoutP) {
+                float4 b0 = *reinterpret_cast<const float4*>(bias + col);
+                float4 b1 = *reinterpret_cast<const float4*>(bias + col + 4);
+                float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float o[8];
+                int64_t doff = col;
+                int lim = p.Cout - col;
+                if (p.convT) {                            // 8-column groups never straddle taps (ctC % 8 == 0)
+                    int tap = col / p.ctC, co = col - tap * p.ctC;
+                    doff = ct_base + ((int64_t)(tap >> 1) * (2 * p.W) + (tap & 1)) * p.ctC + co;
+                    lim = p.ctCout - co;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float f = epi_fast<ACT>(__uint_as_float(v[8 * h + j]) + bb[j], p.epi);
+                    o[j] = (j < lim) ? f : 0.f;
+                }
+                uint4 pk;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(o[0], o[1]);
+                __nv_bfloat162 t1 = __floats2bfloat162_rn(o[2], o[3]);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(o[4], o[5]);
+                __nv_bfloat162 t3 = __floats2bfloat162_rn(o[6], o[7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&t0);
+                pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                pk.z = *reinterpret_cast<uint32_t*>(&t2);
+                pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                *reinterpret_cast<uint4*>(dst + doff) = pk;
+            }
+        }
+    }
+}
+
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 issue two fp32 lanes per instruction)
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
+    f2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f2_t f2_pack_u(uint32_t lo, uint32_t hi) {
+    f2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f2_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
+    f2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
+    f2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+    f2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+
+// act(acc + bias) * a1 + b1 on two columns at once.  The leading affine of the chain is already folded into the
+// weights and the bias (DevWeights::tc_prefolded), hardswish is v * sat(v / 6 + 0.5): one saturating FMA per lane.
+template <int ACT>
+__device__ __forceinline__ uint32_t epi_pair(uint32_t acc_lo, uint32_t acc_hi, f2_t bias2, f2_t a1, f2_t b1, bool post,
+                                             const Epilogue& e) {
+    f2_t v = f2_add(f2_pack_u(acc_lo, acc_hi), bias2);
+    float x, y;
+    if (ACT == EPI_HSWISH) {
+        f2_unpack(v, x, y);
+        v = f2_mul(v, f2_pack(fma_sat(x, 0.16666667f, 0.5f), fma_sat(y, 0.16666667f, 0.5f)));
+    } else if (ACT == EPI_RELU) {
+        f2_unpack(v, x, y);
+        v = f2_pack(fmaxf(x, 0.f), fmaxf(y, 0.f));
+    } else if (ACT != 0) {
+        f2_unpack(v, x, y);
+        x = epi_act(x, e.act, e.pa, e.pb);
+        y = epi_act(y, e.act, e.pa, e.pb);
+        v = f2_pack(x, y);
+    }
+    if (post) v = f2_fma(v, a1, b1);
+    f2_unpack(v, x, y);
+    __nv_bfloat162 t = __floats2bfloat162_rn(x, y);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// Coalesced epilogue: columns [c_begin, c_end) of the warp's 32 accumulator rows -> bias, activation, bf16 -> a padded
+// shared-memory tile owned by this warp -> 16-byte global stores in which consecutive lanes write consecutive chunks of
+// a row (full 128-byte lines) instead of every lane writing into its own row.  `bias_s` is the CTA's bias slice in
+// shared memory (index = column inside the tile); off8 / valid describe this lane's row (offset in 8-element units).
+template <int ACT>
+__device__ __forceinline__ void epilogue_cols_staged(uint32_t trow, const float* __restrict__ bias_s, bf16* __restrict__ y,
+                                                     uint32_t off8, bool valid, int n0, int c_begin, int c_end, const Params& p,
+                                                     uint8_t* stage, int row_bytes, int lane) {
+    const int c_lim = min(c_end, p.CoutP - n0);              // columns that exist in the output tensor
+    uint8_t* my = stage + (size_t)lane * row_bytes;
+    const bool post = p.epi.a1 != 1.f || p.epi.b1 != 0.f;
+    const f2_t a1 = f2_pack(p.epi.a1, p.epi.a1), b1 = f2_pack(p.epi.b1, p.epi.b1);
+#pragma unroll 1
+    for (int c = c_begin; c < c_lim; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + (uint32_t)c, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int cl = c + 8 * h;                         // column inside the tile
+            if (cl < c_lim) {
+                const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cl);
+                const float4 b1v = *reinterpret_cast<const float4*>(bias_s + cl + 4);
+                uint4 pk;
+                pk.x = epi_pair<ACT>(v[8 * h + 0], v[8 * h + 1], f2_pack(b0.x, b0.y), a1, b1, post, p.epi);
+                pk.y = epi_pair<ACT>(v[8 * h + 2], v[8 * h + 3], f2_pack(b0.z, b0.w), a1, b1, post, p.epi);
+                pk.z = epi_pair<ACT>(v[8 * h + 4], v[8 * h + 5], f2_pack(b1v.x, b1v.y), a1, b1, post, p.epi);
+                pk.w = epi_pair<ACT>(v[8 * h + 6], v[8 * h + 7], f2_pack(b1v.z, b1v.w), a1, b1, post, p.epi);
+                const int lim = p.Cout - (n0 + cl);           // pad lanes of the last group stay zero
+                if (lim < 8) {
+                    uint32_t* w = &pk.x;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (2 * j >= lim) w[j] = 0u;
+                        else if (2 * j + 1 >= lim) w[j] &= 0x0000ffffu;
+                    }
+                }
+                *reinterpret_cast<uint4*>(my + (size_t)(cl - c_begin) * 2) = pk;
+            }
+        }
+    }
+    __syncwarp();
+    const int chunks = (c_lim - c_begin) >> 3;               // 16-byte chunks per row (CoutP % 8 == 0)
+    if (chunks > 0) {
+        int lg = 0;
+        while ((1 << lg) < chunks) ++lg;                      // lanes per row = next power of two (<= 16 for BN <= 256)
+        const int cc = lane & ((1 << lg) - 1), rsub = lane >> lg, rows_per_pass = 32 >> lg;
+        const uint32_t col8 = (uint32_t)(n0 + c_begin) >> 3;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += rows_per_pass) {
+            const int rr = r0 + rsub;
+            const uint32_t o_rr = __shfl_sync(0xffffffffu, off8, rr);
+            const int v_rr = __shfl_sync(0xffffffffu, (int)valid, rr);
+            if (cc < chunks && v_rr) {
+                uint4 val = *reinterpret_cast<const uint4*>(stage + (size_t)rr * row_bytes + (size_t)cc * 16);
+                *reinterpret_cast<uint4*>(y + ((size_t)(o_rr + col8 + cc) << 3)) = val;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// DB head tail, one half (dy) of the first transposed conv's taps: see epilogue_row_ct2.  w2q holds the second
+// convolution's weights as float4 per input channel (its 4 taps), then its bias.
+template <int ACT>
+__device__ __forceinline__ void epilogue_ct2_half(uint32_t trow, const float* __restrict__ bias, const float* __restrict__ w2q,
+                                                  bool valid, int m, int dy, const Params& p) {
+    float res[2][4];
+    const float b2 = w2q[4 * p.ctC];
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+        const int tap = dy * 2 + dx;
+        float a[4] = {b2, b2, b2, b2};
+#pragma unroll 1
+        for (int cc = 0; cc < p.ctC; cc += 8) {
+            uint32_t v[8];
+            tmem_ld8(trow + (uint32_t)(tap * p.ctC + cc), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const float* bp = bias + tap * p.ctC + cc;
+            float4 bq0 = *reinterpret_cast<const float4*>(bp), bq1 = *reinterpret_cast<const float4*>(bp + 4);
+            float bb[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float f = (cc + j < p.ctCout) ? epi_fast<ACT>(__uint_as_float(v[j]) + bb[j], p.epi) : 0.f;
+                float4 w = *reinterpret_cast<const float4*>(w2q + 4 * (cc + j));
+                a[0] = fmaf(f, w.x, a[0]);
+                a[1] = fmaf(f, w.y, a[1]);
+                a[2] = fmaf(f, w.z, a[2]);
+                a[3] = fmaf(f, w.w, a[3]);
+            }
+        }
+#pragma unroll
+        for (int t2 = 0; t2 < 4; ++t2) res[dx][t2] = epi_apply(a[t2], p.epi2);
+    }
+    if (!valid) return;
+    int xx = m % p.W;
+    int r = m / p.W;
+    int yy = r % p.H;
+    int nn = r / p.H;
+    const int64_t OW = 4 * (int64_t)p.W;
+    float* dst = p.ct2_out + ((int64_t)nn * (4 * p.H) + 4 * yy + 2 * dy) * OW + 4 * xx;
+#pragma unroll
+    for (int ey = 0; ey < 2; ++ey) {
+        float4 o = make_float4(res[0][ey * 2], res[0][ey * 2 + 1], res[1][ey * 2], res[1][ey * 2 + 1]);
+        *reinterpret_cast<float4*>(dst + ey * OW) = o;
+    }
+}
+
+__global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_b,
+                                                                const float* __restrict__ bias, bf16* __restrict__ y,
+                                                                const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int BN = p.ws_bn, STG = p.ws_stages;
+    const int nkb = p.taps * p.kchunks;
+    const int B_KB_BYTES = BN * BK * 2;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_base = base;
+    const uint32_t a_base = b_base + (uint32_t)nkb * B_KB_BYTES;
+    const uint32_t stage_base = a_base + (uint32_t)STG * WS_A_BYTES;
+    const int stage_row = BN + 16;                          // bytes per staged row (BN/2 bf16 columns + padding)
+    const uint32_t bar_base = (stage_base + 8u * 32u * (uint32_t)stage_row + 63u) & ~63u;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (WS_MAX_STAGES + s); };
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * WS_MAX_STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * WS_MAX_STAGES + 2 + a); };
+    const uint32_t b_bar = bar_base + 8u * (2 * WS_MAX_STAGES + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * WS_MAX_STAGES + 5);
+    uint32_t* tmem_slot_ptr = (uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    float* w2q = (float*)(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));
+    float* bias_s = w2q + (4 * CT2_MAX_C + 4);              // this CTA's bias slice [BN] (its output-channel tile is fixed)
+    {
+        const int nt0 = (blockIdx.x % ((p.CoutP + BN - 1) / BN)) * BN;
+        for (int i = threadIdx.x; i < BN; i += kWsThreads) bias_s[i] = bias[nt0 + i];
+    }
+    if (p.ct2) {                                            // [ci][4 taps] then the bias
+        for (int i = threadIdx.x; i < 4 * p.ctC; i += kWsThreads) w2q[i] = p.ct2_w[(i & 3) * p.ctC + (i >> 2)];
+        if (threadIdx.x == 0) w2q[4 * p.ctC] = p.ct2_w[4 * p.ctC];
+    }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = p.mode == 0 ? (p.M + BM - 1) / BM : p.tiles_x * p.tiles_y * p.N;
+    const int n_tiles = (p.CoutP + BN - 1) / BN;
+    const int my_nt = blockIdx.x % n_tiles;
+    const int n0 = my_nt * BN;
+    const int m_first = blockIdx.x / n_tiles, m_step = gridDim.x / n_tiles;
+    const uint32_t tmem_cols = (uint32_t)(2 * BN);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STG; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full_bar(a), 1);
+            mbar_init(tmem_empty_bar(a), 8);                // one arrival per epilogue warp
+        }
+        mbar_init(b_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    auto tile_origin = [&](int mt, int& m0, int& img, int& y0, int& x0) {
+        m0 = mt * BM;
+        img = 0; y0 = 0; x0 = 0;
+        if (p.mode == 1) {
+            int tx = mt % p.tiles_x;
+            int r = mt / p.tiles_x;
+            int ty = r % p.tiles_y;
+            img = r / p.tiles_y;
+            y0 = ty * p.TH;
+            x0 = tx * p.TW;
+        }
+    };
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(b_bar, (uint32_t)nkb * B_KB_BYTES);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(b_base + kb * B_KB_BYTES, &map_b, b_bar, kb * BK, n0);
+            uint32_t it = 0;
+            for (int mt = m_first; mt < m_tiles; mt += m_step) {
+                int m0, img, y0, x0;
+                tile_origin(mt, m0, img, y0, x0);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    int s = it % STG;
+                    uint32_t ph = (it / STG) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), WS_A_BYTES);
+                    int tap = kb / p.kchunks, chunk = kb - tap * p.kchunks;
+                    if (p.mode == 0) {
+                        tma_load_2d(a_base + s * WS_A_BYTES, &map_a, full_bar(s), chunk * BK, m0);
+                    } else {
+                        int ky = tap / p.kw, kx = tap - ky * p.kw;
+                        tma_load_4d(a_base + s * WS_A_BYTES, &map_a, full_bar(s), chunk * BK, x0 + kx - p.pad_l, y0 + ky - p.pad_t, img);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BN);
+            mbar_wait(b_bar, 0);
+            uint32_t it = 0, t = 0;
+            for (int mt = m_first; mt < m_tiles; mt += m_step, ++t) {
+                int acc = t & 1;
+                uint32_t aph = (t >> 1) & 1;
+                mbar_wait(tmem_empty_bar(acc), aph ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    int s = it % STG;
+                    uint32_t ph = (it / STG) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint64_t adesc = make_smem_desc(a_base + s * WS_A_BYTES);
+                    uint64_t bdesc = make_smem_desc(b_base + kb * B_KB_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(tmem_full_bar(acc));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------------------------------------------------------- epilogue: warps 2..9
+        const int q = warp & 3;                             // TMEM lane quarter this warp may touch
+        const int half = (warp - 2) >> 2;                   // which half of the tile's columns
+        const int row = q * 32 + lane;
+        const int c_begin = half * (BN / 2), c_end = c_begin + BN / 2;
+        const int act_code = p.epi.fast ? p.epi.act : -1;
+        uint32_t t = 0;
+        for (int mt = m_first; mt < m_tiles; mt += m_step, ++t) {
+            int m0, img, y0, x0;
+            tile_origin(mt, m0, img, y0, x0);
+            int acc = t & 1;
+            uint32_t aph = (t >> 1) & 1;
+            mbar_wait(tmem_full_bar(acc), aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            bool valid;
+            int64_t off;
+            if (p.mode == 0) {
+                int m = m0 + row;
+                valid = m < p.M;
+                off = (int64_t)m * p.CoutP;
+            } else {
+                int ty = row / p.TW, tx = row - ty * p.TW;
+                int yy = y0 + ty, xx = x0 + tx;
+                valid = yy < p.H && xx < p.W;
+                off = (((int64_t)img * p.H + yy) * p.W + xx) * p.CoutP;
+            }
+            const uint32_t trow = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+            int64_t ctb = 0;
+            bf16* dst = y + off;
+            if (p.convT) {                                  // mode 0 rows are input pixels (n, yy, xx)
+                int m = m0 + row;
+                int xx = m % p.W;
+                int r = m / p.W;
+                int yy = r % p.H;
+                int nn = r / p.H;
+                ctb = ((((int64_t)nn * (2 * p.H) + 2 * yy) * (2 * p.W)) + 2 * xx) * p.ctC;
+                dst = y;
+            }
+            if (p.ct2) {
+                const int m = m0 + row;
+                switch (act_code) {
+                    case EPI_RELU: epilogue_ct2_half<EPI_RELU>(trow, bias, w2q, valid, m, half, p); break;
+                    case EPI_HSWISH: epilogue_ct2_half<EPI_HSWISH>(trow, bias, w2q, valid, m, half, p); break;
+                    default: epilogue_ct2_half<-1>(trow, bias, w2q, valid, m, half, p); break;
+                }
+            } else {
+                if (p.convT) {
+                    switch (act_code) {
+                        case 0: epilogue_cols<0>(trow, bias, dst, valid, n0, c_begin, c_end, p, ctb); break;
+                        case EPI_RELU: epilogue_cols<EPI_RELU>(trow, bias, dst, valid, n0, c_begin, c_end, p, ctb); break;
+                        case EPI_HSWISH: epilogue_cols<EPI_HSWISH>(trow, bias, dst, valid, n0, c_begin, c_end, p, ctb); break;
+                        default: epilogue_cols<-1>(trow, bias, dst, valid, n0, c_begin, c_end, p, ctb); break;
+                    }
+                } else {
+                    uint8_t* stg = smem_raw + (stage_base - smem_u32(smem_raw)) + (size_t)(warp - 2) * 32 * stage_row;
+#define B200_EPI(A) epilogue_cols_staged<A>(trow, bias_s, y, (uint32_t)(off >> 3), valid, n0, c_begin, c_end, p, stg, stage_row, lane)
+                    switch (act_code) {
+                        case 0: B200_EPI(0); break;
+                        case EPI_RELU: B200_EPI(EPI_RELU); break;
+                        case EPI_HSWISH: B200_EPI(EPI_HSWISH); break;
+                        case EPI_SIGMOID: B200_EPI(EPI_SIGMOID); break;
+                        case EPI_SWISH: B200_EPI(EPI_SWISH); break;
+                        case EPI_HSIGMOID: B200_EPI(EPI_HSIGMOID); break;
+                        default: epilogue_cols<-1>(trow, bias, dst, valid, n0, c_begin, c_end, p, ctb); break;   // interpreted chain
+                    }
+#undef B200_EPI
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 

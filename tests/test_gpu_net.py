@@ -103,14 +103,16 @@ def test_rec_fused_ctc_head_bf16(engine_bf16, torch_graphs, shape):
     idx, prob = engine_bf16.rec_argmax(x)
     dense = engine_bf16.session_run(_lib.REC, x)
     assert idx.shape == dense.shape[:2]
-    # the dense path rounds the logits to bf16 before the softmax, the fused head keeps them in fp32: compare where
-    # the dense path's winner is clear, and the probabilities within the bf16 tolerance
+    # the dense path rounds the logits to bf16 before the softmax (ulp 0.06-0.12 at logit ~ 10-20, i.e. several per cent
+    # in probability), the fused head keeps them in fp32: both must pick the same class wherever the dense path's
+    # winner is clear, and agree on the probability within that rounding
     d_idx, d_prob = dense.argmax(2), dense.max(2)
     srt = np.sort(dense, axis=2)
-    clear = (srt[:, :, -1] - srt[:, :, -2]) > 0.05
+    clear = (srt[:, :, -1] - srt[:, :, -2]) > 0.25
     assert clear.mean() > 0.5
     assert (idx[clear] == d_idx[clear]).all()
-    assert np.abs(prob - d_prob)[clear].max() < 3e-2
+    assert (idx == d_idx).mean() > 0.97
+    assert np.abs(prob - d_prob)[clear].max() < 6e-2
     ref = torch_graphs("rec").run(None, {"x": x})[0]
     assert (idx == ref.argmax(2)).mean() > 0.9
     r_clear = (np.sort(ref, axis=2)[:, :, -1] - np.sort(ref, axis=2)[:, :, -2]) > 0.1
