@@ -410,15 +410,18 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 // BN (32..256) is a run-time parameter chosen so that the slab fits; with BN = 256 a 240-channel layer reads its
 // activations exactly once.  Eight epilogue warps (two per TMEM lane quarter, each taking half of the columns) drain
 // the double-buffered accumulators.
-constexpr int kWsThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kWsEpiWarps = 8;           // two per TMEM lane quarter, each taking half of the tile's columns (more warps
+                                         // measured slower: the waiting warps' barrier polling competes for issue slots)
+constexpr int kWsThreads = 64 + 32 * kWsEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr int WS_MAX_STAGES = 12;
 constexpr int WS_A_BYTES = BM * BK * 2;
 constexpr size_t WS_SMEM_LIMIT = 225 * 1024;
 
 inline size_t ws_tail_bytes() { return 1024 /*alignment*/ + 512 /*barriers*/ + (4 * CT2_MAX_C + 4) * 4 + 64 + 256 * 4 /*bias slice*/; }
-// epilogue staging: 8 warps x 32 rows x (BN/2 columns bf16 + 16 bytes of padding against bank conflicts)
-inline size_t ws_stage_row_bytes(int bn) { return (size_t)bn + 16; }
-inline size_t ws_staging_bytes(int bn) { return 8 * 32 * ws_stage_row_bytes(bn); }
+// epilogue staging: 16 warps x 32 rows x (their column part in bf16 + 16 bytes of padding against bank conflicts)
+inline int ws_parts(int bn) { (void)bn; return kWsEpiWarps / 4; }             // column parts (each a multiple of 16 columns)
+inline size_t ws_stage_row_bytes(int bn) { return (size_t)(bn / ws_parts(bn)) * 2 + 16; }
+inline size_t ws_staging_bytes(int bn) { return (size_t)kWsEpiWarps * 32 * ws_stage_row_bytes(bn); }
 inline size_t ws_slab_bytes(int bn, int nkb) { return (size_t)nkb * bn * BK * 2 + ws_staging_bytes(bn); }
 // largest BN whose slab leaves room for at least 3 activation stages; 0 when none fits
 inline int ws_pick_bn(int coutp, int nkb) {
@@ -609,50 +612,54 @@ __device__ __forceinline__ void epilogue_cols_staged(uint32_t trow, const float*
     __syncwarp();
 }
 
-// DB head tail, one half (dy) of the first transposed conv's taps: see epilogue_row_ct2.  w2q holds the second
-// convolution's weights as float4 per input channel (its 4 taps), then its bias.
+// DB head tail, one first-stage tap (dy, dx) per epilogue warp part: this thread's accumulator row holds the first
+// transposed conv's 4 taps x ctC channels for input pixel (n, yy, xx).  Bias + activation give the mid-resolution
+// pixel (2yy + dy, 2xx + dx); the second transposed conv (ctC -> 1 channel, 2x2) and its activation turn it into a 2x2
+// block of the final map, written as two 8-byte pieces of the dense fp32 output (the four parts of a row quarter
+// together cover the 4x4 block; neighbouring lanes are neighbouring xx, so a warp writes whole lines).  All TMEM
+// columns of the tap are fetched with one wait so the four output chains run with full instruction-level parallelism.
+// w2q holds the second convolution's weights as float4 per input channel (its 4 taps), then its bias.
 template <int ACT>
-__device__ __forceinline__ void epilogue_ct2_half(uint32_t trow, const float* __restrict__ bias, const float* __restrict__ w2q,
-                                                  bool valid, int m, int dy, const Params& p) {
-    float res[2][4];
+__device__ __forceinline__ void epilogue_ct2_tap(uint32_t trow, const float* __restrict__ bias_s, const float* __restrict__ w2q,
+                                                 bool valid, int m, int tap, const Params& p) {
     const float b2 = w2q[4 * p.ctC];
+    float a[4] = {b2, b2, b2, b2};
+    uint32_t v[CT2_MAX_C];
 #pragma unroll
-    for (int dx = 0; dx < 2; ++dx) {
-        const int tap = dy * 2 + dx;
-        float a[4] = {b2, b2, b2, b2};
-#pragma unroll 1
-        for (int cc = 0; cc < p.ctC; cc += 8) {
-            uint32_t v[8];
-            tmem_ld8(trow + (uint32_t)(tap * p.ctC + cc), v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const float* bp = bias + tap * p.ctC + cc;
-            float4 bq0 = *reinterpret_cast<const float4*>(bp), bq1 = *reinterpret_cast<const float4*>(bp + 4);
-            float bb[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
+    for (int cc = 0; cc < CT2_MAX_C; cc += 8)
+        if (cc < p.ctC) tmem_ld8(trow + (uint32_t)(tap * p.ctC + cc), v + cc);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const float* bp = bias_s + tap * p.ctC;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float f = (cc + j < p.ctCout) ? epi_fast<ACT>(__uint_as_float(v[j]) + bb[j], p.epi) : 0.f;
-                float4 w = *reinterpret_cast<const float4*>(w2q + 4 * (cc + j));
+    for (int cc = 0; cc < CT2_MAX_C; cc += 4) {
+        if (cc < p.ctC) {
+            const float4 bq = *reinterpret_cast<const float4*>(bp + cc);
+            const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float f = (cc + j < p.ctCout) ? epi_fast<ACT>(__uint_as_float(v[cc + j]) + bb[j], p.epi) : 0.f;
+                const float4 w = *reinterpret_cast<const float4*>(w2q + 4 * (cc + j));
                 a[0] = fmaf(f, w.x, a[0]);
                 a[1] = fmaf(f, w.y, a[1]);
                 a[2] = fmaf(f, w.z, a[2]);
                 a[3] = fmaf(f, w.w, a[3]);
             }
         }
-#pragma unroll
-        for (int t2 = 0; t2 < 4; ++t2) res[dx][t2] = epi_apply(a[t2], p.epi2);
     }
-    if (!valid) return;
-    int xx = m % p.W;
-    int r = m / p.W;
-    int yy = r % p.H;
-    int nn = r / p.H;
-    const int64_t OW = 4 * (int64_t)p.W;
-    float* dst = p.ct2_out + ((int64_t)nn * (4 * p.H) + 4 * yy + 2 * dy) * OW + 4 * xx;
+    if (valid) {
 #pragma unroll
-    for (int ey = 0; ey < 2; ++ey) {
-        float4 o = make_float4(res[0][ey * 2], res[0][ey * 2 + 1], res[1][ey * 2], res[1][ey * 2 + 1]);
-        *reinterpret_cast<float4*>(dst + ey * OW) = o;
+        for (int t2 = 0; t2 < 4; ++t2) a[t2] = epi_apply(a[t2], p.epi2);
+        const int dy = tap >> 1, dx = tap & 1;
+        int xx = m % p.W;
+        int r = m / p.W;
+        int yy = r % p.H;
+        int nn = r / p.H;
+        const int64_t OW = 4 * (int64_t)p.W;
+        float* dst = p.ct2_out + ((int64_t)nn * (4 * p.H) + 4 * yy + 2 * dy) * OW + 4 * xx + 2 * dx;
+        *reinterpret_cast<float2*>(dst) = make_float2(a[0], a[1]);            // (ey = 0, ex = 0..1)
+        *reinterpret_cast<float2*>(dst + OW) = make_float2(a[2], a[3]);       // (ey = 1, ex = 0..1)
     }
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -667,8 +674,9 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
     const uint32_t b_base = base;
     const uint32_t a_base = b_base + (uint32_t)nkb * B_KB_BYTES;
     const uint32_t stage_base = a_base + (uint32_t)STG * WS_A_BYTES;
-    const int stage_row = BN + 16;                          // bytes per staged row (BN/2 bf16 columns + padding)
-    const uint32_t bar_base = (stage_base + 8u * 32u * (uint32_t)stage_row + 63u) & ~63u;
+    const int parts = kWsEpiWarps / 4;                      // column parts of the tile shared out among the epilogue warps
+    const int stage_row = (BN / parts) * 2 + 16;            // bytes per staged row (one part in bf16 + padding)
+    const uint32_t bar_base = (stage_base + (uint32_t)kWsEpiWarps * 32u * (uint32_t)stage_row + 63u) & ~63u;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (WS_MAX_STAGES + s); };
     auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * WS_MAX_STAGES + a); };
@@ -702,7 +710,7 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), 8);                // one arrival per epilogue warp
+            mbar_init(tmem_empty_bar(a), kWsEpiWarps);      // one arrival per epilogue warp
         }
         mbar_init(b_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -785,11 +793,11 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
         }
         __syncwarp();
     } else {
-        // ---------------------------------------------------------------- epilogue: warps 2..9
+        // ---------------------------------------------------------------- epilogue: warps 2..17
         const int q = warp & 3;                             // TMEM lane quarter this warp may touch
-        const int half = (warp - 2) >> 2;                   // which half of the tile's columns
+        const int part = (warp - 2) >> 2;                   // which part of the tile's columns (0..3)
         const int row = q * 32 + lane;
-        const int c_begin = half * (BN / 2), c_end = c_begin + BN / 2;
+        const int c_begin = part * (BN / parts), c_end = part < parts ? c_begin + BN / parts : c_begin;
         const int act_code = p.epi.fast ? p.epi.act : -1;
         uint32_t t = 0;
         for (int mt = m_first; mt < m_tiles; mt += m_step, ++t) {
@@ -825,11 +833,12 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
             }
             if (p.ct2) {
                 const int m = m0 + row;
-                switch (act_code) {
-                    case EPI_RELU: epilogue_ct2_half<EPI_RELU>(trow, bias, w2q, valid, m, half, p); break;
-                    case EPI_HSWISH: epilogue_ct2_half<EPI_HSWISH>(trow, bias, w2q, valid, m, half, p); break;
-                    default: epilogue_ct2_half<-1>(trow, bias, w2q, valid, m, half, p); break;
-                }
+                for (int tap = part * (4 / parts); tap < (part + 1) * (4 / parts); ++tap)   // first-stage taps of this warp
+                    switch (act_code) {
+                        case EPI_RELU: epilogue_ct2_tap<EPI_RELU>(trow, bias_s, w2q, valid, m, tap, p); break;
+                        case EPI_HSWISH: epilogue_ct2_tap<EPI_HSWISH>(trow, bias_s, w2q, valid, m, tap, p); break;
+                        default: epilogue_ct2_tap<-1>(trow, bias_s, w2q, valid, m, tap, p); break;
+                    }
             } else {
                 if (p.convT) {
                     switch (act_code) {
