@@ -203,13 +203,12 @@ def main():
         sampler.start()
     launches0 = eng.launch_count()
     barrier()
-    dev_ms = net_ms = 0.0
+    dev_ms = 0.0
     n_boxes = 0
     for _ in range(args.steps):
         eng.l2_flush()
-        ms, nb, net = eng.det_resident_run(params, 1)
+        ms, nb, _ = eng.det_resident_run(params, 1)
         dev_ms += ms
-        net_ms += net
         n_boxes += nb
     barrier()
     launches = eng.launch_count() - launches0
@@ -241,6 +240,9 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+
+    # ---- the network alone: the two 8-page sub-batches of a step, replayed back to back as CUDA graphs
+    net_ms = 2 * eng.time_plan(_lib.DET, PAGES_PER_GPU // 2, SIDE, SIDE, iters=10)
 
     # ---- roofline of the dominant kernel class (live CUDA-event timing per launch)
     peaks = load_peaks()
@@ -281,7 +283,7 @@ def main():
                    "boxes_per_step": n_boxes / max(args.steps, 1)},
         "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
-        "network_ms_per_step": net_ms / args.steps,
+        "network_ms_per_step": net_ms,
         "roofline": roof,
         "kernel_classes": breakdown,
         "clocks": sampler.summary(),

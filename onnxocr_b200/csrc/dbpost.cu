@@ -105,10 +105,15 @@ __global__ void ccl_merge_kernel(const uint8_t* __restrict__ bm, int* __restrict
         bool hasN = y > 0, hasW = x > 0, hasE = x + 1 < w;
         bool N = hasN && bm[i - w] == v;
         bool W = hasW && bm[i - 1] == v;
+        // The link to the pixel above is implied when the left neighbour (same class, same 32-pixel segment, hence already
+        // in this pixel's run) has the same class above it: i ~ i-1 ~ i-1-w ~ i-w.  Only the first pixel of such a chain
+        // performs the union, which removes most of the atomic traffic.
+        const bool implied = N && W && (i & 31) != 0 && bm[i - w - 1] == v;
         if (v) {                                  // foreground: 8-connectivity
             bool NW = hasN && hasW && bm[i - w - 1];
             bool NE = hasN && hasE && bm[i - w + 1];
-            if (N) {
+            if (implied) {
+            } else if (N) {
                 unite(L, (int)i, (int)(i - w));
             } else {
                 if (NW) unite(L, (int)i, (int)(i - w - 1));
@@ -117,7 +122,7 @@ __global__ void ccl_merge_kernel(const uint8_t* __restrict__ bm, int* __restrict
             // ccl_init_kernel already joined W inside a 32-pixel segment; join across segment boundaries here
             if (W && (i & 31) == 0) unite(L, (int)i, (int)(i - 1));
         } else {                                  // background: 4-connectivity
-            if (N) unite(L, (int)i, (int)(i - w));
+            if (N && !implied) unite(L, (int)i, (int)(i - w));
             if (W && (i & 31) == 0) unite(L, (int)i, (int)(i - 1));
         }
     }
@@ -447,14 +452,25 @@ int grid_for(int64_t total, int block = 256) {
 void Stages::db_postprocess_device(const float* d_prob, int n, int h, int w, const int* src_hs, const int* src_ws,
                                    const b200ocr_det_params& p, int capacity, std::vector<int32_t>* boxes,
                                    std::vector<double>* scores, std::vector<int>* counts_out) {
-    if (!db_) db_ = new DbWork();
-    DbWork& W = *db_;
+    DbPending pend;
+    // lane 0's stream must see what the caller enqueued on the engine stream (the probability map)
+    B200_CUDA_CHECK(cudaEventRecord(ev_fork_, st_));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(det_st_[0], ev_fork_, 0));
+    db_post_enqueue(0, d_prob, n, h, w, src_hs, src_ws, p, capacity, &pend);
+    db_post_collect(&pend, boxes, scores, counts_out);
+}
+
+// Everything of DBPostProcess up to the result copies, enqueued on the lane's stream without any host synchronisation.
+void Stages::db_post_enqueue(int lane, const float* d_prob, int n, int h, int w, const int* src_hs, const int* src_ws,
+                             const b200ocr_det_params& p, int capacity, DbPending* pend) {
+    if (!db_lane_[lane]) db_lane_[lane] = new DbWork();
+    DbWork& W = *db_lane_[lane];
     if ((int64_t)n * h * w >= (int64_t)1 << 30) throw std::runtime_error("bad argument: probability-map batch too large for 30-bit pixel indices");
     if (h >= 60000 || w >= 60000) throw std::runtime_error("bad argument: probability map too large");
     const int64_t total = (int64_t)n * h * w;
     const int hw = h * w;
     const int maxc = std::max(1, std::min(capacity, p.max_candidates));
-    cudaStream_t st = st_;
+    cudaStream_t st = det_st_[lane];
     uint8_t* bm = (uint8_t*)W.bitmap.get((size_t)total * (p.use_dilation ? 2 : 1));
     int* L = (int*)W.labels.get((size_t)total * sizeof(int));
     int* flags = (int*)W.flags.get((size_t)total * sizeof(int));
@@ -526,6 +542,43 @@ void Stages::db_postprocess_device(const float* d_prob, int n, int h, int w, con
     B200_CUDA_CHECK(cudaMemcpyAsync(hb, res_box, (size_t)nt * 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaMemcpyAsync(hs, score, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaMemcpyAsync(hv, valid, (size_t)nt, cudaMemcpyDeviceToHost, st));
+    pend->lane = lane; pend->n = n; pend->h = h; pend->w = w; pend->maxc = maxc; pend->nt = nt;
+    pend->d_prob = d_prob; pend->p = p; pend->active = true;
+}
+
+// Waits for the lane, runs the rare large-contour fallback, and gathers the boxes of each page in cv2 order.
+void Stages::db_post_collect(DbPending* pend, std::vector<int32_t>* boxes, std::vector<double>* scores,
+                             std::vector<int>* counts_out) {
+    if (!pend->active) throw std::runtime_error("internal: collecting a det lane that has nothing pending");
+    pend->active = false;
+    DbWork& W = *db_lane_[pend->lane];
+    cudaStream_t st = det_st_[pend->lane];
+    const int n = pend->n, h = pend->h, w = pend->w, maxc = pend->maxc, nt = pend->nt;
+    const b200ocr_det_params& p = pend->p;
+    const float* d_prob = pend->d_prob;
+    const int64_t total = (int64_t)n * h * w;
+    uint8_t* bm = (uint8_t*)W.bitmap.p + (p.use_dilation ? total : 0);
+    int* cand = (int*)W.cand.p;
+    int* counts = (int*)W.counts.p;
+    int* d_src = counts + n;
+    int* npts = (int*)W.npts.p;
+    int* offs = (int*)W.offs.p;
+    float* box1 = (float*)W.box1.p;
+    uint8_t* valid = (uint8_t*)W.valid.p;
+    double* score = (double*)W.score.p;
+    int* res_box = (int*)W.res_box.p;
+    int* h_counts = (int*)W.h_counts.p;
+    char* h_res = (char*)W.h_res.p;
+    int* hb = (int*)h_res;
+    double* hs = (double*)(h_res + (size_t)nt * 8 * sizeof(int));
+    uint8_t* hv = (uint8_t*)(h_res + (size_t)nt * (8 * sizeof(int) + sizeof(double)));
+    size_t tmp_bytes = 0;
+    auto run_tail = [&]() {
+        score_kernel<<<nt, 128, 0, st>>>(d_prob, box1, valid, score, h, w, maxc, p.box_thresh);
+        unclip_kernel<<<(unsigned)ceil_div(nt, 32), 32, 0, st>>>(box1, valid, res_box, d_src, n, h, w, maxc, p.unclip_ratio,
+                                                                  (float)(p.min_size + 2));
+        launches += 2;
+    };
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
     if (h_counts[n] > 0) {
         // rare: some contour exceeded the shared-memory capacity of the warp kernel -> generic two-pass path for those

@@ -330,8 +330,8 @@ struct Arena {
 };
 }  // namespace
 
-Plan* Model::plan_for(int n, int h, int w, bool head, bool own_arena) {
-    std::vector<int> key{n, h, w, head ? 1 : 0, own_arena ? 1 : 0};
+Plan* Model::plan_for(int n, int h, int w, bool head, int own_arena, int slot) {
+    std::vector<int> key{n, h, w, head ? 1 : 0, own_arena, slot};
     auto it = plans_.find(key);
     if (it != plans_.end()) return it->second.get();
     if (plans_.size() >= 768) {                         // bounded cache (dynamic rec widths x batch sizes)
@@ -345,7 +345,7 @@ Plan* Model::plan_for(int n, int h, int w, bool head, bool own_arena) {
     return raw;
 }
 
-std::unique_ptr<Plan> Model::build_plan(int n, int h, int w, bool head, bool own_arena) {
+std::unique_ptr<Plan> Model::build_plan(int n, int h, int w, bool head, int own_arena) {
     std::unique_ptr<Plan> p(new Plan());
     p->head_mode = head;
     p->model_arena = &arena_;
@@ -355,7 +355,7 @@ std::unique_ptr<Plan> Model::build_plan(int n, int h, int w, bool head, bool own
     if (prec_ == PREC_BF16) build_steps<bf16>(*p);
     else build_steps<float>(*p);
     constexpr size_t kPrivateMax = (size_t)192 << 20, kPrivateBudget = (size_t)24 << 30;
-    if (own_arena && p->arena_bytes <= kPrivateMax && private_bytes_ + p->arena_bytes <= kPrivateBudget) {
+    if ((own_arena == 2 || (own_arena == 1 && p->arena_bytes <= kPrivateMax)) && private_bytes_ + p->arena_bytes <= kPrivateBudget) {
         B200_CUDA_CHECK(cudaMalloc(&p->own_arena, p->arena_bytes));
         p->model_arena = &p->own_arena;
         private_bytes_ += p->arena_bytes;

@@ -95,7 +95,9 @@ public:
     // head = true: the final Linear + Softmax run as the fused CTC head (no dense output; see Plan::head_*)
     // own_arena = true: give the plan a private activation slab when it is small (so independent small batches can
     // overlap on several streams); falls back to the shared slab when the private budget is exhausted.
-    Plan* plan_for(int n, int h, int w, bool head = false, bool own_arena = false);
+    //   own_arena: 0 shared slab, 1 private when small, 2 always private; slot distinguishes otherwise identical plans
+    //   that must be able to run at the same time (the two det lanes).
+    Plan* plan_for(int n, int h, int w, bool head = false, int own_arena = 0, int slot = 0);
     // Host NCHW fp32 in -> plan launched on `st` (no synchronisation); head selects the fused CTC head variant.
     Plan* launch_host_input(const float* nchw, int n, int c, int h, int w, cudaStream_t st, bool head);
     // Per-step device time (ms, averaged over iters) measured with CUDA events between launches.
@@ -107,7 +109,7 @@ public:
     std::string describe() const;
 
 private:
-    std::unique_ptr<Plan> build_plan(int n, int h, int w, bool head, bool own_arena);
+    std::unique_ptr<Plan> build_plan(int n, int h, int w, bool head, int own_arena);
     size_t private_bytes_ = 0;
     template <typename T> void build_steps(Plan& p);
     std::unique_ptr<CGraph> g_;

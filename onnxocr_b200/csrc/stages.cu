@@ -188,6 +188,8 @@ static short* g_cubic_tab[16] = {nullptr};
 Stages::Stages(cudaStream_t st) : st_(st) {
     for (auto& e : ev_) B200_CUDA_CHECK(cudaEventCreate(&e));
     for (auto& a : aux_) B200_CUDA_CHECK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    for (auto& a : det_st_) B200_CUDA_CHECK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    for (auto& e : ev_det_done_) B200_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
     for (auto& e : ev_join_) B200_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     db_ = nullptr;
@@ -195,6 +197,9 @@ Stages::Stages(cudaStream_t st) : st_(st) {
 
 Stages::~Stages() {
     for (auto& a : aux_) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+    for (auto& a : det_st_) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+    for (auto& e : ev_det_done_) cudaEventDestroy(e);
+    for (auto& d : db_lane_) db_free(d);
     cudaEventDestroy(ev_fork_);
     for (auto& e : ev_join_) cudaEventDestroy(e);
     for (auto& e : ev_) cudaEventDestroy(e);
@@ -586,30 +591,30 @@ static int filter_boxes(const int32_t* in, int n, int img_h, int img_w, std::vec
 }
 
 // All pages of a call go to the device once and stay there until their crops are cut (the warp samples the
-// full-resolution original, predict_system.py:36,51).
-void Stages::upload_pages(const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n, PagePool* pool) {
+// full-resolution original, predict_system.py:36,51).  plan_pool lays the pool out; det_on_pool uploads each page right
+// before the sub-batch that needs it is enqueued, so the copy of the next sub-batch overlaps the network of this one.
+void Stages::plan_pool(const int* hs, const int* ws, const int* strides, int n, PagePool* pool) {
     pool->off.assign(n, 0);
     pool->stride.assign(n, 0);
     size_t total = 0;
     for (int i = 0; i < n; ++i) {
-        if (!pages[i] || hs[i] <= 0 || ws[i] <= 0) throw std::runtime_error("bad argument: empty page at index " + std::to_string(i));
+        if (hs[i] <= 0 || ws[i] <= 0) throw std::runtime_error("bad argument: empty page at index " + std::to_string(i));
         pool->stride[i] = strides && strides[i] > 0 ? strides[i] : ws[i] * 3;
         if (pool->stride[i] < ws[i] * 3) throw std::runtime_error("bad argument: row stride smaller than a row at page " + std::to_string(i));
         pool->off[i] = total;
         total += ((size_t)hs[i] * pool->stride[i] + 255) & ~(size_t)255;
     }
     pool->base = (uint8_t*)d_img_.get(total);
-    for (int i = 0; i < n; ++i)
-        B200_CUDA_CHECK(cudaMemcpyAsync(pool->base + pool->off[i], pages[i], (size_t)hs[i] * pool->stride[i], cudaMemcpyHostToDevice, st_));
 }
 
-// TextDetector.__call__ for device-resident pages: equal-shaped pages run as one batch (<= 16);
+// TextDetector.__call__ for a batch of pages: equal-shaped pages run as sub-batches of up to 8 that alternate between
+// two lanes (stream + activation slab + DBPostProcess scratch each).  A lane's boxes are collected (the only host
+// synchronisation) just before the lane is reused, i.e. while the other lane's network is executing.
 // boxes[i] receives page i's filtered float32 quads (cv2 contour order), 8 floats each.
-void Stages::det_on_pool(Model* det, const PagePool& pool, const int* hs, const int* ws, int n, const b200ocr_det_params& p,
-                         std::vector<std::vector<float>>* boxes_pp, float* probmap_out, size_t probmap_capacity,
-                         int* probmap_dims_out) {
+void Stages::det_on_pool(Model* det, const PagePool& pool, const uint8_t* const* pages, const int* hs, const int* ws, int n,
+                         const b200ocr_det_params& p, std::vector<std::vector<float>>* boxes_pp, float* probmap_out,
+                         size_t probmap_capacity, int* probmap_dims_out) {
     boxes_pp->assign(n, {});
-    cudaEventRecord(ev_[0], st_);
     std::vector<int> idx(n);
     std::iota(idx.begin(), idx.end(), 0);
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
@@ -626,59 +631,80 @@ void Stages::det_on_pool(Model* det, const PagePool& pool, const int* hs, const 
         }
     }
     if (probmap_out && prob_off[n] > probmap_capacity) throw std::runtime_error("probability-map buffer too small");
-    float t_pre = 0, t_net = 0, t_post = 0;
-    const int max_batch = 16;
-    for (int g0 = 0; g0 < n;) {
-        int g1 = g0;
-        while (g1 < n && hs[idx[g1]] == hs[idx[g0]] && ws[idx[g1]] == ws[idx[g0]] && g1 - g0 < max_batch) ++g1;
-        int b = g1 - g0;
-        const DetGeom& g = geo[idx[g0]];
-        int h = hs[idx[g0]], w = ws[idx[g0]];
-        std::vector<ResizeJob> jobs(b);
-        for (int k = 0; k < b; ++k) {
-            int i = idx[g0 + k];
-            jobs[k] = make_job(pool.base + pool.off[i], h, w, pool.stride[i], g.pad_h, g.pad_w, g.dst_h, g.dst_w, 0);
-        }
-        ResizeJob* d_jobs = (ResizeJob*)d_misc_.get(sizeof(ResizeJob) * max_batch);
-        B200_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(ResizeJob) * b, cudaMemcpyHostToDevice, st_));
-        Plan* pl = det->plan_for(b, g.dst_h, g.dst_w);
-        cudaEventRecord(ev_[1], st_);
-        dim3 grid((unsigned)ceil_div(g.dst_w, 256), g.dst_h, b);
-        if (det->precision() == PREC_BF16)
-            resize_norm_kernel<bf16><<<grid, 256, 0, st_>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
-        else
-            resize_norm_kernel<float><<<grid, 256, 0, st_>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
-        cudaEventRecord(ev_[2], st_);
-        pl->launch(st_);
-        launches += pl->launches + 1;
-        cudaEventRecord(ev_[3], st_);
-        B200_CUDA_CHECK(cudaGetLastError());
-        // the dense output is [b,1,H,W] fp32 == the probability maps
-        if (probmap_out)
-            for (int k = 0; k < b; ++k)
-                B200_CUDA_CHECK(cudaMemcpyAsync(probmap_out + prob_off[idx[g0 + k]],
-                                                pl->out_dense + (size_t)k * g.dst_h * g.dst_w,
-                                                (size_t)g.dst_h * g.dst_w * sizeof(float), cudaMemcpyDeviceToHost, st_));
-        std::vector<int> sh(b, h), sw(b, w);
+    // everything enqueued on the engine stream so far (e.g. resident page uploads) is visible to the lanes
+    B200_CUDA_CHECK(cudaEventRecord(ev_fork_, st_));
+    for (int l = 0; l < kDetLanes; ++l) B200_CUDA_CHECK(cudaStreamWaitEvent(det_st_[l], ev_fork_, 0));
+
+    struct Chunk { int g0, b, h, w; };
+    DbPending pend[kDetLanes];
+    Chunk pend_chunk[kDetLanes];
+    auto collect = [&](int lane) {
+        if (!pend[lane].active) return;
         std::vector<int32_t> boxes;
         std::vector<double> scores;
         std::vector<int> counts;
-        db_postprocess_device(pl->out_dense, b, g.dst_h, g.dst_w, sh.data(), sw.data(), p, p.max_candidates, &boxes, &scores, &counts);
-        float ms;
-        cudaEventElapsedTime(&ms, ev_[1], ev_[2]); t_pre += ms;
-        cudaEventElapsedTime(&ms, ev_[2], ev_[3]); t_net += ms;
+        db_post_collect(&pend[lane], &boxes, &scores, &counts);
+        const Chunk& c = pend_chunk[lane];
         size_t bo = 0;
-        for (int k = 0; k < b; ++k) {
-            int i = idx[g0 + k];
-            filter_boxes(boxes.data() + bo * 8, counts[k], h, w, &(*boxes_pp)[i]);
+        for (int k = 0; k < c.b; ++k) {
+            int i = idx[c.g0 + k];
+            filter_boxes(boxes.data() + bo * 8, counts[k], c.h, c.w, &(*boxes_pp)[i]);
             bo += counts[k];
+        }
+    };
+    const int max_group = 16, sub = 8;
+    int turn = 0;
+    for (int g0 = 0; g0 < n;) {
+        int g1 = g0;
+        while (g1 < n && hs[idx[g1]] == hs[idx[g0]] && ws[idx[g1]] == ws[idx[g0]] && g1 - g0 < max_group) ++g1;
+        const int group = g1 - g0;
+        const int step = group > sub + sub / 2 ? sub : group;          // 16 pages -> 8 + 8; up to 12 stay together
+        for (int c0 = g0; c0 < g1; c0 += step) {
+            const int b = std::min(step, g1 - c0);
+            const int lane = turn++ % kDetLanes;
+            collect(lane);                                            // frees the lane's scratch, slab and job table
+            cudaStream_t st = det_st_[lane];
+            const DetGeom& g = geo[idx[c0]];
+            const int h = hs[idx[c0]], w = ws[idx[c0]];
+            std::vector<ResizeJob> jobs(b);
+            for (int k = 0; k < b; ++k) {
+                int i = idx[c0 + k];
+                if (pages) {
+                    if (!pages[i]) throw std::runtime_error("bad argument: null page at index " + std::to_string(i));
+                    B200_CUDA_CHECK(cudaMemcpyAsync(pool.base + pool.off[i], pages[i], (size_t)h * pool.stride[i], cudaMemcpyHostToDevice, st));
+                }
+                jobs[k] = make_job(pool.base + pool.off[i], h, w, pool.stride[i], g.pad_h, g.pad_w, g.dst_h, g.dst_w, 0);
+            }
+            ResizeJob* d_jobs = (ResizeJob*)d_lane_jobs_[lane].get(sizeof(ResizeJob) * max_group);
+            B200_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(ResizeJob) * b, cudaMemcpyHostToDevice, st));
+            Plan* pl = det->plan_for(b, g.dst_h, g.dst_w, false, /*own_arena=*/2, /*slot=*/lane);
+            dim3 grid((unsigned)ceil_div(g.dst_w, 256), g.dst_h, b);
+            if (det->precision() == PREC_BF16)
+                resize_norm_kernel<bf16><<<grid, 256, 0, st>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
+            else
+                resize_norm_kernel<float><<<grid, 256, 0, st>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
+            pl->launch(st);
+            launches += pl->launches + 1;
+            B200_CUDA_CHECK(cudaGetLastError());
+            // the dense output is [b,1,H,W] fp32 == the probability maps
+            if (probmap_out)
+                for (int k = 0; k < b; ++k)
+                    B200_CUDA_CHECK(cudaMemcpyAsync(probmap_out + prob_off[idx[c0 + k]],
+                                                    pl->out_dense + (size_t)k * g.dst_h * g.dst_w,
+                                                    (size_t)g.dst_h * g.dst_w * sizeof(float), cudaMemcpyDeviceToHost, st));
+            std::vector<int> sh(b, h), sw(b, w);
+            db_post_enqueue(lane, pl->out_dense, b, g.dst_h, g.dst_w, sh.data(), sw.data(), p, p.max_candidates, &pend[lane]);
+            pend_chunk[lane] = {c0, b, h, w};
         }
         g0 = g1;
     }
-    stage_ms[0] = t_pre;
-    stage_ms[1] = t_net;
-    stage_ms[2] = t_post;
-    stage_ms[3] = t_pre + t_net + t_post;
+    for (int k = 0; k < kDetLanes; ++k) collect((turn + k) % kDetLanes);   // oldest first
+    // later work on the engine stream (crops, cls, rec) reads the pages the lanes uploaded
+    for (int l = 0; l < kDetLanes; ++l) {
+        B200_CUDA_CHECK(cudaEventRecord(ev_det_done_[l], det_st_[l]));
+        B200_CUDA_CHECK(cudaStreamWaitEvent(st_, ev_det_done_[l], 0));
+    }
+    for (float& v : stage_ms) v = 0.f;
 }
 
 void Stages::det_pages(Model* det, const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n,
@@ -686,9 +712,9 @@ void Stages::det_pages(Model* det, const uint8_t* const* pages, const int* hs, c
                        size_t probmap_capacity, int* probmap_dims_out) {
     if (n == 0) return;
     PagePool pool;
-    upload_pages(pages, hs, ws, strides, n, &pool);
+    plan_pool(hs, ws, strides, n, &pool);
     std::vector<std::vector<float>> boxes;
-    det_on_pool(det, pool, hs, ws, n, p, &boxes, probmap_out, probmap_capacity, probmap_dims_out);
+    det_on_pool(det, pool, pages, hs, ws, n, p, &boxes, probmap_out, probmap_capacity, probmap_dims_out);
     B200_CUDA_CHECK(cudaStreamSynchronize(st_));
     for (int i = 0; i < n; ++i) {
         int m = (int)(boxes[i].size() / 8);
@@ -756,10 +782,10 @@ void Stages::ocr_pages(Model* det, Model* cls, Model* rec, const uint8_t* const*
     auto ms_since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<float, std::milli>(now() - t0).count(); };
     auto t0 = now();
     PagePool pool;
-    upload_pages(pages, hs, ws, strides, n, &pool);
+    plan_pool(hs, ws, strides, n, &pool);
     ocr_ms[0] = ms_since(t0); t0 = now();
     std::vector<std::vector<float>> boxes;
-    det_on_pool(det, pool, hs, ws, n, op.det, &boxes, nullptr, 0, nullptr);
+    det_on_pool(det, pool, pages, hs, ws, n, op.det, &boxes, nullptr, 0, nullptr);
     ocr_ms[1] = ms_since(t0); t0 = now();
     int total = 0;
     for (int i = 0; i < n; ++i) {
@@ -947,46 +973,26 @@ void Stages::resident_run(Model* det, const b200ocr_det_params& p, int iters, fl
                           float* net_ms_total) {
     int n = (int)res_h_.size();
     if (n == 0) throw std::runtime_error("bad argument: no resident pages uploaded");
-    for (int i = 1; i < n; ++i)
-        if (res_h_[i] != res_h_[0] || res_w_[i] != res_w_[0]) throw std::runtime_error("bad argument: resident pages must share one shape");
-    DetGeom g = det_geometry(res_h_[0], res_w_[0], p);
-    std::vector<ResizeJob> jobs(n);
-    uint8_t* d = (uint8_t*)d_res_.p;
-    for (int i = 0; i < n; ++i)
-        jobs[i] = make_job(d + res_off_[i], res_h_[i], res_w_[i], res_stride_[i], g.pad_h, g.pad_w, g.dst_h, g.dst_w, 0);
-    ResizeJob* d_jobs = (ResizeJob*)d_misc_.get(sizeof(ResizeJob) * n);
-    B200_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(ResizeJob) * n, cudaMemcpyHostToDevice, st_));
-    Plan* pl = det->plan_for(n, g.dst_h, g.dst_w);
-    float total = 0, net_total = 0;
+    PagePool pool;
+    pool.base = (uint8_t*)d_res_.p;
+    pool.off = res_off_;
+    pool.stride = res_stride_;
+    float total = 0;
     int boxes_total = 0;
-    std::vector<int> sh(res_h_), sw(res_w_);
     for (int it = 0; it < iters; ++it) {
+        std::vector<std::vector<float>> boxes;
         cudaEventRecord(ev_[0], st_);
-        dim3 grid((unsigned)ceil_div(g.dst_w, 256), g.dst_h, n);
-        if (det->precision() == PREC_BF16)
-            resize_norm_kernel<bf16><<<grid, 256, 0, st_>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
-        else
-            resize_norm_kernel<float><<<grid, 256, 0, st_>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
-        cudaEventRecord(ev_[1], st_);
-        pl->launch(st_);
-        cudaEventRecord(ev_[2], st_);
-        launches += pl->launches + 1;
-        std::vector<int32_t> boxes;
-        std::vector<double> scores;
-        std::vector<int> counts;
-        db_postprocess_device(pl->out_dense, n, g.dst_h, g.dst_w, sh.data(), sw.data(), p, p.max_candidates, &boxes, &scores, &counts);
-        cudaEventRecord(ev_[3], st_);
+        det_on_pool(det, pool, nullptr, res_h_.data(), res_w_.data(), n, p, &boxes, nullptr, 0, nullptr);
+        cudaEventRecord(ev_[3], st_);                  // the engine stream has joined both lanes
         B200_CUDA_CHECK(cudaEventSynchronize(ev_[3]));
         float ms;
         cudaEventElapsedTime(&ms, ev_[0], ev_[3]);
         total += ms;
-        cudaEventElapsedTime(&ms, ev_[1], ev_[2]);
-        net_total += ms;
-        for (int c : counts) boxes_total += c;
+        for (auto& b : boxes) boxes_total += (int)(b.size() / 8);
     }
     if (ms_total) *ms_total = total;
     if (n_boxes_total) *n_boxes_total = boxes_total;
-    if (net_ms_total) *net_ms_total = net_total;
+    if (net_ms_total) *net_ms_total = 0.f;             // the lanes overlap network and post-processing: see b200ocr_time_plan
 }
 
 }  // namespace b200ocr

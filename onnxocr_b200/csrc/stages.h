@@ -80,10 +80,27 @@ private:
         std::vector<size_t> off;
         std::vector<int> stride;
     };
-    void upload_pages(const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n, PagePool* pool);
-    void det_on_pool(Model* det, const PagePool& pool, const int* hs, const int* ws, int n, const b200ocr_det_params& p,
-                     std::vector<std::vector<float>>* boxes_pp, float* probmap_out, size_t probmap_capacity,
-                     int* probmap_dims_out);
+    void plan_pool(const int* hs, const int* ws, const int* strides, int n, PagePool* pool);
+    // pages == nullptr: the pool already holds the pixels (resident benchmark path)
+    void det_on_pool(Model* det, const PagePool& pool, const uint8_t* const* pages, const int* hs, const int* ws, int n,
+                     const b200ocr_det_params& p, std::vector<std::vector<float>>* boxes_pp, float* probmap_out,
+                     size_t probmap_capacity, int* probmap_dims_out);
+    // Two det lanes (stream + DBPostProcess scratch + job table each): while the host waits for the boxes of one
+    // sub-batch, the network of the next one is already running on the other lane.
+    struct DbPending {
+        int lane = 0, n = 0, h = 0, w = 0, maxc = 0, nt = 0;
+        const float* d_prob = nullptr;
+        b200ocr_det_params p;
+        bool active = false;
+    };
+    void db_post_enqueue(int lane, const float* d_prob, int n, int h, int w, const int* src_hs, const int* src_ws,
+                         const b200ocr_det_params& p, int capacity, DbPending* pend);
+    void db_post_collect(DbPending* pend, std::vector<int32_t>* boxes, std::vector<double>* scores, std::vector<int>* counts);
+    static constexpr int kDetLanes = 2;
+    cudaStream_t det_st_[kDetLanes];
+    DbWork* db_lane_[kDetLanes] = {nullptr, nullptr};
+    DevBuf d_lane_jobs_[kDetLanes];
+    cudaEvent_t ev_det_done_[kDetLanes];
     void rec_batch(Model* rec, const struct ResizeJob* d_jobs, const int* d_slots, int b, int img_h, int W, int max_len,
                    int* d_ids, int* d_lens, float* d_scores, int lane);
     void rec_batches(Model* rec, const struct ResizeJob* d_jobs, const int* d_slots, const std::vector<int>& imgw_sorted,
