@@ -366,7 +366,7 @@ class Engine(object):
             counts = (C.c_int * n)()
             rc = self._L.b200ocr_ocr_pages(self._h, ptrs, hs, ws, st, n, C.byref(params), _ptr(boxes), cap, counts, _ptr(ids),
                                            max_len, _ptr(lens), _ptr(scores), _ptr(cl), _ptr(cs))
-            if rc == -4 and cap < 1000 * n:            # B200OCR_E_CAPACITY: more lines than assumed
+            if rc == -4 and line_cap is None and cap < 1000 * n:   # B200OCR_E_CAPACITY: more lines than assumed
                 cap = 1000 * n
                 continue
             self._check(rc)

@@ -557,12 +557,17 @@ __global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restric
         const int gi = threadIdx.x % G;
         const int ch = c0 + gi * 8;
         const bool ch_ok = ch < p.CP;
-        for (int pix = threadIdx.x / G; pix < rows_in * IC; pix += 256 / G) {
-            int ic = pix % IC, ir = pix / IC;
+        constexpr int STEP = 256 / G;             // pixels advanced per iteration
+        int pix = threadIdx.x / G;
+        int ir = pix / IC, ic = pix - ir * IC;
+        for (; pix < rows_in * IC; pix += STEP) {
             int iy = iy0 + ir, ix = ix0 + ic;
             bool ok = ch_ok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
             const bf16* src = ok ? x + (((int64_t)n * p.H + iy) * p.W + ix) * p.CP + ch : x;
             cp_async16_zfill(dw_tile + pix * PS + gi * 4, src, ok);
+            ic += STEP % IC;
+            ir += STEP / IC;
+            if (ic >= IC) { ic -= IC; ++ir; }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }

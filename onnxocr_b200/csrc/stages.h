@@ -80,6 +80,9 @@ private:
         std::vector<size_t> off;
         std::vector<int> stride;
     };
+    void upload_page(uint8_t* dst, const uint8_t* src, size_t bytes, cudaStream_t st);
+    PinBuf h_stage_;
+    size_t stage_cap_ = 0, stage_used_ = 0;
     void plan_pool(const int* hs, const int* ws, const int* strides, int n, PagePool* pool);
     // pages == nullptr: the pool already holds the pixels (resident benchmark path)
     void det_on_pool(Model* det, const PagePool& pool, const uint8_t* const* pages, const int* hs, const int* ws, int n,

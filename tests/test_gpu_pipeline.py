@@ -108,3 +108,39 @@ def test_ocr_bf16_text_lines(system_bf16, oracle):
         same += sum(1 for a, b in zip(got_t, exp_t) if a == b) if len(got_t) == len(exp_t) else len(set(got_t) & set(exp_t))
     assert total >= 30
     assert same / total >= 0.9, (same, total)
+
+
+def test_c5_a4_300dpi_det_matches_oracle(lib_built, model_paths):
+    """BASELINE config 5: A4 @ 300 dpi (3508 x 2480) with det_limit_side_len 2560 -> det input 2560 x 1824 (exercises
+    the real resize path of the fused pre-processing kernel and the large-map post-processing)."""
+    page = synth_pages.render_page(3508, 2480, 24, seed=300, min_px=40, max_px=64)[0]
+    oracle = OraclePipeline(model_paths, use_angle_cls=False, det_limit_side_len=2560)
+    exp, exp_map = oracle.detect(page, return_map=True)
+    eng = _lib.Engine(0)
+    eng.load_onnx(_lib.DET, model_paths["det"], _lib.FP32)
+    params = _lib.det_params(limit_side_len=2560)
+    boxes, maps = eng.det_pages([page], params, want_prob=True)
+    assert maps[0].shape == (2560, 1824) == exp_map.shape
+    assert np.abs(maps[0] - exp_map).max() < 1e-4
+    assert len(exp) >= 10
+    assert boxes[0].shape == exp.shape and np.array_equal(boxes[0], exp)
+    eng.close()
+
+
+def test_ocr_batch_bf16_c5_and_tiny_pages(system_bf16):
+    """Level C on pages of very different sizes in one call: an A4 @ 300 dpi page, a 20 x 30 page (h + w < 64: the
+    reference pads it to 32 x 32, operators.py:72-76) and a blank page."""
+    big = synth_pages.render_page(3508, 2480, 12, seed=301, min_px=40, max_px=64)[0]
+    tiny = np.full((20, 30, 3), 255, np.uint8)
+    blank = np.full((700, 500, 3), 255, np.uint8)
+    res = system_bf16.ocr_batch([big, tiny, blank])
+    assert len(res) == 3 and res[1] == [] and res[2] == []
+    assert len(res[0]) >= 8
+    assert all(len(t) > 0 and 0.5 <= s <= 1.0 for _, (t, s) in res[0])
+
+
+def test_ocr_pages_line_capacity_error(system_fp32):
+    """More lines than the caller's buffers hold is reported as an error, never truncated silently."""
+    page = synth_pages.render_page(480, 640, 9, seed=70)[0]
+    with pytest.raises(RuntimeError, match="line capacity too small"):
+        system_fp32.engine.ocr_pages([page], system_fp32._ocr_params(True), line_cap=2)
