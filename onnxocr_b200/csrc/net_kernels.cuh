@@ -901,9 +901,10 @@ __global__ void __launch_bounds__(128) conv_stem_kernel(const T* __restrict__ x,
         int64_t q = m / p.Wo;
         int oy = (int)(q % p.Ho);
         int n = (int)(q / p.Ho);
-        float acc[COUT];
+        // output channels in packed fp32x2 pairs (FFMA2), weights fetched as 16-byte broadcast loads
+        f32x2_t acc2[COUT / 2];
 #pragma unroll
-        for (int j = 0; j < COUT; ++j) acc[j] = bias[j];
+        for (int j = 0; j < COUT / 2; ++j) acc2[j] = pack_f32x2(bias[2 * j], bias[2 * j + 1]);
         for (int ky = 0; ky < p.kh; ++ky) {
             int iy = oy * p.sh - p.pt + ky;
             if ((unsigned)iy >= (unsigned)p.H) continue;
@@ -914,11 +915,20 @@ __global__ void __launch_bounds__(128) conv_stem_kernel(const T* __restrict__ x,
                 ST<T>::ld4(x + (((int64_t)n * p.H + iy) * p.W + ix) * 4, v);
                 const float* wt = sw + (ky * p.kw + kx) * 4 * COUT;
 #pragma unroll
-                for (int ci = 0; ci < 3; ++ci)
+                for (int ci = 0; ci < 3; ++ci) {
+                    const f32x2_t vv = pack_f32x2(v[ci], v[ci]);
 #pragma unroll
-                    for (int j = 0; j < COUT; ++j) acc[j] = fmaf(v[ci], wt[ci * COUT + j], acc[j]);
+                    for (int j = 0; j < COUT; j += 4) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(wt + ci * COUT + j);
+                        ffma2(acc2[j / 2], vv, pack_f32x2(w4.x, w4.y));
+                        ffma2(acc2[j / 2 + 1], vv, pack_f32x2(w4.z, w4.w));
+                    }
+                }
             }
         }
+        float acc[COUT];
+#pragma unroll
+        for (int j = 0; j < COUT / 2; ++j) unpack_f32x2(acc2[j], acc[2 * j], acc[2 * j + 1]);
         T* dst = y + m * p.CoutP;
 #pragma unroll
         for (int j = 0; j < COUT; j += 4) {

@@ -414,6 +414,7 @@ constexpr int kWsEpiWarps = 8;           // two per TMEM lane quarter, each taki
                                          // measured slower: the waiting warps' barrier polling competes for issue slots)
 constexpr int kWsThreads = 64 + 32 * kWsEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr int WS_MAX_STAGES = 12;
+constexpr int WS_MAX_ACC = 8;
 constexpr int WS_A_BYTES = BM * BK * 2;
 constexpr size_t WS_SMEM_LIMIT = 225 * 1024;
 
@@ -662,6 +663,62 @@ __device__ __forceinline__ void epilogue_ct2_tap(uint32_t trow, const float* __r
     __syncwarp();
 }
 
+// Same as epilogue_ct2_tap with the channel count fixed at compile time (the PP-OCR DB head has 24): no per-channel
+// guards, the four second-stage accumulators advance as two packed FFMA2, sigmoid through the fast exponential.
+template <int ACT, int C, bool PLAIN>
+__device__ __forceinline__ void epilogue_ct2_tap_fixed(uint32_t trow, const float* __restrict__ bias_s,
+                                                       const float* __restrict__ w2q, bool valid, int m, int tap,
+                                                       const Params& p) {
+    const float b2 = w2q[4 * C];
+    f2_t a01 = f2_pack(b2, b2), a23 = a01;
+    uint32_t v[C];
+#pragma unroll
+    for (int cc = 0; cc < C; cc += 8) tmem_ld8(trow + (uint32_t)(tap * C + cc), v + cc);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const float* bp = bias_s + tap * C;
+#pragma unroll
+    for (int cc = 0; cc < C; cc += 4) {
+        const float4 bq = *reinterpret_cast<const float4*>(bp + cc);
+        const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float f = __uint_as_float(v[cc + j]) + bb[j];
+            if (PLAIN) {
+                if (ACT == EPI_RELU) f = fmaxf(f, 0.f);
+                else if (ACT == EPI_HSWISH) f = f * fma_sat(f, 0.16666667f, 0.5f);
+            } else {
+                f = epi_fast<ACT>(f, p.epi);
+            }
+            const float4 w = *reinterpret_cast<const float4*>(w2q + 4 * (cc + j));
+            const f2_t ff = f2_pack(f, f);
+            a01 = f2_fma(ff, f2_pack(w.x, w.y), a01);
+            a23 = f2_fma(ff, f2_pack(w.z, w.w), a23);
+        }
+    }
+    if (valid) {
+        float a[4];
+        f2_unpack(a01, a[0], a[1]);
+        f2_unpack(a23, a[2], a[3]);
+        if (p.epi2.fast && p.epi2.act == EPI_SIGMOID && p.epi2.a0 == 1.f && p.epi2.b0 == 0.f && p.epi2.a1 == 1.f && p.epi2.b1 == 0.f) {
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2) a[t2] = __fdividef(1.f, 1.f + __expf(-a[t2]));
+        } else {
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2) a[t2] = epi_apply(a[t2], p.epi2);
+        }
+        const int dy = tap >> 1, dx = tap & 1;
+        int xx = m % p.W;
+        int r = m / p.W;
+        int yy = r % p.H;
+        int nn = r / p.H;
+        const int64_t OW = 4 * (int64_t)p.W;
+        float* dst = p.ct2_out + ((int64_t)nn * (4 * p.H) + 4 * yy + 2 * dy) * OW + 4 * xx + 2 * dx;
+        *reinterpret_cast<float2*>(dst) = make_float2(a[0], a[1]);
+        *reinterpret_cast<float2*>(dst + OW) = make_float2(a[2], a[3]);
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 const float* __restrict__ bias, bf16* __restrict__ y,
@@ -679,10 +736,13 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
     const uint32_t bar_base = (stage_base + (uint32_t)kWsEpiWarps * 32u * (uint32_t)stage_row + 63u) & ~63u;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (WS_MAX_STAGES + s); };
+    // accumulator ring in TMEM: as many BN-column buffers as fit (at most 8), so that the MMA warp runs several tiles
+    // ahead of the epilogue and the per-tile barrier round trips of small layers overlap instead of adding up
+    const int NACC = min(WS_MAX_ACC, 512 / BN);
     auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * WS_MAX_STAGES + a); };
-    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * WS_MAX_STAGES + 2 + a); };
-    const uint32_t b_bar = bar_base + 8u * (2 * WS_MAX_STAGES + 4);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * WS_MAX_STAGES + 5);
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * WS_MAX_STAGES + WS_MAX_ACC + a); };
+    const uint32_t b_bar = bar_base + 8u * (2 * WS_MAX_STAGES + 2 * WS_MAX_ACC);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * WS_MAX_STAGES + 2 * WS_MAX_ACC + 1);
     uint32_t* tmem_slot_ptr = (uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* w2q = (float*)(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));
     float* bias_s = w2q + (4 * CT2_MAX_C + 4);              // this CTA's bias slice [BN] (its output-channel tile is fixed)
@@ -701,14 +761,14 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
     const int my_nt = blockIdx.x % n_tiles;
     const int n0 = my_nt * BN;
     const int m_first = blockIdx.x / n_tiles, m_step = gridDim.x / n_tiles;
-    const uint32_t tmem_cols = (uint32_t)(2 * BN);
+    const uint32_t tmem_cols = (uint32_t)(NACC * BN);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STG; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < NACC; ++a) {
             mbar_init(tmem_full_bar(a), 1);
             mbar_init(tmem_empty_bar(a), kWsEpiWarps);      // one arrival per epilogue warp
         }
@@ -771,8 +831,8 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
             mbar_wait(b_bar, 0);
             uint32_t it = 0, t = 0;
             for (int mt = m_first; mt < m_tiles; mt += m_step, ++t) {
-                int acc = t & 1;
-                uint32_t aph = (t >> 1) & 1;
+                int acc = t % NACC;
+                uint32_t aph = (t / NACC) & 1;
                 mbar_wait(tmem_empty_bar(acc), aph ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -803,8 +863,8 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
         for (int mt = m_first; mt < m_tiles; mt += m_step, ++t) {
             int m0, img, y0, x0;
             tile_origin(mt, m0, img, y0, x0);
-            int acc = t & 1;
-            uint32_t aph = (t >> 1) & 1;
+            int acc = t % NACC;
+            uint32_t aph = (t / NACC) & 1;
             mbar_wait(tmem_full_bar(acc), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             bool valid;
@@ -833,7 +893,13 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
             }
             if (p.ct2) {
                 const int m = m0 + row;
+                const bool plain = p.epi.a0 == 1.f && p.epi.b0 == 0.f && p.epi.a1 == 1.f && p.epi.b1 == 0.f;
                 for (int tap = part * (4 / parts); tap < (part + 1) * (4 / parts); ++tap)   // first-stage taps of this warp
+                    if (p.ctC == 24 && p.ctCout == 24 && act_code == EPI_RELU && plain)
+                        epilogue_ct2_tap_fixed<EPI_RELU, 24, true>(trow, bias_s, w2q, valid, m, tap, p);
+                    else if (p.ctC == 24 && p.ctCout == 24 && act_code == EPI_RELU)
+                        epilogue_ct2_tap_fixed<EPI_RELU, 24, false>(trow, bias_s, w2q, valid, m, tap, p);
+                    else
                     switch (act_code) {
                         case EPI_RELU: epilogue_ct2_tap<EPI_RELU>(trow, bias_s, w2q, valid, m, tap, p); break;
                         case EPI_HSWISH: epilogue_ct2_tap<EPI_HSWISH>(trow, bias_s, w2q, valid, m, tap, p); break;
