@@ -94,6 +94,15 @@ static bool tc_ws_enabled() {             // B200OCR_TC=stream selects the A+B s
     return v == 1;
 }
 
+static bool pixel_pack_enabled() {        // B200OCR_NO_PIXEL_PACK=1 disables the packed narrow-layer GEMM (A/B measurements)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200OCR_NO_PIXEL_PACK");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 static bool dw_strip_enabled() {          // B200OCR_DW=tile selects the previous depthwise kernel (A/B measurements)
     static int v = -1;
     if (v < 0) {
@@ -181,6 +190,23 @@ Model::Model(const std::string& path, int precision) : prec_(precision) {
             d.tc_bn = bn;
             d.tc_rows = rows;
             d.tc_k = (int)K;
+            if (taps == 1 && (cinp == 16 || cinp == 32) && cw.cout == coutp && pixel_pack_enabled()) {
+                const int P = 64 / cinp, cols = P * coutp;
+                const int prow = round_up(cols, 256);
+                std::vector<bf16> pw((size_t)prow * 64, __float2bfloat16(0.f));
+                std::vector<float> pb(prow + 256, 0.f);
+                for (int j = 0; j < P; ++j)
+                    for (int co = 0; co < cw.cout; ++co) {
+                        for (int ci = 0; ci < cw.cin; ++ci)
+                            pw[(size_t)(j * coutp + co) * 64 + j * cinp + ci] = __float2bfloat16(pre_a * cw.w[(size_t)ci * cw.cout + co]);
+                        pb[j * coutp + co] = cw.bias[co] * pre_a + pre_b;
+                    }
+                B200_CUDA_CHECK(cudaMalloc(&d.pk_w, pw.size() * sizeof(bf16)));
+                B200_CUDA_CHECK(cudaMemcpy(d.pk_w, pw.data(), pw.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+                d.pk_bias = upload(pb);
+                d.pk_P = P;
+                d.pk_rows = prow;
+            }
         }
     };
     for (auto& c : g_->nodes) {
@@ -226,6 +252,8 @@ Model::~Model() {
         if (d.bias) cudaFree(d.bias);
         if (d.w_bf16) cudaFree(d.w_bf16);
         if (d.head_bias) cudaFree(d.head_bias);
+        if (d.pk_w) cudaFree(d.pk_w);
+        if (d.pk_bias) cudaFree(d.pk_bias);
         if (d.tc_bias) cudaFree(d.tc_bias);
     }
     for (auto& v : dvec_) {
@@ -640,6 +668,19 @@ void Model::build_steps(Plan& p) {
                     tp.tiles_x = (int)ceil_div(iv.w, tp.TW);
                     tp.tiles_y = (int)ceil_div(iv.h, tp.TH);
                     int bn = dw.tc_bn;
+                    // narrow pointwise layer: P pixels per GEMM row against the block-diagonal weight
+                    const void* wb_ptr = dw.w_bf16;
+                    int wb_rows = dw.tc_rows, wb_k = dw.tc_k;
+                    const float* tbias = dw.tc_bias;
+                    int icp = iv.cp;
+                    if (pointwise && !c.is_linear && dw.pk_w && dw.pk_P * iv.cp == 64 && tp.M % dw.pk_P == 0 && tc_ws_enabled()) {
+                        tp.M /= dw.pk_P;
+                        tp.Cout = tp.CoutP = dw.pk_P * cp.CoutP;
+                        tp.kchunks = 1;
+                        icp = 64;
+                        wb_ptr = dw.pk_w; wb_rows = dw.pk_rows; wb_k = 64;
+                        tbias = dw.pk_bias;
+                    }
                     // weight-stationary kernel whenever the layer's weight slab fits in shared memory
                     const int nkb = tp.taps * tp.kchunks;
                     // k x k convolutions re-read the activation tile once per tap, which dominates: they keep the streaming
@@ -652,13 +693,12 @@ void Model::build_steps(Plan& p) {
                     }
                     std::shared_ptr<TcState> ts(new TcState());
                     {
-                        uint64_t dims[2] = {(uint64_t)dw.tc_k, (uint64_t)dw.tc_rows};
-                        uint64_t str[1] = {(uint64_t)dw.tc_k * 2};
+                        uint64_t dims[2] = {(uint64_t)wb_k, (uint64_t)wb_rows};
+                        uint64_t str[1] = {(uint64_t)wb_k * 2};
                         uint32_t box[2] = {(uint32_t)tc::BK, (uint32_t)bn};
-                        make_tmap(&ts->map_b, dw.w_bf16, 2, dims, str, box);
+                        make_tmap(&ts->map_b, wb_ptr, 2, dims, str, box);
                     }
-                    const float* tbias = dw.tc_bias;
-                    int icp = iv.cp, iN = iv.n, iH = iv.h, iW = iv.w;
+                    int iN = iv.n, iH = iv.h, iW = iv.w;
                     const tc::Params tp0 = tp;
                     emit(std::string(ct2 ? "tcconvT2 " : tc_ct ? "tcconvT " : c.is_linear ? "tclinear " : "tcconv ") + c.name, [=](cudaStream_t st) {
                         (void)ct2_w;                                    // keeps the second-stage weights alive with the plan

@@ -41,6 +41,11 @@ struct DevWeights {
     float* bias = nullptr;         // [ColsW]
     void* w_bf16 = nullptr;        // tcgen05 operand pack: bf16 [tc_rows][tc_k], K-major (bf16 models only)
     float* tc_bias = nullptr;
+    // pixel-packed operand for narrow pointwise layers (CinP 16 / 32): P = 64 / CinP pixels form one 64-wide GEMM row and
+    // the weight becomes block diagonal [P * CoutP rows][64] — same tensors in memory, 128-byte TMA rows, P x fewer tiles
+    void* pk_w = nullptr;
+    float* pk_bias = nullptr;
+    int pk_P = 0, pk_rows = 0;
     bool tc_prefolded = false;     // the epilogue's leading affine (a0, b0) is folded into w_bf16 / tc_bias
     float* head_bias = nullptr;    // CTC head: bias with -1e30 beyond the last class (padding never wins the argmax)
     int tc_bn = 0, tc_rows = 0, tc_k = 0;
