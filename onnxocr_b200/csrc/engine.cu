@@ -896,7 +896,15 @@ void Model::build_steps(Plan& p) {
                 });
                 int64_t total4 = (int64_t)iv.n * HW * (iv.cp / 4);
                 cost_bytes = vbytes(in) + vbytes(out);
+                const int64_t total8 = (int64_t)iv.n * HW * (iv.cp / 8);
+                const bool se_x8 = std::is_same<T, bf16>::value && iv.cp % 8 == 0 && total8 < ((int64_t)1 << 31);
                 emit("se_apply " + c.name, [=](cudaStream_t st) {
+                    if (se_x8) {
+                        se_apply_bf16x8_kernel<<<grid_for(total8), 256, 0, st>>>((const bf16*)pp->ptr(in), (const float*)pp->bufptr(scale),
+                                                                                  (bf16*)pp->ptr(out), (uint32_t)HW, CP, C,
+                                                                                  (uint32_t)total8, residual, epi);
+                        return;
+                    }
                     se_apply_kernel<T><<<grid_for(total4), 256, 0, st>>>((const T*)pp->ptr(in), (const float*)pp->bufptr(scale),
                                                                           (T*)pp->ptr(out), HW, CP, C, total4, residual, epi);
                 });
@@ -1021,7 +1029,14 @@ void Model::build_steps(Plan& p) {
                 } else {
                     int64_t tot = (int64_t)av.n * av.h * av.w * (av.cp / 4);
                     cost_bytes = vbytes(a) + vbytes(bsrc) + vbytes(out);
+                    const int64_t tot8 = (int64_t)av.n * av.h * av.w * (av.cp / 8);
+                    const bool x8 = std::is_same<T, bf16>::value && av.cp % 8 == 0 && !bc && tot8 < ((int64_t)1 << 31);
                     emit("eltwise " + c.name, [=](cudaStream_t st) {
+                        if (x8) {
+                            eltwise_bf16x8_kernel<<<grid_for(tot8), 256, 0, st>>>((const bf16*)pp->ptr(a), (const bf16*)pp->ptr(bsrc),
+                                                                                  (bf16*)pp->ptr(out), ep, (uint32_t)tot8);
+                            return;
+                        }
                         eltwise_kernel<T><<<grid_for(tot), 256, 0, st>>>((const T*)pp->ptr(a), (const T*)pp->ptr(bsrc),
                                                                           (T*)pp->ptr(out), ep);
                     });

@@ -756,6 +756,36 @@ __global__ void se_apply_kernel(const T* __restrict__ x, const float* __restrict
     }
 }
 
+// bf16 fast path of se_apply_kernel: 8 channels (16 bytes) per thread, 32-bit index arithmetic, packed fp32x2 math.
+__global__ void __launch_bounds__(256) se_apply_bf16x8_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
+                                                              bf16* __restrict__ y, uint32_t HW, int CP, int C, uint32_t total8,
+                                                              int residual, const Epilogue epi) {
+    const uint32_t cg = (uint32_t)CP >> 3;
+    const uint32_t per_img = HW * cg;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += gridDim.x * blockDim.x) {
+        const uint32_t n = i / per_img;
+        const uint32_t g = i % cg;
+        const uint4 v = reinterpret_cast<const uint4*>(x)[i];
+        const float4 s0 = *reinterpret_cast<const float4*>(scale + (size_t)n * CP + g * 8);
+        const float4 s1 = *reinterpret_cast<const float4*>(scale + (size_t)n * CP + g * 8 + 4);
+        const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const uint32_t* u = &v.x;
+        uint4 o;
+        uint32_t* uo = &o.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a0 = __uint_as_float(u[j] << 16), a1 = __uint_as_float(u[j] & 0xffff0000u);
+            float t0 = a0 * sv[2 * j], t1 = a1 * sv[2 * j + 1];
+            if (epi.n) { t0 = epi_apply(t0, epi); t1 = epi_apply(t1, epi); }
+            if (residual) { t0 += a0; t1 += a1; }
+            int c = (int)g * 8 + 2 * j;
+            __nv_bfloat162 r = __floats2bfloat162_rn(c < C ? t0 : 0.f, c + 1 < C ? t1 : 0.f);
+            uo[j] = *reinterpret_cast<uint32_t*>(&r);
+        }
+        reinterpret_cast<uint4*>(y)[i] = o;
+    }
+}
+
 // ----------------------------------------------------------------------------------------
 // pooling
 // ----------------------------------------------------------------------------------------
@@ -826,6 +856,58 @@ __global__ void eltwise_kernel(const T* __restrict__ a, const T* __restrict__ b,
     }
 }
 
+// bf16 fast path of eltwise_kernel: 8 channels (16 bytes) per thread, 32-bit index arithmetic, a plain add runs as four
+// packed bf16x2 adds (fp32 inside, one rounding — identical to add-in-fp32-then-round).  Needs CP % 8 == 0, no
+// channel broadcast, fewer than 2^31 16-byte chunks.
+__global__ void __launch_bounds__(256) eltwise_bf16x8_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
+                                                             bf16* __restrict__ y, const EltP p, uint32_t total8) {
+    const uint32_t cg = (uint32_t)p.CP >> 3;
+    const uint32_t Hb = p.H / p.fh, Wb = p.W / p.fw;
+    const bool same = p.fh == 1 && p.fw == 1;
+    const bool plain_add = p.op == 0 && p.epi.n == 0 && p.C == p.CP;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += gridDim.x * blockDim.x) {
+        uint32_t bi = i;
+        uint32_t g = 0;
+        if (!same || !plain_add) {
+            g = i % cg;
+            if (!same) {
+                uint32_t q = i / cg;
+                uint32_t xw = q % (uint32_t)p.W;
+                q /= (uint32_t)p.W;
+                uint32_t yh = q % (uint32_t)p.H;
+                uint32_t n = q / (uint32_t)p.H;
+                bi = ((n * Hb + yh / (uint32_t)p.fh) * Wb + xw / (uint32_t)p.fw) * cg + g;
+            }
+        }
+        const uint4 va = reinterpret_cast<const uint4*>(a)[i];
+        const uint4 vb = reinterpret_cast<const uint4*>(b)[bi];
+        uint4 o;
+        if (plain_add) {
+            const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&va);
+            const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&vb);
+            __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) po[j] = __hadd2(pa[j], pb[j]);
+        } else {
+            const uint32_t* ua = &va.x;
+            const uint32_t* ub = &vb.x;
+            uint32_t* uo = &o.x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float a0 = __uint_as_float(ua[j] << 16), a1 = __uint_as_float(ua[j] & 0xffff0000u);
+                float b0 = __uint_as_float(ub[j] << 16), b1 = __uint_as_float(ub[j] & 0xffff0000u);
+                float t0 = p.op == 0 ? a0 + b0 : a0 * b0, t1 = p.op == 0 ? a1 + b1 : a1 * b1;
+                int c = (int)g * 8 + 2 * j;
+                t0 = c < p.C ? epi_apply(t0, p.epi) : 0.f;
+                t1 = c + 1 < p.C ? epi_apply(t1, p.epi) : 0.f;
+                __nv_bfloat162 r = __floats2bfloat162_rn(t0, t1);
+                uo[j] = *reinterpret_cast<uint32_t*>(&r);
+            }
+        }
+        reinterpret_cast<uint4*>(y)[i] = o;
+    }
+}
+
 // generic scalar version for cpad == 1 tensors
 template <typename T>
 __global__ void eltwise_scalar_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t total,
@@ -875,6 +957,20 @@ __global__ void concat_slice_vec_kernel(const T* __restrict__ src, T* __restrict
     const int vc = Cs / EPV;
     int64_t total = (int64_t)N * H * W * vc;
     const int Hs = H / fh, Ws = W / fw;
+    if (total < ((int64_t)1 << 31)) {               // 32-bit index arithmetic (64-bit divisions dominate otherwise)
+        const uint32_t t32 = (uint32_t)total, uvc = (uint32_t)vc, uW = (uint32_t)W, uH = (uint32_t)H;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < t32; i += gridDim.x * blockDim.x) {
+            uint32_t q = i / uvc;
+            int c = (int)(i - q * uvc) * EPV;
+            uint32_t r = q / uW;
+            int xw = (int)(q - r * uW);
+            uint32_t n = r / uH;
+            int yh = (int)(r - n * uH);
+            uint4 v = *reinterpret_cast<const uint4*>(src + (((int64_t)n * Hs + yh / fh) * Ws + xw / fw) * CsP + c);
+            *reinterpret_cast<uint4*>(dst + ((int64_t)q) * CdP + c_off + c) = v;
+        }
+        return;
+    }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = (int)(i % vc) * EPV;
         int64_t q = i / vc;
