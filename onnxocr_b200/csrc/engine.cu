@@ -685,11 +685,29 @@ void Model::build_steps(Plan& p) {
                     const int nkb = tp.taps * tp.kchunks;
                     // k x k convolutions re-read the activation tile once per tap, which dominates: they keep the streaming
                     // kernel (2 CTAs per SM); 1x1 / linear / transposed convolutions run weight-stationary
-                    const int ws_bn = (tc_ws_enabled() && tp.mode == 0) ? tc::ws_pick_bn(tp.CoutP, nkb) : 0;
+                    // k x k: halo mode — one (16+kh-1) x (8+kw-1) pixel tile per 64-channel chunk in smem, taps as shifted
+                    // descriptors.  Correct (tests/test_gpu_tc.py passes with B200OCR_TC_HALO=1) and it cuts the L2->SM
+                    // traffic 6x, but measured SLOWER than the per-tap re-load kernel on these layers (0.132 vs 0.096 ms
+                    // for 3x3 96->24 @ 240^2 x 8): with N = 32 the 72 small UMMAs per tile are issue-bound on the single
+                    // MMA thread and the streaming kernel runs two CTAs per SM.  Off by default until the issue loop is
+                    // restructured.
+                    static const bool halo_on = [] { const char* e = getenv("B200OCR_TC_HALO"); return e && e[0] == '1'; }();
+                    const bool halo = tp.mode == 1 && halo_on && c.kh <= 5 && c.kw <= 5;
+                    size_t stage_bytes = tc::WS_A_BYTES;
+                    if (halo) {
+                        stage_bytes = tc::ws_halo_stage_bytes(c.kh, c.kw);
+                        tp.TW = tc::WS_HALO_TW; tp.TH = tc::WS_HALO_TH;
+                        tp.tiles_x = (int)ceil_div(iv.w, tp.TW);
+                        tp.tiles_y = (int)ceil_div(iv.h, tp.TH);
+                        tp.kh = c.kh;
+                    }
+                    const int ws_bn = (tc_ws_enabled() && (tp.mode == 0 || halo)) ? tc::ws_pick_bn(tp.CoutP, nkb, stage_bytes) : 0;
                     if (ws_bn) {
                         bn = ws_bn;
                         tp.ws_bn = ws_bn;
-                        tp.ws_stages = tc::ws_pick_stages(ws_bn, nkb);
+                        tp.ws_stages = tc::ws_pick_stages(ws_bn, nkb, stage_bytes);
+                        tp.ws_halo = halo ? 1 : 0;
+                        tp.ws_stage_bytes = (int)stage_bytes;
                     }
                     std::shared_ptr<TcState> ts(new TcState());
                     {
@@ -715,6 +733,7 @@ void Model::build_steps(Plan& p) {
                                 uint64_t dims[4] = {(uint64_t)icp, (uint64_t)iW, (uint64_t)iH, (uint64_t)iN};
                                 uint64_t str[3] = {(uint64_t)icp * 2, (uint64_t)iW * icp * 2, (uint64_t)iH * iW * icp * 2};
                                 uint32_t box[4] = {(uint32_t)tc::BK, (uint32_t)tp.TW, (uint32_t)tp.TH, 1};
+                                if (tp.ws_halo) { box[1] = (uint32_t)(tp.TW + tp.kw - 1); box[2] = (uint32_t)(tp.TH + tp.kh - 1); }
                                 make_tmap(&ts->map_a, x, 4, dims, str, box);
                             }
                             ts->a_ptr = x;
@@ -723,7 +742,7 @@ void Model::build_steps(Plan& p) {
                         if (ws_bn) {
                             int n_tiles = (int)ceil_div(tp.CoutP, ws_bn);
                             int m_groups = std::max(1, std::min(m_tiles, 148 / n_tiles));
-                            size_t smem = tc::ws_smem_bytes(ws_bn, nkb, tp.ws_stages);
+                            size_t smem = tc::ws_smem_bytes(ws_bn, nkb, tp.ws_stages, tp.ws_halo ? (size_t)tp.ws_stage_bytes : (size_t)tc::WS_A_BYTES);
                             cudaFuncSetAttribute(tc::conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::WS_SMEM_LIMIT);
                             tc::conv_tc_ws_kernel<<<dim3((unsigned)(n_tiles * m_groups)), tc::kWsThreads, smem, st>>>(
                                 ts->map_a, ts->map_b, tbias, (bf16*)pp->ptr(out), tp);

@@ -38,6 +38,8 @@ struct Params {
     // convT -> convT(2x2, stride 2, <= 1 output channel) -> activation fused into the epilogue (the DB head's tail):
     // ct2_w = [4 taps][ctC] second-stage weights followed by its bias; ct2_out = dense fp32 [N][4H][4W]
     int ws_bn, ws_stages;        // weight-stationary kernel: output-channel tile width and activation ring depth
+    int ws_halo, ws_stage_bytes; // halo mode (k x k): bytes per ring stage; kh for the halo height
+    int kh;
     int ct2;
     const float* ct2_w;
     float* ct2_out;
@@ -91,6 +93,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset
     d |= (uint64_t)1 << 46;                                // descriptor version
     d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
+    return d;
+}
+
+// General form: 8-row core groups `sbo_bytes` apart and a start address that is only 128-byte aligned — the tap-shifted
+// views of a halo tile.  Measured on B200: the 128-byte swizzle is applied to the absolute shared-memory address bits
+// (exactly as the TMA unit wrote the tile), so the descriptor's "matrix base offset" field stays 0 even though the start
+// is not aligned to the 1024-byte swizzle repeat; setting it to (start >> 7) & 7 gives wrong operands.
+__device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
     return d;
 }
 
@@ -425,17 +440,26 @@ inline size_t ws_stage_row_bytes(int bn) { return (size_t)(bn / ws_parts(bn)) * 
 inline size_t ws_staging_bytes(int bn) { return (size_t)kWsEpiWarps * 32 * ws_stage_row_bytes(bn); }
 inline size_t ws_slab_bytes(int bn, int nkb) { return (size_t)nkb * bn * BK * 2 + ws_staging_bytes(bn); }
 // largest BN whose slab leaves room for at least 3 activation stages; 0 when none fits
-inline int ws_pick_bn(int coutp, int nkb) {
+// halo mode (k x k convolutions): one stage holds the (TH + kh - 1) x (TW + kw - 1) pixel halo of a 16 x 8 output tile
+// for one 64-channel chunk; the taps read it through shifted descriptors instead of re-loading it from L2 per tap
+constexpr int WS_HALO_TW = 8, WS_HALO_TH = 16;
+inline size_t ws_halo_stage_bytes(int kh, int kw) {
+    size_t b = (size_t)(WS_HALO_TH + kh - 1) * (WS_HALO_TW + kw - 1) * 128;
+    return (b + 1023) & ~(size_t)1023;
+}
+inline int ws_pick_bn(int coutp, int nkb, size_t stage_bytes = WS_A_BYTES) {
     int want = coutp <= 32 ? 32 : (coutp <= 64 ? 64 : (coutp <= 128 ? 128 : 256));
     for (int bn = want; bn >= 32; bn >>= 1)
-        if (ws_slab_bytes(bn, nkb) + 3 * WS_A_BYTES + ws_tail_bytes() <= WS_SMEM_LIMIT) return bn;
+        if (ws_slab_bytes(bn, nkb) + 3 * stage_bytes + ws_tail_bytes() <= WS_SMEM_LIMIT) return bn;
     return 0;
 }
-inline int ws_pick_stages(int bn, int nkb) {
+inline int ws_pick_stages(int bn, int nkb, size_t stage_bytes = WS_A_BYTES) {
     size_t left = WS_SMEM_LIMIT - ws_slab_bytes(bn, nkb) - ws_tail_bytes();
-    return (int)std::min<size_t>(WS_MAX_STAGES, left / WS_A_BYTES);
+    return (int)std::min<size_t>(WS_MAX_STAGES, left / stage_bytes);
 }
-inline size_t ws_smem_bytes(int bn, int nkb, int stages) { return ws_slab_bytes(bn, nkb) + (size_t)stages * WS_A_BYTES + ws_tail_bytes(); }
+inline size_t ws_smem_bytes(int bn, int nkb, int stages, size_t stage_bytes = WS_A_BYTES) {
+    return ws_slab_bytes(bn, nkb) + (size_t)stages * stage_bytes + ws_tail_bytes();
+}
 
 
 // columns [c_begin, c_end) of this thread's accumulator row -> bias, activation chain, bf16, 16-byte NHWC stores
@@ -730,7 +754,8 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_base = base;
     const uint32_t a_base = b_base + (uint32_t)nkb * B_KB_BYTES;
-    const uint32_t stage_base = a_base + (uint32_t)STG * WS_A_BYTES;
+    const uint32_t ASB = p.ws_halo ? (uint32_t)p.ws_stage_bytes : (uint32_t)WS_A_BYTES;   // bytes per activation stage
+    const uint32_t stage_base = a_base + (uint32_t)STG * ASB;
     const int parts = kWsEpiWarps / 4;                      // column parts of the tile shared out among the epilogue warps
     const int stage_row = (BN / parts) * 2 + 16;            // bytes per staged row (one part in bf16 + padding)
     const uint32_t bar_base = (stage_base + (uint32_t)kWsEpiWarps * 32u * (uint32_t)stage_row + 63u) & ~63u;
@@ -808,6 +833,17 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
             for (int mt = m_first; mt < m_tiles; mt += m_step) {
                 int m0, img, y0, x0;
                 tile_origin(mt, m0, img, y0, x0);
+                if (p.ws_halo) {
+                    const uint32_t halo_bytes = (uint32_t)(p.TH + p.kh - 1) * (uint32_t)(p.TW + p.kw - 1) * 128u;
+                    for (int ch = 0; ch < p.kchunks; ++ch, ++it) {
+                        int s = it % STG;
+                        uint32_t ph = (it / STG) & 1;
+                        mbar_wait(empty_bar(s), ph ^ 1);
+                        mbar_expect_tx(full_bar(s), halo_bytes);
+                        tma_load_4d(a_base + s * ASB, &map_a, full_bar(s), ch * BK, x0 - p.pad_l, y0 - p.pad_t, img);
+                    }
+                    continue;
+                }
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     int s = it % STG;
                     uint32_t ph = (it / STG) & 1;
@@ -836,6 +872,25 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
                 mbar_wait(tmem_empty_bar(acc), aph ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                if (p.ws_halo) {
+                    const uint32_t hw = (uint32_t)(p.TW + p.kw - 1);          // halo width in pixels
+                    for (int ch = 0; ch < p.kchunks; ++ch, ++it) {
+                        int s = it % STG;
+                        uint32_t ph = (it / STG) & 1;
+                        mbar_wait(full_bar(s), ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        for (int tap = 0; tap < p.taps; ++tap) {
+                            int ky = tap / p.kw, kx = tap - ky * p.kw;
+                            // rows of the A operand = pixels (ty + ky, tx + kx) of the halo tile: 8-pixel groups, one halo row apart
+                            uint64_t adesc = make_smem_desc_sbo(a_base + s * ASB + ((uint32_t)ky * hw + (uint32_t)kx) * 128u, hw * 128u);
+                            uint64_t bdesc = make_smem_desc(b_base + (tap * p.kchunks + ch) * B_KB_BYTES);
+#pragma unroll
+                            for (int k2 = 0; k2 < BK / 16; ++k2)
+                                umma_bf16(tmem_d, adesc + (uint64_t)(2 * k2), bdesc + (uint64_t)(2 * k2), idesc, (ch | tap | k2) != 0);
+                        }
+                        umma_commit(empty_bar(s));
+                    }
+                } else
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     int s = it % STG;
                     uint32_t ph = (it / STG) & 1;
