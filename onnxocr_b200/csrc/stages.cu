@@ -448,13 +448,14 @@ void Stages::rec_batches(Model* rec, const ResizeJob* d_jobs, const int* d_slots
         B200_CUDA_CHECK(cudaEventRecord(ev_fork_, st_));
         for (int a = 0; a < kAux; ++a) B200_CUDA_CHECK(cudaStreamWaitEvent(aux_[a], ev_fork_, 0));
     }
-    int rr = 0;
     std::vector<char> used(kAux, 0);
     for (auto& be : batches) {
         int b = be.second - be.first, W = imgw_sorted[be.first];
         int lane = 0;
         if (fan_out && b <= small_batch) {
-            lane = 1 + (rr++ % kAux);
+            // a plan (b, W) always runs on the same auxiliary stream: its private slab may still be in use by the
+            // previous wave's batch of the same shape, and stream order is what protects it
+            lane = 1 + (int)(((unsigned)b * 2654435761u + (unsigned)W * 40503u) % (unsigned)kAux);
             used[lane - 1] = 1;
         }
         rec_batch(rec, d_jobs + be.first, d_slots + be.first, b, img_h, W, max_len, d_ids, d_lens, d_scores, lane);
@@ -668,9 +669,13 @@ void Stages::det_on_pool(Model* det, const PagePool& pool, const uint8_t* const*
         }
     }
     if (probmap_out && prob_off[n] > probmap_capacity) throw std::runtime_error("probability-map buffer too small");
-    // everything enqueued on the engine stream so far (e.g. resident page uploads) is visible to the lanes
-    B200_CUDA_CHECK(cudaEventRecord(ev_fork_, st_));
-    for (int l = 0; l < kDetLanes; ++l) B200_CUDA_CHECK(cudaStreamWaitEvent(det_st_[l], ev_fork_, 0));
+    // resident pages were uploaded on the engine stream: make them visible to the lanes.  When the lanes upload the
+    // pages themselves nothing on the engine stream concerns them, and NOT waiting lets this detection overlap the
+    // recogniser work of the previous wave that is still queued there.
+    if (!pages) {
+        B200_CUDA_CHECK(cudaEventRecord(ev_fork_, st_));
+        for (int l = 0; l < kDetLanes; ++l) B200_CUDA_CHECK(cudaStreamWaitEvent(det_st_[l], ev_fork_, 0));
+    }
 
     struct Chunk { int g0, b, h, w; };
     DbPending pend[kDetLanes];
@@ -817,153 +822,191 @@ void Stages::ocr_pages(Model* det, Model* cls, Model* rec, const uint8_t* const*
     if (n == 0) return;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms_since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<float, std::milli>(now() - t0).count(); };
+    for (float& v : ocr_ms) v = 0.f;
     auto t0 = now();
     PagePool pool;
     plan_pool(hs, ws, strides, n, &pool);
-    ocr_ms[0] = ms_since(t0); t0 = now();
-    std::vector<std::vector<float>> boxes;
-    det_on_pool(det, pool, pages, hs, ws, n, op.det, &boxes, nullptr, 0, nullptr);
-    ocr_ms[1] = ms_since(t0); t0 = now();
-    int total = 0;
-    for (int i = 0; i < n; ++i) {
-        sorted_boxes(&boxes[i]);
-        n_boxes_out[i] = (int)(boxes[i].size() / 8);
-        total += n_boxes_out[i];
-    }
-    if (total > line_cap) throw std::runtime_error("line capacity too small: need " + std::to_string(total));
-    if (total == 0) {
-        B200_CUDA_CHECK(cudaStreamSynchronize(st_));
-        return;
-    }
-    // ---- crops: get_rotate_crop_image for every box of every page in one launch
-    std::vector<WarpJob> wj(total);
-    std::vector<int> ch(total), cw(total), first_line(n + 1, 0);
-    std::vector<size_t> coff(total + 1, 0);
-    int max_w = 1, max_h = 1, li = 0;
-    for (int i = 0; i < n; ++i) {
-        first_line[i] = li;
-        for (int k = 0; k < n_boxes_out[i]; ++k, ++li) {
-            const float* b = &boxes[i][(size_t)k * 8];
-            memcpy(boxes_out + (size_t)li * 8, b, 8 * sizeof(float));
-            WarpJob& j = wj[li];
-            if (!make_warp_job(b, &j)) throw std::runtime_error("degenerate box (zero-size crop) on page " + std::to_string(i));
-            j.img = pool.base + pool.off[i];
-            j.h = hs[i]; j.w = ws[i]; j.stride = pool.stride[i];
-            j.out_off = coff[li];
-            coff[li + 1] = coff[li] + (((size_t)j.cw * j.ch * 3 + 15) & ~(size_t)15);
-            ch[li] = j.rot90 ? j.cw : j.ch;
-            cw[li] = j.rot90 ? j.ch : j.cw;
-            max_w = std::max(max_w, j.cw);
-            max_h = std::max(max_h, j.ch);
-        }
-    }
-    first_line[n] = li;
-    ocr_ms[2] = ms_since(t0); t0 = now();
+    ocr_ms[0] = ms_since(t0);
     const bool use_cls = op.use_angle_cls && cls != nullptr;
-    // one device block for every job table of this call
-    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    size_t o_wj = 0, o_cj = o_wj + al(sizeof(WarpJob) * total), o_rj = o_cj + al(sizeof(ResizeJob) * total),
-           o_cs = o_rj + al(sizeof(ResizeJob) * total), o_rs = o_cs + al(sizeof(int) * total),
-           o_cl = o_rs + al(sizeof(int) * total), o_cc = o_cl + al(sizeof(int) * total), o_end = o_cc + al(sizeof(float) * total);
-    char* d_tab = (char*)d_jobs_.get(o_end);
-    WarpJob* d_wj = (WarpJob*)(d_tab + o_wj);
-    ResizeJob* d_cj = (ResizeJob*)(d_tab + o_cj);
-    ResizeJob* d_rj = (ResizeJob*)(d_tab + o_rj);
-    int* d_cslot = (int*)(d_tab + o_cs);
-    int* d_rslot = (int*)(d_tab + o_rs);
-    int* d_clabel = (int*)(d_tab + o_cl);
-    float* d_cscore = (float*)(d_tab + o_cc);
-    uint8_t* d_pool = (uint8_t*)d_crops_.get(coff[total] + 16);
-    B200_CUDA_CHECK(cudaMemcpyAsync(d_wj, wj.data(), sizeof(WarpJob) * total, cudaMemcpyHostToDevice, st_));
-    {
-        dim3 block(32, 8);
-        dim3 grid((unsigned)ceil_div(max_w, 32), (unsigned)ceil_div(max_h, 8), total);
-        warp_cubic_kernel<<<grid, block, 0, st_>>>(d_wj, cubic_tab_device(), d_pool);
-        launches += 1;
-        B200_CUDA_CHECK(cudaGetLastError());
-    }
-    // ---- cls: every batch has the same 48 x 192 canvas, so all crops of all pages form one device batch
-    if (use_cls) {
-        const int img_h = 48, img_w = 192;
-        std::vector<int> order = aspect_order(ch.data(), cw.data(), total);
-        std::vector<ResizeJob> jobs(total);
-        for (int k = 0; k < total; ++k) {
-            int i = order[k];
-            int rw = resized_w_rule(ch[i], cw[i], img_h, img_w);
-            jobs[k] = make_job(d_pool + coff[i], ch[i], cw[i], cw[i] * 3, ch[i], cw[i], img_h, rw, 0);
+    const int img_h = 48, img_w0 = 320;
+    const int batch_num = op.rec_batch_num > 0 ? op.rec_batch_num : 6;
+    // results of all waves land in pinned memory (an asynchronous copy into the caller's pageable arrays would block the
+    // host and with it the next wave's detection); copied out after the final drain
+    const size_t res_ints = (size_t)line_cap * ((size_t)max_len + 4);
+    int* h_res = (int*)h_pin2_.get(res_ints * sizeof(int));
+    int* h_ids = h_res;
+    int* h_lens = h_ids + (size_t)line_cap * max_len;
+    float* h_scores = (float*)(h_lens + line_cap);
+    int* h_clabel = (int*)(h_scores + line_cap);
+    float* h_cscore = (float*)(h_clabel + line_cap);
+    // Waves: while the recogniser of wave k runs on the engine / auxiliary streams, the host is already driving the
+    // upload + detection of wave k+1 on the det lanes.  Measured: with ordinary pages the GPU is already saturated by
+    // one wave (C4: 444 pages/s as one wave vs 386 as four — smaller det batches cost more than the overlap gains), so
+    // waves are used only when the page uploads are the long pole (A4 @ 300 dpi: 26 MB per page, +4 %).
+    size_t page_bytes = 0;
+    for (int i = 0; i < n; ++i) page_bytes += (size_t)hs[i] * pool.stride[i];
+    const int wave = (page_bytes > ((size_t)96 << 20) && n >= 8) ? std::max(4, (n + 1) / 2) : n;
+    int line0 = 0;
+    for (int p0 = 0; p0 < n; p0 += wave) {
+        const int p1 = std::min(n, p0 + wave), np = p1 - p0;
+        t0 = now();
+        PagePool sub;
+        sub.base = pool.base;
+        sub.off.assign(pool.off.begin() + p0, pool.off.begin() + p1);
+        sub.stride.assign(pool.stride.begin() + p0, pool.stride.begin() + p1);
+        std::vector<std::vector<float>> boxes;
+        det_on_pool(det, sub, pages + p0, hs + p0, ws + p0, np, op.det, &boxes, nullptr, 0, nullptr);
+        ocr_ms[1] += ms_since(t0); t0 = now();
+        int total = 0;
+        for (int i = 0; i < np; ++i) {
+            sorted_boxes(&boxes[i]);
+            n_boxes_out[p0 + i] = (int)(boxes[i].size() / 8);
+            total += n_boxes_out[p0 + i];
         }
-        B200_CUDA_CHECK(cudaMemcpyAsync(d_cj, jobs.data(), sizeof(ResizeJob) * total, cudaMemcpyHostToDevice, st_));
-        B200_CUDA_CHECK(cudaMemcpyAsync(d_cslot, order.data(), sizeof(int) * total, cudaMemcpyHostToDevice, st_));
-        const int chunk = 512;
-        for (int beg = 0; beg < total; beg += chunk) {
-            int b = std::min(chunk, total - beg);
-            Plan* p = cls->plan_for(b, img_h, img_w);
-            dim3 grid((unsigned)ceil_div(img_w, 256), img_h, b);
-            if (cls->precision() == PREC_BF16)
-                resize_norm_kernel<bf16><<<grid, 256, 0, st_>>>(d_cj + beg, img_h, img_w, p->in_ptr(), 0, rec_norm());
-            else
-                resize_norm_kernel<float><<<grid, 256, 0, st_>>>(d_cj + beg, img_h, img_w, p->in_ptr(), 0, rec_norm());
-            p->launch(st_);
-            int ncls = (int)(p->out_dense_elems / b);
-            cls_argmax_kernel<<<(unsigned)ceil_div(b, 128), 128, 0, st_>>>(p->out_dense, b, ncls, d_cslot + beg, d_clabel, d_cscore);
-            launches += p->launches + 2;
+        if (line0 + total > line_cap) {
+            cudaStreamSynchronize(st_);
+            throw std::runtime_error("line capacity too small: need more than " + std::to_string(line0 + total));
+        }
+        if (total == 0) continue;
+        // ---- crops: get_rotate_crop_image for every box of every page of the wave in one launch
+        std::vector<WarpJob> wj(total);
+        std::vector<int> ch(total), cw(total), first_line(np + 1, 0);
+        std::vector<size_t> coff(total + 1, 0);
+        int max_w = 1, max_h = 1, li = 0;
+        for (int i = 0; i < np; ++i) {
+            first_line[i] = li;
+            for (int k = 0; k < n_boxes_out[p0 + i]; ++k, ++li) {
+                const float* b = &boxes[i][(size_t)k * 8];
+                memcpy(boxes_out + (size_t)(line0 + li) * 8, b, 8 * sizeof(float));
+                WarpJob& j = wj[li];
+                if (!make_warp_job(b, &j)) {
+                    cudaStreamSynchronize(st_);
+                    throw std::runtime_error("degenerate box (zero-size crop) on page " + std::to_string(p0 + i));
+                }
+                j.img = pool.base + pool.off[p0 + i];
+                j.h = hs[p0 + i]; j.w = ws[p0 + i]; j.stride = pool.stride[p0 + i];
+                j.out_off = coff[li];
+                coff[li + 1] = coff[li] + (((size_t)j.cw * j.ch * 3 + 15) & ~(size_t)15);
+                ch[li] = j.rot90 ? j.cw : j.ch;
+                cw[li] = j.rot90 ? j.ch : j.cw;
+                max_w = std::max(max_w, j.cw);
+                max_h = std::max(max_h, j.ch);
+            }
+        }
+        first_line[np] = li;
+        ocr_ms[2] += ms_since(t0); t0 = now();
+        // one device block for every job table of this wave (reused by the next wave in stream order)
+        auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        size_t o_wj = 0, o_cj = o_wj + al(sizeof(WarpJob) * total), o_rj = o_cj + al(sizeof(ResizeJob) * total),
+               o_cs = o_rj + al(sizeof(ResizeJob) * total), o_rs = o_cs + al(sizeof(int) * total),
+               o_cl = o_rs + al(sizeof(int) * total), o_cc = o_cl + al(sizeof(int) * total), o_end = o_cc + al(sizeof(float) * total);
+        char* d_tab = (char*)d_jobs_.get(o_end);
+        WarpJob* d_wj = (WarpJob*)(d_tab + o_wj);
+        ResizeJob* d_cj = (ResizeJob*)(d_tab + o_cj);
+        ResizeJob* d_rj = (ResizeJob*)(d_tab + o_rj);
+        int* d_cslot = (int*)(d_tab + o_cs);
+        int* d_rslot = (int*)(d_tab + o_rs);
+        int* d_clabel = (int*)(d_tab + o_cl);
+        float* d_cscore = (float*)(d_tab + o_cc);
+        uint8_t* d_pool = (uint8_t*)d_crops_.get(coff[total] + 16);
+        B200_CUDA_CHECK(cudaMemcpyAsync(d_wj, wj.data(), sizeof(WarpJob) * total, cudaMemcpyHostToDevice, st_));
+        {
+            dim3 block(32, 8);
+            dim3 grid((unsigned)ceil_div(max_w, 32), (unsigned)ceil_div(max_h, 8), total);
+            warp_cubic_kernel<<<grid, block, 0, st_>>>(d_wj, cubic_tab_device(), d_pool);
+            launches += 1;
             B200_CUDA_CHECK(cudaGetLastError());
         }
-    }
-    ocr_ms[3] = ms_since(t0); t0 = now();
-    // ---- rec: the reference's plan per page (aspect order, groups of rec_batch_num, imgW = int(48 * max ratio))
-    const int img_h = 48, img_w0 = 320;
-    int batch_num = op.rec_batch_num > 0 ? op.rec_batch_num : 6;
-    std::vector<int> imgw(total);
-    for (int pg = 0; pg < n; ++pg) {
-        int l0 = first_line[pg], m = first_line[pg + 1] - l0;
-        if (m == 0) continue;
-        std::vector<int> order = aspect_order(ch.data() + l0, cw.data() + l0, m);
-        for (int beg = 0; beg < m; beg += batch_num) {
-            int end = std::min(m, beg + batch_num);
-            double max_wh = img_w0 / (double)img_h;
-            for (int k = beg; k < end; ++k) max_wh = std::max(max_wh, cw[l0 + order[k]] * 1.0 / ch[l0 + order[k]]);
-            int W = (int)(img_h * max_wh);
-            if (op.rec_width_bucket > 0) W = (int)ceil_div(W, op.rec_width_bucket) * op.rec_width_bucket;
-            for (int k = beg; k < end; ++k) imgw[l0 + order[k]] = W;
+        // ---- cls: every batch has the same 48 x 192 canvas, so all crops of the wave form one device batch
+        if (use_cls) {
+            const int cimg_w = 192;
+            std::vector<int> order = aspect_order(ch.data(), cw.data(), total);
+            std::vector<ResizeJob> jobs(total);
+            for (int k = 0; k < total; ++k) {
+                int i = order[k];
+                int rw = resized_w_rule(ch[i], cw[i], img_h, cimg_w);
+                jobs[k] = make_job(d_pool + coff[i], ch[i], cw[i], cw[i] * 3, ch[i], cw[i], img_h, rw, 0);
+            }
+            B200_CUDA_CHECK(cudaMemcpyAsync(d_cj, jobs.data(), sizeof(ResizeJob) * total, cudaMemcpyHostToDevice, st_));
+            B200_CUDA_CHECK(cudaMemcpyAsync(d_cslot, order.data(), sizeof(int) * total, cudaMemcpyHostToDevice, st_));
+            const int chunk = 512;
+            for (int beg = 0; beg < total; beg += chunk) {
+                int b = std::min(chunk, total - beg);
+                Plan* p = cls->plan_for(b, img_h, cimg_w);
+                dim3 grid((unsigned)ceil_div(cimg_w, 256), img_h, b);
+                if (cls->precision() == PREC_BF16)
+                    resize_norm_kernel<bf16><<<grid, 256, 0, st_>>>(d_cj + beg, img_h, cimg_w, p->in_ptr(), 0, rec_norm());
+                else
+                    resize_norm_kernel<float><<<grid, 256, 0, st_>>>(d_cj + beg, img_h, cimg_w, p->in_ptr(), 0, rec_norm());
+                p->launch(st_);
+                int ncls = (int)(p->out_dense_elems / b);
+                cls_argmax_kernel<<<(unsigned)ceil_div(b, 128), 128, 0, st_>>>(p->out_dense, b, ncls, d_cslot + beg, d_clabel, d_cscore);
+                launches += p->launches + 2;
+                B200_CUDA_CHECK(cudaGetLastError());
+            }
         }
-    }
-    std::vector<int> rorder(total);
-    std::iota(rorder.begin(), rorder.end(), 0);
-    std::stable_sort(rorder.begin(), rorder.end(), [&](int a, int b) { return imgw[a] < imgw[b]; });
-    {
-        std::vector<ResizeJob> jobs(total);
-        for (int k = 0; k < total; ++k) {
-            int i = rorder[k];
-            int rw = resized_w_rule(ch[i], cw[i], img_h, imgw[i]);
-            jobs[k] = make_job(d_pool + coff[i], ch[i], cw[i], cw[i] * 3, ch[i], cw[i], img_h, rw, 0);
+        ocr_ms[3] += ms_since(t0); t0 = now();
+        // ---- rec: the reference's plan per page (aspect order, groups of rec_batch_num, imgW = int(48 * max ratio))
+        std::vector<int> imgw(total);
+        for (int pg = 0; pg < np; ++pg) {
+            int l0 = first_line[pg], m = first_line[pg + 1] - l0;
+            if (m == 0) continue;
+            std::vector<int> order = aspect_order(ch.data() + l0, cw.data() + l0, m);
+            for (int beg = 0; beg < m; beg += batch_num) {
+                int end = std::min(m, beg + batch_num);
+                double max_wh = img_w0 / (double)img_h;
+                for (int k = beg; k < end; ++k) max_wh = std::max(max_wh, cw[l0 + order[k]] * 1.0 / ch[l0 + order[k]]);
+                int W = (int)(img_h * max_wh);
+                if (op.rec_width_bucket > 0) W = (int)ceil_div(W, op.rec_width_bucket) * op.rec_width_bucket;
+                for (int k = beg; k < end; ++k) imgw[l0 + order[k]] = W;
+            }
         }
-        B200_CUDA_CHECK(cudaMemcpyAsync(d_rj, jobs.data(), sizeof(ResizeJob) * total, cudaMemcpyHostToDevice, st_));
-        B200_CUDA_CHECK(cudaMemcpyAsync(d_rslot, rorder.data(), sizeof(int) * total, cudaMemcpyHostToDevice, st_));
+        std::vector<int> rorder(total);
+        std::iota(rorder.begin(), rorder.end(), 0);
+        std::stable_sort(rorder.begin(), rorder.end(), [&](int a, int b) { return imgw[a] < imgw[b]; });
+        {
+            std::vector<ResizeJob> jobs(total);
+            for (int k = 0; k < total; ++k) {
+                int i = rorder[k];
+                int rw = resized_w_rule(ch[i], cw[i], img_h, imgw[i]);
+                jobs[k] = make_job(d_pool + coff[i], ch[i], cw[i], cw[i] * 3, ch[i], cw[i], img_h, rw, 0);
+            }
+            B200_CUDA_CHECK(cudaMemcpyAsync(d_rj, jobs.data(), sizeof(ResizeJob) * total, cudaMemcpyHostToDevice, st_));
+            B200_CUDA_CHECK(cudaMemcpyAsync(d_rslot, rorder.data(), sizeof(int) * total, cudaMemcpyHostToDevice, st_));
+        }
+        if (use_cls) {                            // predict_cls.py:85-88: '180' in label and score > cls_thresh
+            rot_patch_kernel<<<(unsigned)ceil_div(total, 128), 128, 0, st_>>>(d_rj, d_rslot, total, d_clabel, d_cscore,
+                                                                             (unsigned)op.cls_rot_label_mask, op.cls_thresh);
+            launches += 1;
+        }
+        int* d_ids = (int*)d_boxes_.get(((size_t)total * max_len + 2 * (size_t)total) * sizeof(int));
+        int* d_lens = d_ids + (size_t)total * max_len;
+        float* d_scores = (float*)(d_lens + total);
+        B200_CUDA_CHECK(cudaMemsetAsync(d_ids, 0, (size_t)total * max_len * sizeof(int), st_));
+        {
+            std::vector<int> imgw_sorted(total);
+            for (int k = 0; k < total; ++k) imgw_sorted[k] = imgw[rorder[k]];
+            rec_batches(rec, d_rj, d_rslot, imgw_sorted, img_h, max_len, d_ids, d_lens, d_scores);
+        }
+        B200_CUDA_CHECK(cudaMemcpyAsync(h_ids + (size_t)line0 * max_len, d_ids, (size_t)total * max_len * sizeof(int), cudaMemcpyDeviceToHost, st_));
+        B200_CUDA_CHECK(cudaMemcpyAsync(h_lens + line0, d_lens, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, st_));
+        B200_CUDA_CHECK(cudaMemcpyAsync(h_scores + line0, d_scores, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, st_));
+        if (use_cls) {
+            B200_CUDA_CHECK(cudaMemcpyAsync(h_clabel + line0, d_clabel, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, st_));
+            B200_CUDA_CHECK(cudaMemcpyAsync(h_cscore + line0, d_cscore, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, st_));
+        }
+        ocr_ms[4] += ms_since(t0);
+        line0 += total;
     }
-    if (use_cls) {                                // predict_cls.py:85-88: '180' in label and score > cls_thresh
-        rot_patch_kernel<<<(unsigned)ceil_div(total, 128), 128, 0, st_>>>(d_rj, d_rslot, total, d_clabel, d_cscore,
-                                                                         (unsigned)op.cls_rot_label_mask, op.cls_thresh);
-        launches += 1;
-    }
-    int* d_ids = (int*)d_boxes_.get(((size_t)total * max_len + 2 * (size_t)total) * sizeof(int));
-    int* d_lens = d_ids + (size_t)total * max_len;
-    float* d_scores = (float*)(d_lens + total);
-    B200_CUDA_CHECK(cudaMemsetAsync(d_ids, 0, (size_t)total * max_len * sizeof(int), st_));
-    {
-        std::vector<int> imgw_sorted(total);
-        for (int k = 0; k < total; ++k) imgw_sorted[k] = imgw[rorder[k]];
-        rec_batches(rec, d_rj, d_rslot, imgw_sorted, img_h, max_len, d_ids, d_lens, d_scores);
-    }
-    ocr_ms[4] = ms_since(t0); t0 = now();
-    B200_CUDA_CHECK(cudaMemcpyAsync(ids_out, d_ids, (size_t)total * max_len * sizeof(int), cudaMemcpyDeviceToHost, st_));
-    B200_CUDA_CHECK(cudaMemcpyAsync(lens_out, d_lens, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, st_));
-    B200_CUDA_CHECK(cudaMemcpyAsync(scores_out, d_scores, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, st_));
-    if (use_cls && cls_labels_out)
-        B200_CUDA_CHECK(cudaMemcpyAsync(cls_labels_out, d_clabel, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, st_));
-    if (use_cls && cls_scores_out)
-        B200_CUDA_CHECK(cudaMemcpyAsync(cls_scores_out, d_cscore, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, st_));
+    t0 = now();
     B200_CUDA_CHECK(cudaStreamSynchronize(st_));
+    if (line0 > 0) {
+        memcpy(ids_out, h_ids, (size_t)line0 * max_len * sizeof(int));
+        memcpy(lens_out, h_lens, (size_t)line0 * sizeof(int));
+        memcpy(scores_out, h_scores, (size_t)line0 * sizeof(float));
+        if (use_cls && cls_labels_out) memcpy(cls_labels_out, h_clabel, (size_t)line0 * sizeof(int));
+        if (use_cls && cls_scores_out) memcpy(cls_scores_out, h_cscore, (size_t)line0 * sizeof(float));
+    }
     ocr_ms[5] = ms_since(t0);
 }
 
