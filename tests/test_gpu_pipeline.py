@@ -144,3 +144,16 @@ def test_ocr_pages_line_capacity_error(system_fp32):
     page = synth_pages.render_page(480, 640, 9, seed=70)[0]
     with pytest.raises(RuntimeError, match="line capacity too small"):
         system_fp32.engine.ocr_pages([page], system_fp32._ocr_params(True), line_cap=2)
+
+
+def test_concurrent_callers_share_one_engine(system_fp32):
+    """The reference calls `model.ocr` on ONE model object from a ThreadPoolExecutor(max_workers=4)
+    (ocr_images_pdfs.py:106,154) and from the service's executor (app/engine.py:111-120): concurrent calls must be
+    safe and give the same results as sequential ones."""
+    from concurrent.futures import ThreadPoolExecutor
+    pages = [synth_pages.render_page(384, 512, 6, seed=400 + i, rot180_frac=0.2)[0] for i in range(8)]
+    expected = [system_fp32.ocr(p)[0] for p in pages]
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        got = list(ex.map(lambda p: system_fp32.ocr(p)[0], pages))
+    assert got == expected
+    assert sum(len(r) for r in expected) >= 24
