@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
+#include <utility>
 #include <stdexcept>
 #include <string>
 
@@ -53,6 +55,41 @@ template <> struct ST<bf16> {
         *reinterpret_cast<uint2*>(p) = t;
     }
 };
+
+// Programmatic dependent launch (PDL): every network kernel lets its successor's CTAs be scheduled while it is still
+// running (launch_dependents at entry) and itself waits for its predecessor to complete and flush before it touches
+// activation memory (wait).  With ~80 short kernels per plan this hides the launch / drain latency between them.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_start() { pdl_trigger(); pdl_wait(); }
+
+// Measured on B200 (tools/time_plans.py, CUDA-graph replay): no difference within noise for any plan (det 16 pages
+// 2.565 vs 2.576 ms, rec 6 crops 0.596 vs 0.587 ms) — the ~9 us per small kernel is its own serial TMA -> MMA -> epilogue
+// latency, not the gap between kernels.  Off unless B200OCR_PDL=1; without the launch attribute both instructions are
+// no-ops.
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200OCR_PDL");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 __device__ __forceinline__ float epi_act(float v, int type, float a, float b) {
     switch (type) {

@@ -457,7 +457,7 @@ void Model::build_steps(Plan& p) {
         use(src);
         int cp = pv.cp, fh = pv.fh, fw = pv.fw, N = pv.n, H = pv.h, W = pv.w;
         emit("upsample", [=](cudaStream_t st) {
-            concat_slice_kernel<T><<<grid_for((int64_t)N * H * W * cp), 256, 0, st>>>(
+            launch_pdl(concat_slice_kernel<T>, grid_for((int64_t)N * H * W * cp), 256, 0, st, 
                 (const T*)pp->ptr(src), (T*)pp->ptr(out), N, H, W, cp, cp, cp, 0, fh, fw);
         });
         return out;
@@ -597,12 +597,12 @@ void Model::build_steps(Plan& p) {
                             ts->a_ptr = x;
                         }
                         cudaFuncSetAttribute(tc::ctc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                        tc::ctc_head_kernel<<<dim3(m_tiles, splits), tc::kThreads, smem, st>>>(
+                        launch_pdl(tc::ctc_head_kernel, dim3(m_tiles, splits), tc::kThreads, smem, st, 
                             ts->map_a, ts->map_b, hbias, (float*)pp->bufptr(b_pmax), (int*)pp->bufptr(b_pidx),
                             (float*)pp->bufptr(b_psum), hp);
                     });
                     emit("ctc_head_merge " + c.name, [=](cudaStream_t st) {
-                        tc::ctc_head_merge_kernel<<<(unsigned)ceil_div(rows, 128), 128, 0, st>>>(
+                        launch_pdl(tc::ctc_head_merge_kernel, (unsigned)ceil_div(rows, 128), 128, 0, st, 
                             (const float*)pp->bufptr(b_pmax), (const int*)pp->bufptr(b_pidx), (const float*)pp->bufptr(b_psum),
                             splits, rows, (int*)pp->bufptr(ib_idx), (float*)pp->bufptr(ib_prob));
                     });
@@ -744,7 +744,7 @@ void Model::build_steps(Plan& p) {
                             int m_groups = std::max(1, std::min(m_tiles, 148 / n_tiles));
                             size_t smem = tc::ws_smem_bytes(ws_bn, nkb, tp.ws_stages, tp.ws_halo ? (size_t)tp.ws_stage_bytes : (size_t)tc::WS_A_BYTES);
                             cudaFuncSetAttribute(tc::conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::WS_SMEM_LIMIT);
-                            tc::conv_tc_ws_kernel<<<dim3((unsigned)(n_tiles * m_groups)), tc::kWsThreads, smem, st>>>(
+                            launch_pdl(tc::conv_tc_ws_kernel, dim3((unsigned)(n_tiles * m_groups)), tc::kWsThreads, smem, st, 
                                 ts->map_a, ts->map_b, tbias, (bf16*)pp->ptr(out), tp);
                             return;
                         }
@@ -754,13 +754,13 @@ void Model::build_steps(Plan& p) {
                         bf16* yo = (bf16*)pp->ptr(out);
                         if (bn == 32) {
                             cudaFuncSetAttribute(tc::conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes<32>());
-                            tc::conv_tc_kernel<32><<<grid, tc::kThreads, tc::smem_bytes<32>(), st>>>(ts->map_a, ts->map_b, tbias, yo, tp);
+                            launch_pdl(tc::conv_tc_kernel<32>, grid, tc::kThreads, tc::smem_bytes<32>(), st, ts->map_a, ts->map_b, tbias, yo, tp);
                         } else if (bn == 64) {
                             cudaFuncSetAttribute(tc::conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes<64>());
-                            tc::conv_tc_kernel<64><<<grid, tc::kThreads, tc::smem_bytes<64>(), st>>>(ts->map_a, ts->map_b, tbias, yo, tp);
+                            launch_pdl(tc::conv_tc_kernel<64>, grid, tc::kThreads, tc::smem_bytes<64>(), st, ts->map_a, ts->map_b, tbias, yo, tp);
                         } else {
                             cudaFuncSetAttribute(tc::conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes<128>());
-                            tc::conv_tc_kernel<128><<<grid, tc::kThreads, tc::smem_bytes<128>(), st>>>(ts->map_a, ts->map_b, tbias, yo, tp);
+                            launch_pdl(tc::conv_tc_kernel<128>, grid, tc::kThreads, tc::smem_bytes<128>(), st, ts->map_a, ts->map_b, tbias, yo, tp);
                         }
                     });
                     if (ct2) {                                          // the dense fp32 graph output was written directly
@@ -782,27 +782,27 @@ void Model::build_steps(Plan& p) {
                     T* y = (T*)pp->ptr(out);
                     if (convt && cp.Cout <= 4 && (cp.CoutP == 1 || cp.CoutP == 4) && cp.CinP % 4 == 0) {
                         size_t smem = (size_t)4 * cp.Cout * cp.CinP * sizeof(float);
-                        convt_small_kernel<T><<<grid_for(cp.M), 256, smem, st>>>(x, wptr, w_ld, bptr, y, cp);
+                        launch_pdl(convt_small_kernel<T>, grid_for(cp.M), 256, smem, st, x, wptr, w_ld, bptr, y, cp);
                         return;
                     }
                     if (!convt && cp.CinP == 4 && cp.Cout <= 32 && cp.CoutP % 4 == 0) {
                         int co = cp.Cout <= 8 ? 8 : (cp.Cout <= 16 ? 16 : 32);
                         size_t smem = (size_t)cp.kh * cp.kw * 4 * co * sizeof(float);
                         int g = grid_for(cp.M, 128);
-                        if (co == 8) conv_stem_kernel<T, 8><<<g, 128, smem, st>>>(x, wptr, w_ld, bptr, y, cp);
-                        else if (co == 16) conv_stem_kernel<T, 16><<<g, 128, smem, st>>>(x, wptr, w_ld, bptr, y, cp);
-                        else conv_stem_kernel<T, 32><<<g, 128, smem, st>>>(x, wptr, w_ld, bptr, y, cp);
+                        if (co == 8) launch_pdl(conv_stem_kernel<T, 8>, g, 128, smem, st, x, wptr, w_ld, bptr, y, cp);
+                        else if (co == 16) launch_pdl(conv_stem_kernel<T, 16>, g, 128, smem, st, x, wptr, w_ld, bptr, y, cp);
+                        else launch_pdl(conv_stem_kernel<T, 32>, g, 128, smem, st, x, wptr, w_ld, bptr, y, cp);
                         return;
                     }
                     if (cols <= 16) {
                         dim3 grid((unsigned)ceil_div(cp.M, 256), (unsigned)ceil_div(cols, 16));
-                        conv_igemm_kernel<T, 256, 16><<<grid, 256, 0, st>>>(x, wptr, bptr, y, cp);
+                        launch_pdl(conv_igemm_kernel<T, 256, 16>, grid, 256, 0, st, x, wptr, bptr, y, cp);
                     } else if (cols <= 32) {
                         dim3 grid((unsigned)ceil_div(cp.M, 128), (unsigned)ceil_div(cols, 32));
-                        conv_igemm_kernel<T, 128, 32><<<grid, 256, 0, st>>>(x, wptr, bptr, y, cp);
+                        launch_pdl(conv_igemm_kernel<T, 128, 32>, grid, 256, 0, st, x, wptr, bptr, y, cp);
                     } else {
                         dim3 grid((unsigned)ceil_div(cp.M, 64), (unsigned)ceil_div(cols, 64));
-                        conv_igemm_kernel<T, 64, 64><<<grid, 256, 0, st>>>(x, wptr, bptr, y, cp);
+                        launch_pdl(conv_igemm_kernel<T, 64, 64>, grid, 256, 0, st, x, wptr, bptr, y, cp);
                     }
                 });
                 vid[c.out] = out;
@@ -858,7 +858,7 @@ void Model::build_steps(Plan& p) {
                         }
                         return;
                     }
-                    dwconv_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)pp->ptr(in), wptr, bptr, (T*)pp->ptr(out), dp);
+                    launch_pdl(dwconv_kernel<T>, grid_for(total), 256, 0, st, (const T*)pp->ptr(in), wptr, bptr, (T*)pp->ptr(out), dp);
                 });
                 vid[c.out] = out;
                 break;
@@ -878,13 +878,13 @@ void Model::build_steps(Plan& p) {
                 use(in);
                 cost_bytes = vbytes(in);
                 emit("gap_partial " + c.name, [=](cudaStream_t st) {
-                    gap_partial_kernel<T><<<dim3(chunks, N), 256, smem, st>>>((const T*)pp->ptr(in), (float*)pp->bufptr(partial),
+                    launch_pdl(gap_partial_kernel<T>, dim3(chunks, N), 256, smem, st, (const T*)pp->ptr(in), (float*)pp->bufptr(partial),
                                                                                 HW, CP, chunks);
                 });
                 if (c.kind == C_GAP) {
                     int out = new_val(F_NCHW, iv.n, 1, 1, iv.c);
                     emit("gap_finish " + c.name, [=](cudaStream_t st) {
-                        gap_finish_kernel<T><<<N, 256, 0, st>>>((const float*)pp->bufptr(partial), (T*)pp->ptr(out), HW, C, CP, chunks);
+                        launch_pdl(gap_finish_kernel<T>, N, 256, 0, st, (const float*)pp->bufptr(partial), (T*)pp->ptr(out), HW, C, CP, chunks);
                     });
                     vid[c.out] = out;
                     break;
@@ -910,7 +910,7 @@ void Model::build_steps(Plan& p) {
                 float alpha = c.scale, beta = c.eps;
                 size_t smem2 = (size_t)(iv.cp + mid + kSeThreads) * sizeof(float);
                 emit("se_fc " + c.name, [=](cudaStream_t st) {
-                    se_fc_kernel<<<N, kSeThreads, smem2, st>>>((const float*)pp->bufptr(partial), chunks, HW, C, CP, mid, w1.w, w1.ColsW,
+                    launch_pdl(se_fc_kernel, N, kSeThreads, smem2, st, (const float*)pp->bufptr(partial), chunks, HW, C, CP, mid, w1.w, w1.ColsW,
                                                          w1.bias, w2.w, w2.ColsW, w2.bias, alpha, beta, (float*)pp->bufptr(scale));
                 });
                 int64_t total4 = (int64_t)iv.n * HW * (iv.cp / 4);
@@ -919,12 +919,12 @@ void Model::build_steps(Plan& p) {
                 const bool se_x8 = std::is_same<T, bf16>::value && iv.cp % 8 == 0 && total8 < ((int64_t)1 << 31);
                 emit("se_apply " + c.name, [=](cudaStream_t st) {
                     if (se_x8) {
-                        se_apply_bf16x8_kernel<<<grid_for(total8), 256, 0, st>>>((const bf16*)pp->ptr(in), (const float*)pp->bufptr(scale),
+                        launch_pdl(se_apply_bf16x8_kernel, grid_for(total8), 256, 0, st, (const bf16*)pp->ptr(in), (const float*)pp->bufptr(scale),
                                                                                   (bf16*)pp->ptr(out), (uint32_t)HW, CP, C,
                                                                                   (uint32_t)total8, residual, epi);
                         return;
                     }
-                    se_apply_kernel<T><<<grid_for(total4), 256, 0, st>>>((const T*)pp->ptr(in), (const float*)pp->bufptr(scale),
+                    launch_pdl(se_apply_kernel<T>, grid_for(total4), 256, 0, st, (const T*)pp->ptr(in), (const float*)pp->bufptr(scale),
                                                                           (T*)pp->ptr(out), HW, CP, C, total4, residual, epi);
                 });
                 p.flops += 4.0 * iv.n * (double)iv.c * mid;
@@ -952,7 +952,7 @@ void Model::build_steps(Plan& p) {
                 int64_t total = (int64_t)iv.n * pl.Ho * pl.Wo * iv.cp;
                 cost_bytes = vbytes(in) + vbytes(out);
                 emit("pool " + c.name, [=](cudaStream_t st) {
-                    pool_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)pp->ptr(in), (T*)pp->ptr(out), pl);
+                    launch_pdl(pool_kernel<T>, grid_for(total), 256, 0, st, (const T*)pp->ptr(in), (T*)pp->ptr(out), pl);
                 });
                 vid[c.out] = out;
                 break;
@@ -988,7 +988,7 @@ void Model::build_steps(Plan& p) {
                 if (cdp != ctot) {
                     int64_t tot = p.vals[out].elems();
                     emit("concat_zero " + c.name, [=](cudaStream_t st) {
-                        fill_zero_kernel<T><<<grid_for(tot), 256, 0, st>>>((T*)pp->ptr(out), tot);
+                        launch_pdl(fill_zero_kernel<T>, grid_for(tot), 256, 0, st, (T*)pp->ptr(out), tot);
                     });
                 }
                 int off = 0;
@@ -1001,10 +1001,10 @@ void Model::build_steps(Plan& p) {
                     emit("concat " + c.name, [=](cudaStream_t st) {
                         constexpr int epv = 16 / (int)sizeof(T);
                         if (Cs % epv == 0 && CsP % epv == 0 && cdp % epv == 0 && coff % epv == 0)
-                            concat_slice_vec_kernel<T><<<grid_for((int64_t)N * H * W * (Cs / epv)), 256, 0, st>>>(
+                            launch_pdl(concat_slice_vec_kernel<T>, grid_for((int64_t)N * H * W * (Cs / epv)), 256, 0, st, 
                                 (const T*)pp->ptr(src), (T*)pp->ptr(out), N, H, W, Cs, CsP, cdp, coff, fh, fw);
                         else
-                            concat_slice_kernel<T><<<grid_for((int64_t)N * H * W * Cs), 256, 0, st>>>(
+                            launch_pdl(concat_slice_kernel<T>, grid_for((int64_t)N * H * W * Cs), 256, 0, st, 
                                 (const T*)pp->ptr(src), (T*)pp->ptr(out), N, H, W, Cs, CsP, cdp, coff, fh, fw);
                     });
                     off += pv.c;
@@ -1042,7 +1042,7 @@ void Model::build_steps(Plan& p) {
                     if (bc || bv.up_src >= 0) throw std::runtime_error("scalar-channel element-wise with broadcast: " + c.name);
                     int64_t tot = av.elems();
                     emit("eltwise " + c.name, [=](cudaStream_t st) {
-                        eltwise_scalar_kernel<T><<<grid_for(tot), 256, 0, st>>>((const T*)pp->ptr(a), (const T*)pp->ptr(bsrc),
+                        launch_pdl(eltwise_scalar_kernel<T>, grid_for(tot), 256, 0, st, (const T*)pp->ptr(a), (const T*)pp->ptr(bsrc),
                                                                                  (T*)pp->ptr(out), tot, ep.op, ep.epi);
                     });
                 } else {
@@ -1052,11 +1052,11 @@ void Model::build_steps(Plan& p) {
                     const bool x8 = std::is_same<T, bf16>::value && av.cp % 8 == 0 && !bc && tot8 < ((int64_t)1 << 31);
                     emit("eltwise " + c.name, [=](cudaStream_t st) {
                         if (x8) {
-                            eltwise_bf16x8_kernel<<<grid_for(tot8), 256, 0, st>>>((const bf16*)pp->ptr(a), (const bf16*)pp->ptr(bsrc),
+                            launch_pdl(eltwise_bf16x8_kernel, grid_for(tot8), 256, 0, st, (const bf16*)pp->ptr(a), (const bf16*)pp->ptr(bsrc),
                                                                                   (bf16*)pp->ptr(out), ep, (uint32_t)tot8);
                             return;
                         }
-                        eltwise_kernel<T><<<grid_for(tot), 256, 0, st>>>((const T*)pp->ptr(a), (const T*)pp->ptr(bsrc),
+                        launch_pdl(eltwise_kernel<T>, grid_for(tot), 256, 0, st, (const T*)pp->ptr(a), (const T*)pp->ptr(bsrc),
                                                                           (T*)pp->ptr(out), ep);
                     });
                 }
@@ -1077,7 +1077,7 @@ void Model::build_steps(Plan& p) {
                 Epilogue epi = c.epi;
                 cost_bytes = vbytes(in) + vbytes(out);
                 emit("unary " + c.name, [=](cudaStream_t st) {
-                    unary_kernel<T><<<grid_for(tot), 256, 0, st>>>((const T*)pp->ptr(in), (T*)pp->ptr(out), tot, CP, C, vec, vop, epi);
+                    launch_pdl(unary_kernel<T>, grid_for(tot), 256, 0, st, (const T*)pp->ptr(in), (T*)pp->ptr(out), tot, CP, C, vec, vop, epi);
                 });
                 vid[c.out] = out;
                 break;
@@ -1097,7 +1097,7 @@ void Model::build_steps(Plan& p) {
                 const float* be = dvec_[c.ln_id].second;
                 cost_bytes = vbytes(in) + vbytes(out);
                 emit("layernorm " + c.name, [=](cudaStream_t st) {
-                    layernorm_kernel<T><<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>((const T*)pp->ptr(in), (T*)pp->ptr(out),
+                    launch_pdl(layernorm_kernel<T>, (unsigned)ceil_div(rows * 32, 256), 256, 0, st, (const T*)pp->ptr(in), (T*)pp->ptr(out),
                                                                                              ga, be, rows, C, CP, eps);
                 });
                 vid[c.out] = out;
@@ -1126,7 +1126,7 @@ void Model::build_steps(Plan& p) {
     {                                                                                                               \
         if (smem > 48 * 1024)                                                                                       \
             cudaFuncSetAttribute(attention_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        attention_kernel<T, HD><<<grid, 64, smem, st>>>(q, o, Tn, heads, CPin, CPout, scale);                       \
+        launch_pdl(attention_kernel<T, HD>, grid, 64, smem, st, q, o, Tn, heads, CPin, CPout, scale);                       \
     }
                     switch (hd) {
                         case 8: B200_ATTN(8) break;
@@ -1139,7 +1139,7 @@ void Model::build_steps(Plan& p) {
 #undef B200_ATTN
                     if (CPout != dim) {
                         int64_t rows = (int64_t)B * Tn;
-                        zero_pad_lanes_kernel<T><<<grid_for(rows * (CPout - dim)), 256, 0, st>>>(o, rows, dim, CPout);
+                        launch_pdl(zero_pad_lanes_kernel<T>, grid_for(rows * (CPout - dim)), 256, 0, st, o, rows, dim, CPout);
                     }
                 });
                 if (hd != 8 && hd != 15 && hd != 16 && hd != 30 && hd != 32)
@@ -1165,13 +1165,13 @@ void Model::build_steps(Plan& p) {
                     int out = (int)p.vals.size() - 1;
                     p.out_written_dense = true;
                     emit("softmax_out " + c.name, [=](cudaStream_t st) {
-                        softmax_kernel<T><<<(unsigned)rows, 256, 0, st>>>((const T*)pp->ptr(in), nullptr, pp->out_dense, C, CP);
+                        launch_pdl(softmax_kernel<T>, (unsigned)rows, 256, 0, st, (const T*)pp->ptr(in), nullptr, pp->out_dense, C, CP);
                     });
                     vid[c.out] = out;
                 } else {
                     int out = new_val(iv.form, iv.n, iv.h, iv.w, iv.c);
                     emit("softmax " + c.name, [=](cudaStream_t st) {
-                        softmax_kernel<T><<<(unsigned)rows, 256, 0, st>>>((const T*)pp->ptr(in), (T*)pp->ptr(out), nullptr, C, CP);
+                        launch_pdl(softmax_kernel<T>, (unsigned)rows, 256, 0, st, (const T*)pp->ptr(in), (T*)pp->ptr(out), nullptr, C, CP);
                     });
                     vid[c.out] = out;
                 }
@@ -1279,7 +1279,7 @@ void Model::build_steps(Plan& p) {
         int N = out.n, C = out.c, H = out.h, W = out.w, CP = out.cp;
         int64_t tot = (int64_t)p.out_dense_elems;
         emit("to_dense", [=](cudaStream_t st) {
-            to_dense_f32_kernel<T><<<grid_for(tot), 256, 0, st>>>((const T*)pp->ptr(ov), pp->out_dense, N, C, H, W, CP, to_nchw);
+            launch_pdl(to_dense_f32_kernel<T>, grid_for(tot), 256, 0, st, (const T*)pp->ptr(ov), pp->out_dense, N, C, H, W, CP, to_nchw);
         });
     }
     if (p.head_rows == 0)
@@ -1401,9 +1401,9 @@ Plan* Model::launch_host_input(const float* nchw, int n, int c, int h, int w, cu
     int cp = cpad_of(c);
     int64_t tot = (int64_t)n * h * w * cp;
     if (prec_ == PREC_BF16)
-        nchw_to_nhwc_kernel<bf16><<<grid_for(tot), 256, 0, st>>>(stage_in_, (bf16*)p->in_ptr(), n, c, h, w, cp);
+        launch_pdl(nchw_to_nhwc_kernel<bf16>, grid_for(tot), 256, 0, st, stage_in_, (bf16*)p->in_ptr(), n, c, h, w, cp);
     else
-        nchw_to_nhwc_kernel<float><<<grid_for(tot), 256, 0, st>>>(stage_in_, (float*)p->in_ptr(), n, c, h, w, cp);
+        launch_pdl(nchw_to_nhwc_kernel<float>, grid_for(tot), 256, 0, st, stage_in_, (float*)p->in_ptr(), n, c, h, w, cp);
     p->launch(st);
     B200_CUDA_CHECK(cudaGetLastError());
     return p;

@@ -13,6 +13,7 @@ namespace b200ocr {
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int N, int C, int H, int W,
                                     int CP) {
+    pdl_start();
     int64_t total = (int64_t)N * H * W * CP;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = (int)(i % CP);
@@ -30,6 +31,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict_
 template <typename T>
 __global__ void to_dense_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int N, int C, int H, int W,
                                     int CP, int to_nchw) {
+    pdl_start();
     int64_t total = (int64_t)N * C * H * W;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int n, c, y, x;
@@ -75,6 +77,7 @@ template <typename T, int BM, int BN>
 __global__ void __launch_bounds__(256) conv_igemm_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                           const float* __restrict__ bias, T* __restrict__ y,
                                                           const ConvP p) {
+    pdl_start();
     constexpr int TM = 4, TN = 4;
     constexpr int TX = BN / TN;            // threads along columns
     constexpr int TY = BM / TM;            // threads along rows
@@ -226,6 +229,7 @@ struct DwP {
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, T* __restrict__ y, const DwP p) {
+    pdl_start();
     const int cg = p.CP >> 2;                       // 4-channel groups
     int64_t total = (int64_t)p.N * p.Ho * p.Wo * cg;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -266,6 +270,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ x, co
 template <int KW, int SW>
 __global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                             const float* __restrict__ bias, bf16* __restrict__ y, const DwP p) {
+    pdl_start();
     constexpr int TW = 4;
     constexpr int NCOL = (TW - 1) * SW + KW;
     const int cg = p.CP >> 3;
@@ -355,6 +360,7 @@ template <int K, int SH, int SW, int CC>
 __global__ void __launch_bounds__(256) dwconv_tile_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                            const float* __restrict__ bias, bf16* __restrict__ y, const DwP p,
                                                            int tiles_x, int tiles_y) {
+    pdl_start();
     constexpr int TW = 16, TH = 8, G = CC / 8;
     constexpr int IR = (TH - 1) * SH + K, IC = (TW - 1) * SW + K;
     constexpr int SLOTS = 256 / G;                // pixels handled per pass
@@ -454,7 +460,7 @@ inline void launch_dwconv_tile_cc(const bf16* x, const bf16* w, const float* bia
     }
     int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
     dim3 grid((unsigned)(tiles_x * tiles_y * p.N), (unsigned)((p.CP + CC - 1) / CC));
-    dwconv_tile_kernel<K, SH, SW, CC><<<grid, 256, smem, st>>>(x, w, bias, y, p, tiles_x, tiles_y);
+    launch_pdl(dwconv_tile_kernel<K, SH, SW, CC>, grid, 256, smem, st, x, w, bias, y, p, tiles_x, tiles_y);
 }
 
 template <int K, int SH, int SW>
@@ -537,6 +543,7 @@ template <int K, int SH, int SW, int WPP, int TY>
 __global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ bias, bf16* __restrict__ y, const DwP p,
                                                             int tiles_x, int tiles_y) {
+    pdl_start();
     constexpr int TX = 256 / WPP;
     constexpr int IR = (TY - 1) * SH + K, IC = (TX - 1) * SW + K;
     constexpr int PS = (SW == 2 && WPP < 32) ? WPP * 3 / 2 : WPP;
@@ -611,7 +618,7 @@ inline void launch_dwconv_strip_w(const bf16* x, const float* w, const float* bi
     }
     int tiles_x = (p.Wo + TX - 1) / TX, tiles_y = (p.Ho + TY - 1) / TY;
     dim3 grid((unsigned)(tiles_x * tiles_y * p.N), (unsigned)((p.CP + 2 * WPP - 1) / (2 * WPP)));
-    dwconv_strip_kernel<K, SH, SW, WPP, TY><<<grid, 256, smem, st>>>(x, w, bias, y, p, tiles_x, tiles_y);
+    launch_pdl(dwconv_strip_kernel<K, SH, SW, WPP, TY>, grid, 256, smem, st, x, w, bias, y, p, tiles_x, tiles_y);
 }
 
 template <int K, int SH, int SW>
@@ -633,6 +640,7 @@ inline void launch_dwconv_strip(const bf16* x, const float* w, const float* bias
 template <typename T>
 __global__ void __launch_bounds__(256) gap_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, int HW,
                                                            int CP, int chunks) {
+    pdl_start();
     extern __shared__ float sm[];                   // [rows][CP]
     const int cg = CP >> 2;
     const int rows = max(1, 256 / cg);
@@ -661,6 +669,7 @@ __global__ void __launch_bounds__(256) gap_partial_kernel(const T* __restrict__ 
 template <typename T>
 __global__ void gap_finish_kernel(const float* __restrict__ partial, T* __restrict__ out, int HW, int C, int CP,
                                   int chunks) {
+    pdl_start();
     int n = blockIdx.x;
     for (int c = threadIdx.x; c < CP; c += blockDim.x) {
         float s = 0.f;
@@ -679,6 +688,7 @@ __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(const float* __restri
                                                            const float* __restrict__ b1, const float* __restrict__ w2, int w2_ld,
                                                            const float* __restrict__ b2, float alpha, float beta,
                                                            float* __restrict__ scale) {
+    pdl_start();
     extern __shared__ float sm[];                   // mean[CP] + hidden[mid] + part[kSeThreads]
     float* mean = sm;
     float* hid = sm + CP;
@@ -737,6 +747,7 @@ __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(const float* __restri
 template <typename T>
 __global__ void se_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale, T* __restrict__ y, int64_t HW,
                                 int CP, int C, int64_t total4, int residual, const Epilogue epi) {
+    pdl_start();
     const int cg = CP >> 2;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
         int g = (int)(i % cg);
@@ -760,6 +771,7 @@ __global__ void se_apply_kernel(const T* __restrict__ x, const float* __restrict
 __global__ void __launch_bounds__(256) se_apply_bf16x8_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
                                                               bf16* __restrict__ y, uint32_t HW, int CP, int C, uint32_t total8,
                                                               int residual, const Epilogue epi) {
+    pdl_start();
     const uint32_t cg = (uint32_t)CP >> 3;
     const uint32_t per_img = HW * cg;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += gridDim.x * blockDim.x) {
@@ -794,6 +806,7 @@ struct PoolP {
 };
 template <typename T>
 __global__ void pool_kernel(const T* __restrict__ x, T* __restrict__ y, const PoolP p) {
+    pdl_start();
     int64_t total = (int64_t)p.N * p.Ho * p.Wo * p.CP;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = (int)(i % p.CP);
@@ -832,6 +845,7 @@ struct EltP {
 };
 template <typename T>
 __global__ void eltwise_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, const EltP p) {
+    pdl_start();
     const int cg = p.CP >> 2;
     int64_t total = (int64_t)p.N * p.H * p.W * cg;
     const int Hb = p.H / p.fh, Wb = p.W / p.fw;
@@ -861,6 +875,7 @@ __global__ void eltwise_kernel(const T* __restrict__ a, const T* __restrict__ b,
 // channel broadcast, fewer than 2^31 16-byte chunks.
 __global__ void __launch_bounds__(256) eltwise_bf16x8_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
                                                              bf16* __restrict__ y, const EltP p, uint32_t total8) {
+    pdl_start();
     const uint32_t cg = (uint32_t)p.CP >> 3;
     const uint32_t Hb = p.H / p.fh, Wb = p.W / p.fw;
     const bool same = p.fh == 1 && p.fw == 1;
@@ -912,6 +927,7 @@ __global__ void __launch_bounds__(256) eltwise_bf16x8_kernel(const bf16* __restr
 template <typename T>
 __global__ void eltwise_scalar_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t total,
                                       int op, const Epilogue epi) {
+    pdl_start();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         float va = ST<T>::ld(a + i), vb = ST<T>::ld(b + i);
         ST<T>::st(y + i, epi_apply(op == 0 ? va + vb : va * vb, epi));
@@ -922,6 +938,7 @@ __global__ void eltwise_scalar_kernel(const T* __restrict__ a, const T* __restri
 template <typename T>
 __global__ void unary_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t total, int CP, int C,
                              const float* __restrict__ vec, int vec_op, const Epilogue epi) {
+    pdl_start();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = (int)(i % CP);
         float v = ST<T>::ld(x + i);
@@ -935,6 +952,7 @@ __global__ void unary_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t
 template <typename T>
 __global__ void concat_slice_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int H, int W, int Cs, int CsP,
                                     int CdP, int c_off, int fh, int fw) {
+    pdl_start();
     int64_t total = (int64_t)N * H * W * Cs;
     const int Hs = H / fh, Ws = W / fw;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -953,6 +971,7 @@ __global__ void concat_slice_kernel(const T* __restrict__ src, T* __restrict__ d
 template <typename T>
 __global__ void concat_slice_vec_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int H, int W, int Cs, int CsP,
                                         int CdP, int c_off, int fh, int fw) {
+    pdl_start();
     constexpr int EPV = 16 / (int)sizeof(T);
     const int vc = Cs / EPV;
     int64_t total = (int64_t)N * H * W * vc;
@@ -988,6 +1007,7 @@ __global__ void concat_slice_vec_kernel(const T* __restrict__ src, T* __restrict
 template <typename T, int COUT>
 __global__ void __launch_bounds__(128) conv_stem_kernel(const T* __restrict__ x, const float* __restrict__ w, int w_ld,
                                                         const float* __restrict__ bias, T* __restrict__ y, const ConvP p) {
+    pdl_start();
     extern __shared__ float sw[];                 // [taps * 4][COUT]
     const int taps = p.kh * p.kw;
     for (int i = threadIdx.x; i < taps * 4 * COUT; i += blockDim.x) sw[i] = w[(int64_t)(i / COUT) * w_ld + (i % COUT)];
@@ -1041,6 +1061,7 @@ __global__ void __launch_bounds__(128) conv_stem_kernel(const T* __restrict__ x,
 template <typename T>
 __global__ void __launch_bounds__(256) convt_small_kernel(const T* __restrict__ x, const float* __restrict__ w, int w_ld,
                                                           const float* __restrict__ bias, T* __restrict__ y, const ConvP p) {
+    pdl_start();
     extern __shared__ float sw[];                 // [tap][co][CinP]
     const int CoP = p.CoutP;                      // 1 or 4
     for (int i = threadIdx.x; i < 4 * p.Cout * p.CinP; i += blockDim.x) {
@@ -1080,6 +1101,7 @@ __global__ void __launch_bounds__(256) convt_small_kernel(const T* __restrict__ 
 
 template <typename T>
 __global__ void fill_zero_kernel(T* __restrict__ p, int64_t total) {
+    pdl_start();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
         ST<T>::st(p + i, 0.f);
 }
@@ -1090,6 +1112,7 @@ __global__ void fill_zero_kernel(T* __restrict__ p, int64_t total) {
 template <typename T>
 __global__ void layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, int64_t rows, int C, int CP, float eps) {
+    pdl_start();
     int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
     int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -1120,6 +1143,7 @@ __global__ void layernorm_kernel(const T* __restrict__ x, T* __restrict__ y, con
 template <typename T, int HD>
 __global__ void attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int Tn, int heads, int CPin, int CPout,
                                  float scale) {
+    pdl_start();
     extern __shared__ float sm[];                   // K[Tn][HD] V[Tn][HD]
     float* Ks = sm;
     float* Vs = sm + (size_t)Tn * HD;
@@ -1166,6 +1190,7 @@ __global__ void attention_kernel(const T* __restrict__ qkv, T* __restrict__ out,
 // zero the pad lanes [C, CP) of every row (used after attention, whose threads write only real channels)
 template <typename T>
 __global__ void zero_pad_lanes_kernel(T* __restrict__ x, int64_t rows, int C, int CP) {
+    pdl_start();
     int padn = CP - C;
     int64_t total = rows * padn;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
@@ -1178,6 +1203,7 @@ __global__ void zero_pad_lanes_kernel(T* __restrict__ x, int64_t rows, int C, in
 template <typename T>
 __global__ void __launch_bounds__(256) softmax_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                        float* __restrict__ y_dense, int C, int CP) {
+    pdl_start();
     __shared__ float red[32];
     const int64_t row = blockIdx.x;
     const T* xr = x + row * CP;

@@ -237,6 +237,7 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                            const __grid_constant__ CUtensorMap map_b,
                                                            const float* __restrict__ bias, bf16* __restrict__ y, const Params p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();                                             // activations of the previous kernel are complete and visible
 
     // tile index -> origin.  n tiles vary fastest so that CTAs working on the same pixels run together (A stays in L2).
     auto tile_origin = [&](int tile, int& n0, int& m0, int& img, int& y0, int& x0) {
@@ -747,6 +749,7 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 const float* __restrict__ bias, bf16* __restrict__ y,
                                                                 const Params p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const int BN = p.ws_bn, STG = p.ws_stages;
     const int nkb = p.taps * p.kchunks;
@@ -810,6 +813,7 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();                                             // activations of the previous kernel are complete and visible
 
     auto tile_origin = [&](int mt, int& m0, int& img, int& y0, int& x0) {
         m0 = mt * BM;
@@ -1028,6 +1032,7 @@ __global__ void __launch_bounds__(kThreads) ctc_head_kernel(const __grid_constan
                                                             const float* __restrict__ bias /* -1e30 beyond the last class */,
                                                             float* __restrict__ pmax, int* __restrict__ pidx,
                                                             float* __restrict__ psum, const HeadParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     constexpr int A_KB_BYTES = BM * BK * 2, B_KB_BYTES = HEAD_BN * BK * 2;
     const int KB = p.kblocks;
@@ -1072,6 +1077,7 @@ __global__ void __launch_bounds__(kThreads) ctc_head_kernel(const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();                                             // activations of the previous kernel are complete and visible
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1186,6 +1192,7 @@ __global__ void __launch_bounds__(kThreads) ctc_head_kernel(const __grid_constan
 __global__ void ctc_head_merge_kernel(const float* __restrict__ pmax, const int* __restrict__ pidx,
                                       const float* __restrict__ psum, int splits, int rows, int* __restrict__ idx,
                                       float* __restrict__ prob) {
+    pdl_start();
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     float m = pmax[r];
