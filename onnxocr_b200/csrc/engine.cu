@@ -94,6 +94,15 @@ static bool tc_ws_enabled() {             // B200OCR_TC=stream selects the A+B s
     return v == 1;
 }
 
+static bool gap_se_fused() {              // B200OCR_NO_GAP_SE=1: separate gap_partial + se_fc launches (A/B measurements)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200OCR_NO_GAP_SE");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 static bool pixel_pack_enabled() {        // B200OCR_NO_PIXEL_PACK=1 disables the packed narrow-layer GEMM (A/B measurements)
     static int v = -1;
     if (v < 0) {
@@ -877,10 +886,12 @@ void Model::build_steps(Plan& p) {
                 int N = iv.n, CP = iv.cp, C = iv.c;
                 use(in);
                 cost_bytes = vbytes(in);
-                emit("gap_partial " + c.name, [=](cudaStream_t st) {
-                    launch_pdl(gap_partial_kernel<T>, dim3(chunks, N), 256, smem, st, (const T*)pp->ptr(in), (float*)pp->bufptr(partial),
-                                                                                HW, CP, chunks);
-                });
+                const bool fuse_gap_se = c.kind == C_SE && iv.cp <= kGapSeThreads && c.se_mid <= kGapSeThreads && gap_se_fused();
+                if (!fuse_gap_se)
+                    emit("gap_partial " + c.name, [=](cudaStream_t st) {
+                        launch_pdl(gap_partial_kernel<T>, dim3(chunks, N), 256, smem, st, (const T*)pp->ptr(in),
+                                   (float*)pp->bufptr(partial), HW, CP, chunks);
+                    });
                 if (c.kind == C_GAP) {
                     int out = new_val(F_NCHW, iv.n, 1, 1, iv.c);
                     emit("gap_finish " + c.name, [=](cudaStream_t st) {
@@ -909,6 +920,20 @@ void Model::build_steps(Plan& p) {
                 int mid = c.se_mid;
                 float alpha = c.scale, beta = c.eps;
                 size_t smem2 = (size_t)(iv.cp + mid + kSeThreads) * sizeof(float);
+                if (fuse_gap_se) {
+                    int* dt = nullptr;                              // one ticket counter per image, self-resetting
+                    B200_CUDA_CHECK(cudaMalloc(&dt, (size_t)N * sizeof(int)));
+                    B200_CUDA_CHECK(cudaMemset(dt, 0, (size_t)N * sizeof(int)));
+                    std::shared_ptr<int> tickets(dt, [](int* q) { cudaFree(q); });
+                    const int grows = std::max(1, kGapSeThreads / (iv.cp / 4));
+                    const size_t smem3 = std::max((size_t)grows * iv.cp, (size_t)(iv.cp + mid + kGapSeThreads)) * sizeof(float);
+                    cost_bytes = vbytes(in);
+                    emit("gap_se " + c.name, [=](cudaStream_t st) {
+                        launch_pdl(gap_se_kernel<T>, dim3(chunks, N), kGapSeThreads, smem3, st, (const T*)pp->ptr(in),
+                                   (float*)pp->bufptr(partial), HW, C, CP, chunks, mid, w1.w, w1.ColsW, w1.bias, w2.w, w2.ColsW, w2.bias,
+                                   alpha, beta, (float*)pp->bufptr(scale), tickets.get());
+                    });
+                } else
                 emit("se_fc " + c.name, [=](cudaStream_t st) {
                     launch_pdl(se_fc_kernel, N, kSeThreads, smem2, st, (const float*)pp->bufptr(partial), chunks, HW, C, CP, mid, w1.w, w1.ColsW,
                                                          w1.bias, w2.w, w2.ColsW, w2.bias, alpha, beta, (float*)pp->bufptr(scale));

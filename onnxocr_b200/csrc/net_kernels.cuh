@@ -683,64 +683,121 @@ __global__ void gap_finish_kernel(const float* __restrict__ partial, T* __restri
 // memory) so the dependent-load chains stay short — the kernel is pure latency.
 // w1: [C][mid] (row stride w1_ld), w2: [mid][C] (row stride w2_ld).
 constexpr int kSeThreads = 1024;
-__global__ void __launch_bounds__(kSeThreads) se_fc_kernel(const float* __restrict__ partial, int chunks, int HW, int C, int CP,
-                                                           int mid, const float* __restrict__ w1, int w1_ld,
-                                                           const float* __restrict__ b1, const float* __restrict__ w2, int w2_ld,
-                                                           const float* __restrict__ b2, float alpha, float beta,
-                                                           float* __restrict__ scale) {
-    pdl_start();
-    extern __shared__ float sm[];                   // mean[CP] + hidden[mid] + part[kSeThreads]
+// The three phases of the SE gate for image n, executed by one whole block of NT threads (shared memory: mean[CP] +
+// hidden[mid] + part[NT]).  Partials are read with ld.global.cg: in the fused kernel they were written by other blocks.
+__device__ __forceinline__ void se_fc_body(const float* __restrict__ partial, int n, int chunks, int HW, int C, int CP, int mid,
+                                           const float* __restrict__ w1, int w1_ld, const float* __restrict__ b1,
+                                           const float* __restrict__ w2, int w2_ld, const float* __restrict__ b2, float alpha,
+                                           float beta, float* __restrict__ scale, float* sm) {
     float* mean = sm;
     float* hid = sm + CP;
     float* part = hid + mid;
-    const int n = blockIdx.x, tid = threadIdx.x;
+    const int NT = blockDim.x, tid = threadIdx.x;
     {   // mean over the pixels: slices of the chunk list per channel
-        const int S = max(1, min(chunks, kSeThreads / CP));
+        const int S = max(1, min(chunks, NT / CP));
         const int c = tid % CP, sl = tid / CP;
         float s = 0.f;
         if (sl < S)
-            for (int k = sl; k < chunks; k += S) s += partial[((int64_t)n * chunks + k) * CP + c];
+            for (int k = sl; k < chunks; k += S) s += __ldcg(partial + ((int64_t)n * chunks + k) * CP + c);
         if (sl < S) part[sl * CP + c] = s;
         __syncthreads();
-        if (tid < CP) {
+        for (int cc = tid; cc < CP; cc += NT) {
             float t = 0.f;
-            for (int q = 0; q < S; ++q) t += part[q * CP + tid];
-            mean[tid] = tid < C ? t / (float)HW : 0.f;
+            for (int q = 0; q < S; ++q) t += part[q * CP + cc];
+            mean[cc] = cc < C ? t / (float)HW : 0.f;
         }
         __syncthreads();
     }
     {   // hidden = relu(W1^T mean + b1)
-        const int S = max(1, kSeThreads / mid);
+        const int S = max(1, NT / mid);
         const int j = tid % mid, sl = tid / mid;
         float s = 0.f;
         if (sl < S)
             for (int c = sl; c < C; c += S) s = fmaf(mean[c], w1[(int64_t)c * w1_ld + j], s);
         if (sl < S) part[sl * mid + j] = s;
         __syncthreads();
-        if (tid < mid) {
+        for (int jj = tid; jj < mid; jj += NT) {
             float t = 0.f;
-            for (int q = 0; q < S; ++q) t += part[q * mid + tid];
-            hid[tid] = fmaxf(t + b1[tid], 0.f);
+            for (int q = 0; q < S; ++q) t += part[q * mid + jj];
+            hid[jj] = fmaxf(t + b1[jj], 0.f);
         }
         __syncthreads();
     }
     {   // scale = hsigmoid(W2^T hidden + b2)
-        const int S = max(1, min(mid, kSeThreads / CP));
+        const int S = max(1, min(mid, NT / CP));
         const int c = tid % CP, sl = tid / CP;
         float s = 0.f;
         if (sl < S && c < C)
             for (int j = sl; j < mid; j += S) s = fmaf(hid[j], w2[(int64_t)j * w2_ld + c], s);
         if (sl < S) part[sl * CP + c] = s;
         __syncthreads();
-        if (tid < CP) {
+        for (int cc = tid; cc < CP; cc += NT) {
             float t = 0.f;
-            if (tid < C) {
-                for (int q = 0; q < S; ++q) t += part[q * CP + tid];
-                t = fminf(fmaxf(fmaf(t + b2[tid], alpha, beta), 0.f), 1.f);
+            if (cc < C) {
+                for (int q = 0; q < S; ++q) t += part[q * CP + cc];
+                t = fminf(fmaxf(fmaf(t + b2[cc], alpha, beta), 0.f), 1.f);
             }
-            scale[(int64_t)n * CP + tid] = t;
+            scale[(int64_t)n * CP + cc] = t;
         }
     }
+}
+
+__global__ void __launch_bounds__(kSeThreads) se_fc_kernel(const float* __restrict__ partial, int chunks, int HW, int C, int CP,
+                                                           int mid, const float* __restrict__ w1, int w1_ld,
+                                                           const float* __restrict__ b1, const float* __restrict__ w2, int w2_ld,
+                                                           const float* __restrict__ b2, float alpha, float beta,
+                                                           float* __restrict__ scale) {
+    pdl_start();
+    extern __shared__ float sm[];                   // mean[CP] + hidden[mid] + part[blockDim.x]
+    se_fc_body(partial, blockIdx.x, chunks, HW, C, CP, mid, w1, w1_ld, b1, w2, w2_ld, b2, alpha, beta, scale, sm);
+}
+
+// GAP partial sums and the SE gate in ONE launch: every block reduces its pixel chunk; the block that finishes last for
+// an image (ticket counter, self-resetting) sums the partials in chunk order — deterministic whichever block it is —
+// and runs the two small matrix-vector products.  Saves one dependent launch per SE layer (10 of the det plan's 80).
+// grid (chunks, N), block 512; needs CP <= 512 (the slicing of se_fc_body handles any CP <= blockDim.x) .
+constexpr int kGapSeThreads = 512;
+template <typename T>
+__global__ void __launch_bounds__(kGapSeThreads) gap_se_kernel(const T* __restrict__ x, float* __restrict__ partial, int HW, int C,
+                                                               int CP, int chunks, int mid, const float* __restrict__ w1, int w1_ld,
+                                                               const float* __restrict__ b1, const float* __restrict__ w2,
+                                                               int w2_ld, const float* __restrict__ b2, float alpha, float beta,
+                                                               float* __restrict__ scale, int* __restrict__ tickets) {
+    pdl_start();
+    extern __shared__ float sm[];                   // max([rows][CP], CP + mid + blockDim.x)
+    __shared__ int s_last;
+    const int cg = CP >> 2;
+    const int rows = max(1, kGapSeThreads / cg);
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int per = (HW + chunks - 1) / chunks;
+    const int p0 = chunk * per, p1 = min(HW, p0 + per);
+    const int r = threadIdx.x / cg, g = threadIdx.x % cg;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < rows) {
+        for (int px = p0 + r; px < p1; px += rows) {
+            float v[4];
+            ST<T>::ld4(x + ((int64_t)n * HW + px) * CP + g * 4, v);
+            acc[0] += v[0]; acc[1] += v[1]; acc[2] += v[2]; acc[3] += v[3];
+        }
+        for (int j = 0; j < 4; ++j) sm[r * CP + g * 4 + j] = acc[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < CP; c += blockDim.x) {
+        float s = 0.f;
+        for (int rr = 0; rr < rows; ++rr) s += sm[rr * CP + c];
+        partial[((int64_t)n * chunks + chunk) * CP + c] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = atomicAdd(&tickets[n], 1);
+        s_last = (t == chunks - 1);
+        if (s_last) tickets[n] = 0;                 // ready for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    se_fc_body(partial, n, chunks, HW, C, CP, mid, w1, w1_ld, b1, w2, w2_ld, b2, alpha, beta, scale, sm);
 }
 
 // y = epi(x * scale[n][c]) (+ x when residual)
