@@ -265,17 +265,24 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as fh:
             tj = json.load(fh)
-        key = {"tcconv conv2d.out_2.tmp": "tcconv_out2", "tcconvT2 p2o.ConvTranspose_0.tmp": "tcconvT2",
-               "eltwise p2o.Add_82.tmp": "eltwise_add82", "conv conv2d.out_0.tmp": "stem"}.get(top["name"])
+        key = {"tcconv conv2d.out_2.tmp": "tcconv_out2_packed", "tcconvT2 p2o.ConvTranspose_0.tmp": "tcconvT2",
+               "eltwise p2o.Add_82.tmp": "eltwise_add82", "conv conv2d.out_0.tmp": "stem", "tcconv conv2d.out_46.tmp": "tcconv_out46",
+               "tcconv conv2d.out_61.tmp": "tcconv3x3", "tcconv conv2d.out_58.tmp": "tcconv3x3"}.get(top["name"])
         if key in tj:
             traffic = (tj[key]["dram_read_mb"] + tj[key]["dram_write_mb"]) * 1e6
+    kern_of = {"tcconv": "tc::conv_tc_ws_kernel / tc::conv_tc_kernel<BN> (tcgen05 + TMA implicit GEMM)", "conv": "conv_stem_kernel",
+               "dwconv": "dwconv_strip_kernel", "tcconvT2": "tc::conv_tc_ws_kernel with the fused DB-head tail epilogue",
+               "eltwise": "eltwise_bf16x8_kernel"}.get(kernel_class(top["name"]), kernel_class(top["name"]))
     roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
             "traffic": traffic, "kernel": top["name"], "algorithmic_bytes_per_launch": top["bytes"],
             "launch_ms": top["ms"], "launches_per_step": 2, "share_of_network_time": top["ms"] / total_ms,
             "peak_source": peaks["source"],
-            "note": "kernel = conv_tc_ws_kernel (tcgen05/TMA weight-stationary GEMM) for the named layer at 8 pages; traffic = "
-                    "dram read+write of one launch from profiles/ (ncu --set full); output lines still resident in the 126 MB "
-                    "L2 at kernel end are not in it"}
+            "tensor_tflops": top["flops"] / (top["ms"] / 1e3) / 1e12,
+            "tensor_frac_of_sustained": top["flops"] / (top["ms"] / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
+            "note": "kernel = %s for the named layer at 8 pages (%.0f FLOP per algorithmic byte, below the ridge of %.0f, so "
+                    "HBM-bound); traffic = dram read+write of one launch from profiles/r1_traffic.json (ncu --set full); output "
+                    "lines still resident in the 126 MB L2 at kernel end are not in it" % (
+                        kern_of, top["flops"] / max(top["bytes"], 1.0), peaks["bf16_tflops_sustained"] * 1e3 / peaks["hbm_gbs"])}
     breakdown = {k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4),
                      "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 3),
                      "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1), "launches": v["launches"]}
