@@ -870,6 +870,46 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
             const uint32_t idesc = make_idesc(BN);
             mbar_wait(b_bar, 0);
             uint32_t it = 0, t = 0;
+            if (p.ws_halo && p.taps == 9 && p.kw == 3 && STG >= 2 * p.kchunks + 1 && NACC >= 2) {
+                // 3x3 halo mode, TWO tiles in flight: the 72 small MMAs of a tile all accumulate into the same TMEM
+                // columns, so back-to-back they run at the pipeline latency, not its throughput (measured ~100 cycles per
+                // N = 32 MMA).  Alternating between two tiles' accumulators gives the tensor pipe independent work.
+                const uint32_t hw = (uint32_t)(p.TW + p.kw - 1);
+                const uint64_t bstep = (uint64_t)((uint32_t)(p.kchunks * B_KB_BYTES) >> 4);
+                for (int mt = m_first; mt < m_tiles; mt += 2 * m_step, t += 2) {
+                    const bool two = mt + m_step < m_tiles;
+                    const int acc0 = t % NACC, acc1 = (t + 1) % NACC;
+                    mbar_wait(tmem_empty_bar(acc0), ((t / NACC) & 1) ^ 1);
+                    if (two) mbar_wait(tmem_empty_bar(acc1), (((t + 1) / NACC) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d0 = tmem_base + (uint32_t)(acc0 * BN), d1 = tmem_base + (uint32_t)(acc1 * BN);
+                    for (int ch = 0; ch < p.kchunks; ++ch) {
+                        const uint32_t i0 = it + ch, i1 = it + p.kchunks + ch;
+                        const int s0 = i0 % STG, s1 = i1 % STG;
+                        mbar_wait(full_bar(s0), (i0 / STG) & 1);
+                        if (two) mbar_wait(full_bar(s1), (i1 / STG) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t a0 = make_smem_desc_sbo(a_base + s0 * ASB, hw * 128u);
+                        const uint64_t a1 = make_smem_desc_sbo(a_base + s1 * ASB, hw * 128u);
+                        const uint64_t b0 = make_smem_desc(b_base + ch * B_KB_BYTES);
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint64_t ao = (uint64_t)(((tap / 3) * (WS_HALO_TW + 2) + (tap % 3)) * 8);
+                            const uint64_t bd = b0 + bstep * (uint64_t)tap;
+#pragma unroll
+                            for (int k2 = 0; k2 < BK / 16; ++k2) {
+                                umma_bf16(d0, a0 + ao + (uint64_t)(2 * k2), bd + (uint64_t)(2 * k2), idesc, (ch | tap | k2) != 0);
+                                if (two) umma_bf16(d1, a1 + ao + (uint64_t)(2 * k2), bd + (uint64_t)(2 * k2), idesc, (ch | tap | k2) != 0);
+                            }
+                        }
+                        umma_commit(empty_bar(s0));
+                        if (two) umma_commit(empty_bar(s1));
+                    }
+                    it += (two ? 2 : 1) * p.kchunks;
+                    umma_commit(tmem_full_bar(acc0));
+                    if (two) umma_commit(tmem_full_bar(acc1));
+                }
+            } else
             for (int mt = m_first; mt < m_tiles; mt += m_step, ++t) {
                 int acc = t % NACC;
                 uint32_t aph = (t / NACC) & 1;
@@ -883,6 +923,22 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
                         uint32_t ph = (it / STG) & 1;
                         mbar_wait(full_bar(s), ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (p.taps == 9 && p.kw == 3) {
+                            // 3x3: descriptor arithmetic hoisted — one base descriptor per stage / chunk, per-tap offsets are
+                            // compile-time (A: (ky * 10 + kx) halo rows of 128 bytes) or one multiply (B); the single
+                            // issuing thread would otherwise spend more time building descriptors than the MMAs take
+                            const uint64_t a0 = make_smem_desc_sbo(a_base + s * ASB, hw * 128u);
+                            const uint64_t b0 = make_smem_desc(b_base + ch * B_KB_BYTES);
+                            const uint64_t bstep = (uint64_t)((uint32_t)(p.kchunks * B_KB_BYTES) >> 4);
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint64_t ad = a0 + (uint64_t)(((tap / 3) * (WS_HALO_TW + 2) + (tap % 3)) * 8);
+                                const uint64_t bd = b0 + bstep * (uint64_t)tap;
+#pragma unroll
+                                for (int k2 = 0; k2 < BK / 16; ++k2)
+                                    umma_bf16(tmem_d, ad + (uint64_t)(2 * k2), bd + (uint64_t)(2 * k2), idesc, (ch | tap | k2) != 0);
+                            }
+                        } else
                         for (int tap = 0; tap < p.taps; ++tap) {
                             int ky = tap / p.kw, kx = tap - ky * p.kw;
                             // rows of the A operand = pixels (ty + ky, tx + kx) of the halo tile: 8-pixel groups, one halo row apart
