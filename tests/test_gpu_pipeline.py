@@ -157,3 +157,24 @@ def test_concurrent_callers_share_one_engine(system_fp32):
         got = list(ex.map(lambda p: system_fp32.ocr(p)[0], pages))
     assert got == expected
     assert sum(len(r) for r in expected) >= 24
+
+
+def test_micro_batcher_equals_per_page_calls(system_fp32):
+    """Cross-request batching: 8 threads calling `ocr(img)` through the batcher get exactly the
+    per-page results, from fewer library calls."""
+    from concurrent.futures import ThreadPoolExecutor
+    from onnxocr_b200.batcher import MicroBatcher, decode_pages
+    import cv2
+    pages = [synth_pages.render_page(384 + 32 * (i % 3), 512, 5 + i % 4, seed=500 + i, rot180_frac=0.2)[0] for i in range(12)]
+    expected = [system_fp32.ocr(p) for p in pages]
+    mb = MicroBatcher(system_fp32, max_batch=8, max_wait_ms=20)
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        got = list(ex.map(mb.ocr, pages))
+    mb.close()
+    assert got == expected
+    assert mb.pages == 12 and mb.batches < 12
+    # page feed: encoded bytes -> pinned buffers -> one batched call
+    blobs = [cv2.imencode(".png", p)[1].tobytes() for p in pages[:4]]
+    decoded = decode_pages(blobs, engine=system_fp32.engine, workers=4)
+    assert all(np.array_equal(d, p) for d, p in zip(decoded, pages[:4]))
+    assert system_fp32.ocr_batch(decoded) == [e[0] for e in expected[:4]]
