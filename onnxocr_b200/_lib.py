@@ -343,7 +343,7 @@ class Engine(object):
                                                   _ptr(ids), max_len, lens, _ptr(scores)))
         return [ids[i, :lens[i]].copy() for i in range(n)], scores[:n]
 
-    def ocr_pages(self, pages, params=None, line_cap=None, max_len=160):
+    def ocr_pages(self, pages, params=None, line_cap=None, max_len=None):
         """TextSystem.__call__ for a batch of pages in one call (Level C).  -> per page a dict with
         boxes float32 [m,4,2] (sorted_boxes order), ids (list of int32 arrays), scores float32 [m],
         cls_labels int32 [m], cls_scores float32 [m] (zeros when the classifier is off)."""
@@ -356,6 +356,11 @@ class Engine(object):
         hs, ws = _int_arr([p.shape[0] for p in pages]), _int_arr([p.shape[1] for p in pages])
         st = _int_arr([p.strides[0] for p in pages])
         cap = int(line_cap or max(1000, 300 * n))
+        # id buffer width: sticky across calls — a line longer than the buffer costs one re-run, after which the engine
+        # remembers the width (very wide lines decode to more than 160 characters)
+        sticky = max_len is None
+        if sticky:
+            max_len = getattr(self, "_ocr_max_len", 160)
         while True:
             boxes = np.zeros((cap, 4, 2), np.float32)
             ids = np.zeros((cap, max_len), np.int32)
@@ -373,7 +378,9 @@ class Engine(object):
             total = sum(counts[i] for i in range(n))
             longest = int(lens[:total].max()) if total else 0
             if longest > max_len:                       # a line longer than the id buffer: rerun with room for it
-                max_len = longest + 8
+                max_len = (longest + 8 + 31) // 32 * 32
+                if sticky:
+                    self._ocr_max_len = max_len
                 continue
             break
         out, off = [], 0

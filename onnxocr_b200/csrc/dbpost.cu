@@ -513,11 +513,13 @@ void Stages::db_post_enqueue(int lane, const float* d_prob, int n, int h, int w,
     }
     B200_CUDA_CHECK(cudaMemcpyAsync(d_src, h_src, 2 * n * sizeof(int), cudaMemcpyHostToDevice, st));
     {
-        static bool attr_set = false;
+        static bool attr_set[16] = {false};             // per device: function attributes are per context
+        int dev = 0;
+        cudaGetDevice(&dev);
         size_t smem = kWarpSmem * kWarpsPerBlock;
-        if (!attr_set) {
+        if (!attr_set[dev & 15]) {
             B200_CUDA_CHECK(cudaFuncSetAttribute(contour_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
+            attr_set[dev & 15] = true;
         }
         contour_warp_kernel<<<(unsigned)ceil_div(nt, kWarpsPerBlock), 32 * kWarpsPerBlock, smem, st>>>(
             bm, cand, counts, box1, valid, d_flagged, n, h, w, maxc, (float)p.min_size);

@@ -453,10 +453,12 @@ inline void launch_dwconv_tile_cc(const bf16* x, const bf16* w, const float* bia
     constexpr int TW = 16, TH = 8, G = CC / 8;
     constexpr int IR = (TH - 1) * SH + K, IC = (TW - 1) * SW + K;
     constexpr size_t smem = ((size_t)IR * IC * G + (K > 3 ? K * K * G : 0)) * 16;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[16] = {false};                     // per device: function attributes are per context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr[dev & 15]) {
         cudaFuncSetAttribute(dwconv_tile_kernel<K, SH, SW, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
+        attr[dev & 15] = true;
     }
     int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
     dim3 grid((unsigned)(tiles_x * tiles_y * p.N), (unsigned)((p.CP + CC - 1) / CC));
@@ -611,10 +613,12 @@ inline void launch_dwconv_strip_w(const bf16* x, const float* w, const float* bi
     constexpr int IR = (TY - 1) * SH + K, IC = (TX - 1) * SW + K;
     constexpr int PS = (SW == 2 && WPP < 32) ? WPP * 3 / 2 : WPP;
     constexpr size_t smem = (size_t)IR * IC * PS * 4;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[16] = {false};                     // per device: function attributes are per context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr[dev & 15]) {
         cudaFuncSetAttribute(dwconv_strip_kernel<K, SH, SW, WPP, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
+        attr[dev & 15] = true;
     }
     int tiles_x = (p.Wo + TX - 1) / TX, tiles_y = (p.Ho + TY - 1) / TY;
     dim3 grid((unsigned)(tiles_x * tiles_y * p.N), (unsigned)((p.CP + 2 * WPP - 1) / (2 * WPP)));

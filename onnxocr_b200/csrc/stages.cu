@@ -845,7 +845,7 @@ void Stages::ocr_pages(Model* det, Model* cls, Model* rec, const uint8_t* const*
     // waves are used only when the page uploads are the long pole (A4 @ 300 dpi: 26 MB per page, +4 %).
     size_t page_bytes = 0;
     for (int i = 0; i < n; ++i) page_bytes += (size_t)hs[i] * pool.stride[i];
-    const int wave = (page_bytes > ((size_t)96 << 20) && n >= 8) ? std::max(4, (n + 1) / 2) : n;
+    const int wave = (page_bytes / (size_t)n > ((size_t)16 << 20) && n >= 8) ? std::max(4, (n + 1) / 2) : n;   // A4 @ 300 dpi class pages only
     int line0 = 0;
     for (int p0 = 0; p0 < n; p0 += wave) {
         const int p1 = std::min(n, p0 + wave), np = p1 - p0;
