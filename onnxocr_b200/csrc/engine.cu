@@ -252,6 +252,8 @@ Model::Model(const std::string& path, int precision) : prec_(precision) {
         b.resize(a.size(), 0.f);
         dvec_.push_back({upload(a), upload(b)});
     }
+    // the uploads above went through the legacy stream from pageable memory; the engine's streams are non-blocking
+    B200_CUDA_CHECK(cudaDeviceSynchronize());
 }
 
 Model::~Model() {
@@ -391,6 +393,11 @@ std::unique_ptr<Plan> Model::build_plan(int n, int h, int w, bool head, int own_
     p->w = w;
     if (prec_ == PREC_BF16) build_steps<bf16>(*p);
     else build_steps<float>(*p);
+    // build_steps uploads small per-plan tables (fused-tail weights, SE ticket counters) with cudaMemcpy / cudaMemset on
+    // the legacy stream.  Those are NOT ordered with the engine's non-blocking streams and may still be in flight when
+    // they return (device memset; pageable H2D), so a plan's first launch could see unset counters.  Plans are built
+    // rarely: drain the device once.
+    B200_CUDA_CHECK(cudaDeviceSynchronize());
     constexpr size_t kPrivateMax = (size_t)192 << 20, kPrivateBudget = (size_t)24 << 30;
     if ((own_arena == 2 || (own_arena == 1 && p->arena_bytes <= kPrivateMax)) && private_bytes_ + p->arena_bytes <= kPrivateBudget) {
         B200_CUDA_CHECK(cudaMalloc(&p->own_arena, p->arena_bytes));
@@ -569,7 +576,9 @@ void Model::build_steps(Plan& p) {
                     int rows = iv.n * iv.h * iv.w;
                     int n_tiles = dw.tc_rows / tc::HEAD_BN;
                     int m_tiles = (int)ceil_div(rows, tc::BM);
-                    int splits = std::max(1, std::min({16, n_tiles, (int)ceil_div(2 * 148, m_tiles)}));
+                    // the class range is always cut the same way (independent of the batch size): the merged sum of
+                    // exponentials is then grouped identically for every batch a row may find itself in
+                    int splits = std::max(1, std::min(16, n_tiles));
                     int per = (int)ceil_div(n_tiles, splits);
                     splits = (int)ceil_div(n_tiles, per);
                     int kblocks = (iv.cp + tc::BK - 1) / tc::BK;
@@ -682,7 +691,8 @@ void Model::build_steps(Plan& p) {
                     int wb_rows = dw.tc_rows, wb_k = dw.tc_k;
                     const float* tbias = dw.tc_bias;
                     int icp = iv.cp;
-                    if (pointwise && !c.is_linear && dw.pk_w && dw.pk_P * iv.cp == 64 && tp.M % dw.pk_P == 0 && tc_ws_enabled()) {
+                    // (decided per sample — H*W, not the batch total — so that a crop's result never depends on what it is batched with)
+                    if (pointwise && !c.is_linear && dw.pk_w && dw.pk_P * iv.cp == 64 && (iv.h * iv.w) % dw.pk_P == 0 && tc_ws_enabled()) {
                         tp.M /= dw.pk_P;
                         tp.Cout = tp.CoutP = dw.pk_P * cp.CoutP;
                         tp.kchunks = 1;

@@ -215,6 +215,7 @@ static const short* cubic_tab_device() {
         std::vector<short> t = cubic_table();
         B200_CUDA_CHECK(cudaMalloc(&g_cubic_tab[dev], t.size() * sizeof(short)));
         B200_CUDA_CHECK(cudaMemcpy(g_cubic_tab[dev], t.data(), t.size() * sizeof(short), cudaMemcpyHostToDevice));
+        B200_CUDA_CHECK(cudaDeviceSynchronize());          // legacy-stream copy vs the engine's non-blocking streams
     }
     return g_cubic_tab[dev];
 }

@@ -178,3 +178,27 @@ def test_micro_batcher_equals_per_page_calls(system_fp32):
     decoded = decode_pages(blobs, engine=system_fp32.engine, workers=4)
     assert all(np.array_equal(d, p) for d, p in zip(decoded, pages[:4]))
     assert system_fp32.ocr_batch(decoded) == [e[0] for e in expected[:4]]
+
+
+def test_bf16_results_do_not_depend_on_call_composition(lib_built, model_paths):
+    """The same page must give bit-identical boxes, ids and scores whatever else shares its call — including the very
+    first use of every launch plan (a regression test: per-plan tables uploaded on the legacy stream were once still in
+    flight at a plan's first launch, and narrow layers were pixel-packed depending on the batch total)."""
+    ocr = pipeline.ONNXPaddleOcr(use_angle_cls=True, det_model_dir=model_paths["det"], rec_model_dir=model_paths["rec"],
+                                 cls_model_dir=model_paths["cls"], rec_char_dict_path=model_paths["dict"], precision="bf16")
+    ocr.args._b200_engine = None
+    pages = synth_pages.e2e_pages_c4(20, seed=11)
+    P = ocr._ocr_params(True)
+
+    def raw(pgs):
+        return [(r["boxes"].tolist(), [i.tolist() for i in r["ids"]], r["scores"].tolist(), r["cls_labels"].tolist())
+                for r in ocr.engine.ocr_pages(pgs, P)]
+
+    ref = raw(pages)
+    assert sum(len(r[2]) for r in ref) > 200
+    for k in (2, 3, 7):
+        got = [None] * len(pages)
+        for j in range(k):
+            got[j::k] = raw(pages[j::k])
+        assert got == ref, "results changed when the pages were split over %d calls" % k
+    assert raw(pages) == ref
