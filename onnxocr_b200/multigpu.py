@@ -20,6 +20,24 @@ def process_shard(pages, fn, rank, world):
     return [(i, fn(pages[i])) for i in shard_indices(len(pages), rank, world)]
 
 
+_HOST_GROUP = None
+
+
+def host_group():
+    """A gloo group over all ranks for the host-side result gather (cached).  With the NCCL default group
+    `gather_object` would stage the pickled results through GPU tensors and synchronise the devices (measured on 2
+    B200s: 70-230 ms per gather against 11 ms over gloo).  All ranks must call it (it creates a group)."""
+    global _HOST_GROUP
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return None
+    if dist.get_backend() == "gloo":
+        return None
+    if _HOST_GROUP is None:
+        _HOST_GROUP = dist.new_group(backend="gloo")
+    return _HOST_GROUP
+
+
 def gather_by_page(local, n_items, group=None):
     """All ranks call this; rank 0 receives the results in page order (others get None)."""
     import torch.distributed as dist
@@ -52,4 +70,4 @@ def ocr_pages_sharded(pages, fn, group=None):
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     else:
         rank, world = 0, 1
-    return gather_by_page(process_shard(pages, fn, rank, world), len(pages), group)
+    return gather_by_page(process_shard(pages, fn, rank, world), len(pages), group if group is not None else host_group())

@@ -20,8 +20,10 @@ rank = int(os.environ.get("RANK", "0"))
 world = int(os.environ.get("WORLD_SIZE", "1"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
+host_group = None
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    host_group = dist.new_group(backend="gloo")     # the result gather is host-side work: keep it off the GPUs
 ocr = pipeline.ONNXPaddleOcr(use_angle_cls=True, precision="bf16", gpu_id=local)
 pages = synth_pages.e2e_pages_c4(n, seed=2)
 mine = multigpu.shard_indices(n, rank, world)
@@ -44,7 +46,7 @@ for _ in range(reps):
     ta = time.perf_counter()
     local_res = run_shard()
     tb = time.perf_counter()
-    gathered = multigpu.gather_by_page(local_res, n)
+    gathered = multigpu.gather_by_page(local_res, n, group=host_group)
     t_run += tb - ta
     t_gather += time.perf_counter() - tb
 if world > 1:
