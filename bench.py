@@ -153,13 +153,13 @@ def main():
         if rank != 0:
             return
         pages = make_pages(0)
-        r = cpu_arm(pages, max(1, args.steps), min(warmup, 1), sample_pages=2)
+        r = cpu_arm(pages, max(1, args.steps), min(warmup, 1), sample_pages=4)
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "pages/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C2 det-only: 960x960 synthetic pages, prob map + DBPostProcess boxes",
-                       "pages_per_step": 2},
+                       "pages_per_step": 4},
             "cpu_baseline": {"value": r["value"], "unit": "pages/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -311,7 +311,7 @@ def main():
         "clocks": sampler.summary(),
     }
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_arm(pages, 1, 1, sample_pages=8)
+        r = cpu_arm(pages, 8, 1, sample_pages=PAGES_PER_GPU)          # ~10-25 s of CPU work on the box's cores
         out["cpu_baseline"] = {"value": r["value"], "unit": "pages/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     print(json.dumps(out))
     if world > 1:
