@@ -778,9 +778,21 @@ __global__ void __launch_bounds__(kGapSeThreads) gap_se_kernel(const T* __restri
     const int r = threadIdx.x / cg, g = threadIdx.x % cg;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (r < rows) {
-        for (int px = p0 + r; px < p1; px += rows) {
+        // four independent loads in flight per thread (the per-thread accumulation order px, px+rows, ... is unchanged)
+        int px = p0 + r;
+        const T* base = x + (int64_t)n * HW * CP + g * 4;
+        for (; px + 3 * rows < p1; px += 4 * rows) {
+            float v0[4], v1[4], v2[4], v3[4];
+            ST<T>::ld4(base + (int64_t)px * CP, v0);
+            ST<T>::ld4(base + (int64_t)(px + rows) * CP, v1);
+            ST<T>::ld4(base + (int64_t)(px + 2 * rows) * CP, v2);
+            ST<T>::ld4(base + (int64_t)(px + 3 * rows) * CP, v3);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = (((acc[j] + v0[j]) + v1[j]) + v2[j]) + v3[j];
+        }
+        for (; px < p1; px += rows) {
             float v[4];
-            ST<T>::ld4(x + ((int64_t)n * HW + px) * CP + g * 4, v);
+            ST<T>::ld4(base + (int64_t)px * CP, v);
             acc[0] += v[0]; acc[1] += v[1]; acc[2] += v[2]; acc[3] += v[3];
         }
         for (int j = 0; j < 4; ++j) sm[r * CP + g * 4 + j] = acc[j];
