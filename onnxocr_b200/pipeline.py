@@ -20,8 +20,13 @@ def default_args(**kwargs):
              rec_batch_num=6, rec_char_dict_path=os.path.join(assets, "ppocrv5_dict.txt"), use_space_char=True,
              drop_score=0.5, use_angle_cls=False, cls_model_dir=os.path.join(assets, "ppocrv5_cls.onnx"),
              cls_image_shape="3, 48, 192", label_list=["0", "180"], cls_batch_num=6, cls_thresh=0.9,
-             save_crop_res=False, precision="fp32", fused=True, rec_width_bucket=0)
+             save_crop_res=False, precision="fp32", fused=True, rec_width_bucket=None)
     d.update(kwargs)
+    if d["rec_width_bucket"] is None:
+        # fp32 = the exact mode: every crop padded exactly as the reference's batch plan pads it.  bf16 = the fast mode
+        # (BASELINE.json: "width-bucketed by aspect ratio"): padded widths rounded up to a multiple of 32, which merges
+        # the recogniser's batches across pages (+20-30 % end to end); parity there is statistical anyway.
+        d["rec_width_bucket"] = 32 if str(d["precision"]).lower() == "bf16" else 0
     if d["det_model_dir"] is None or d["rec_model_dir"] is None:
         paths = synth_graphs.ensure_models()
         d["det_model_dir"] = d["det_model_dir"] or paths["det"]
