@@ -129,3 +129,22 @@ def test_rec_argmax_fp32_equals_dense(engine_fp32):
     dense = engine_fp32.session_run(_lib.REC, x)
     assert np.array_equal(idx, dense.argmax(2))
     assert np.array_equal(prob, dense.max(2))
+
+
+def test_server_v2_cls_model_family(lib_built, model_paths, torch_graphs):
+    """the reference's other shipped graph, `ch_ppocr_server_v2.0/cls/cls.onnx` (ir_version 8, an extra
+    'Paddle' opset import), loads through the same wire reader / executor and matches the oracle."""
+    import os
+    from onnxocr_b200 import synth_graphs
+    from oracle.torch_interp import TorchGraph
+    path = os.path.join(synth_graphs.ASSET_DIR, "ch_ppocr_server_v2_cls.onnx")
+    x = _cls_input(5, 7)
+    ref = TorchGraph(path).run(None, {"x": x})[0]
+    eng = _lib.Engine(0)
+    eng.load_onnx(_lib.CLS, path, _lib.FP32)
+    out = eng.session_run(_lib.CLS, x)
+    assert out.shape == ref.shape == (5, 2)
+    assert np.abs(out - ref).max() < FP32_TOL
+    labels, scores = eng.cls_crops(synth_pages.rec_crops_c3(5, seed=7, w=192))
+    assert (labels == ref.argmax(1)).all()
+    eng.close()
