@@ -148,3 +148,29 @@ def test_server_v2_cls_model_family(lib_built, model_paths, torch_graphs):
     labels, scores = eng.cls_crops(synth_pages.rec_crops_c3(5, seed=7, w=192))
     assert (labels == ref.argmax(1)).all()
     eng.close()
+
+
+def test_ort_shim_is_a_drop_in_session(lib_built, model_paths, torch_graphs):
+    """Level A: what `PredictBase.get_onnx_session` + the stages do with an onnxruntime session
+    (predict_base.py:7-52, predict_cls.py:75), through the module named `onnxruntime` that the shim installs."""
+    import importlib
+    import sys
+    import onnxocr_b200
+    saved = sys.modules.pop("onnxruntime", None)
+    try:
+        onnxocr_b200.install_ort_shim()
+        onnxruntime = importlib.import_module("onnxruntime")
+        assert onnxruntime.get_device() == "GPU"
+        sess = onnxruntime.InferenceSession(model_paths["cls"], None, providers=["CUDAExecutionProvider", "CPUExecutionProvider"])
+        in_names = [n.name for n in sess.get_inputs()]
+        out_names = [n.name for n in sess.get_outputs()]
+        assert in_names == ["x"] and len(out_names) == 1
+        x = _cls_input(4, 9)
+        outs = sess.run(out_names, input_feed={name: x for name in in_names})
+        ref = torch_graphs("cls").run(None, {"x": x})[0]
+        assert isinstance(outs, list) and outs[0].shape == ref.shape
+        assert np.abs(outs[0] - ref).max() < FP32_TOL
+    finally:
+        sys.modules.pop("onnxruntime", None)
+        if saved is not None:
+            sys.modules["onnxruntime"] = saved
