@@ -265,93 +265,6 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ x, co
     }
 }
 
-// Depthwise convolution, bf16 storage, 8 channels x 4 consecutive output pixels per thread.  Each input column of the
-// strip is loaded once (16-byte vector) and feeds every output of the strip it overlaps; weights are bf16 [tap][CP].
-template <int KW, int SW>
-__global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
-                                                            const float* __restrict__ bias, bf16* __restrict__ y, const DwP p) {
-    pdl_start();
-    constexpr int TW = 4;
-    constexpr int NCOL = (TW - 1) * SW + KW;
-    const int cg = p.CP >> 3;
-    const int strips_x = (p.Wo + TW - 1) / TW;
-    const int64_t total = (int64_t)p.N * p.Ho * strips_x * cg;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int g = (int)(i % cg);
-        int64_t q = i / cg;
-        int sx = (int)(q % strips_x);
-        q /= strips_x;
-        int oy = (int)(q % p.Ho);
-        int n = (int)(q / p.Ho);
-        const int c = g * 8;
-        const int ox0 = sx * TW;
-        float acc[TW][8];
-        {
-            float4 b0 = *reinterpret_cast<const float4*>(bias + c);
-            float4 b1 = *reinterpret_cast<const float4*>(bias + c + 4);
-#pragma unroll
-            for (int t = 0; t < TW; ++t) {
-                acc[t][0] = b0.x; acc[t][1] = b0.y; acc[t][2] = b0.z; acc[t][3] = b0.w;
-                acc[t][4] = b1.x; acc[t][5] = b1.y; acc[t][6] = b1.z; acc[t][7] = b1.w;
-            }
-        }
-        const int ix0 = ox0 * SW - p.pl;
-        for (int ky = 0; ky < p.kh; ++ky) {
-            int iy = oy * p.sh - p.pt + ky;
-            if ((unsigned)iy >= (unsigned)p.H) continue;
-            float wv[KW][8];
-#pragma unroll
-            for (int kx = 0; kx < KW; ++kx) {
-                uint4 t = *reinterpret_cast<const uint4*>(w + (int64_t)(ky * KW + kx) * p.CP + c);
-                wv[kx][0] = __uint_as_float(t.x << 16); wv[kx][1] = __uint_as_float(t.x & 0xffff0000u);
-                wv[kx][2] = __uint_as_float(t.y << 16); wv[kx][3] = __uint_as_float(t.y & 0xffff0000u);
-                wv[kx][4] = __uint_as_float(t.z << 16); wv[kx][5] = __uint_as_float(t.z & 0xffff0000u);
-                wv[kx][6] = __uint_as_float(t.w << 16); wv[kx][7] = __uint_as_float(t.w & 0xffff0000u);
-            }
-            const bf16* row = x + (((int64_t)n * p.H + iy) * p.W) * p.CP + c;
-#pragma unroll
-            for (int xi = 0; xi < NCOL; ++xi) {
-                int ix = ix0 + xi;
-                if ((unsigned)ix >= (unsigned)p.W) continue;
-                uint4 t = *reinterpret_cast<const uint4*>(row + (int64_t)ix * p.CP);
-                float v[8];
-                v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
-                v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
-                v[4] = __uint_as_float(t.z << 16); v[5] = __uint_as_float(t.z & 0xffff0000u);
-                v[6] = __uint_as_float(t.w << 16); v[7] = __uint_as_float(t.w & 0xffff0000u);
-#pragma unroll
-                for (int t2 = 0; t2 < TW; ++t2) {
-                    constexpr int dummy = 0;
-                    (void)dummy;
-                    int kx = xi - t2 * SW;
-                    if (kx >= 0 && kx < KW) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[t2][j] = fmaf(v[j], wv[kx][j], acc[t2][j]);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < TW; ++t) {
-            int ox = ox0 + t;
-            if (ox >= p.Wo) break;
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = (c + j < p.C) ? epi_apply(acc[t][j], p.epi) : 0.f;
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(o[0], o[1]);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(o[2], o[3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(o[4], o[5]);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(o[6], o[7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0);
-            pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2);
-            pk.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(y + (((int64_t)n * p.Ho + oy) * p.Wo + ox) * p.CP + c) = pk;
-        }
-    }
-}
-
 // Depthwise convolution with the input tile (halo included) staged in shared memory by coalesced 16-byte loads; each
 // thread owns one 8-channel group and walks the pixels of the 16 x 8 output tile assigned to it.  3x3 weights live in
 // registers (packed bf16), 5x5 weights in shared memory.  HBM traffic = input + output once; the k^2 re-reads hit smem.
