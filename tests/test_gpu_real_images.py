@@ -16,7 +16,7 @@ from oracle.restate_pipeline import OraclePipeline
 pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-IMAGES = sorted(glob.glob(os.path.join(HERE, "golden", "real_images", "*.jpg")))
+IMAGES = sorted(glob.glob(os.path.join(HERE, "golden", "real_images", "*.png")))
 
 
 def _read(path):
