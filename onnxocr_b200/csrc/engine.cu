@@ -374,7 +374,11 @@ Plan* Model::plan_for(int n, int h, int w, bool head, int own_arena, int slot) {
     auto it = plans_.find(key);
     if (it != plans_.end()) return it->second.get();
     if (plans_.size() >= 768) {                         // bounded cache (dynamic rec widths x batch sizes)
+        // Evicted plans are parked for one generation instead of being destroyed: a caller may still hold a pointer
+        // into one (the det lanes keep a plan's output map pending until its boxes are collected).
         B200_CUDA_CHECK(cudaDeviceSynchronize());
+        retired_.clear();
+        for (auto& kv : plans_) retired_.push_back(std::move(kv.second));
         plans_.clear();
         private_bytes_ = 0;
     }

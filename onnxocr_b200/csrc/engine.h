@@ -123,6 +123,7 @@ private:
     std::vector<DevWeights> dw_;
     std::vector<std::pair<float*, float*>> dvec_;
     std::map<std::vector<int>, std::unique_ptr<Plan>> plans_;
+    std::vector<std::unique_ptr<Plan>> retired_;   // previous cache generation (see plan_for)
     char* arena_ = nullptr;        // activation slab, grown to the largest plan
     size_t arena_cap_ = 0;
     float* stage_in_ = nullptr;    // device staging for host NCHW input

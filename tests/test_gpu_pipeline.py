@@ -202,3 +202,18 @@ def test_bf16_results_do_not_depend_on_call_composition(lib_built, model_paths):
             got[j::k] = raw(pages[j::k])
         assert got == ref, "results changed when the pages were split over %d calls" % k
     assert raw(pages) == ref
+
+
+def test_plan_cache_eviction_keeps_results(system_bf16):
+    """More distinct (batch, width) shapes than the plan cache holds (768): plans are evicted and rebuilt; results for a
+    shape seen before the eviction must come back unchanged."""
+    eng = system_bf16.engine
+    base = synth_pages.rec_crops_c3(1, seed=31, w=2000)[0]
+    first = {}
+    for w in range(330, 1150):                      # 820 distinct padded widths, one crop each
+        ids, scores = eng.rec_crops([base[:, :w].copy()])
+        if w < 340:
+            first[w] = (ids[0].tolist(), float(scores[0]))
+    for w, (ids0, s0) in first.items():
+        ids, scores = eng.rec_crops([base[:, :w].copy()])
+        assert ids[0].tolist() == ids0 and float(scores[0]) == s0
