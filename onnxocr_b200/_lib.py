@@ -6,6 +6,7 @@ If the shared object is missing or no CUDA device is visible, the error is raise
 import ctypes as C
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -128,9 +129,6 @@ class Engine(object):
         if getattr(self, "_h", None):
             self._L.b200ocr_destroy(self._h)
             self._h = None
-            for ptr in getattr(self, "_pinned", []):
-                self._L.b200ocr_host_free(ptr)
-            self._pinned = []
 
     def __del__(self):
         try:
@@ -210,15 +208,17 @@ class Engine(object):
         self._check(self._L.b200ocr_l2_flush(self._h))
 
     def pinned_array(self, shape, dtype=np.uint8):
-        """numpy array over page-locked host memory (b200ocr_host_alloc); freed with the engine."""
-        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        """numpy array over page-locked host memory (b200ocr_host_alloc).  The buffer belongs to the array: it is
+        released (b200ocr_host_free) when the last view of it is garbage collected, independently of the engine, so a
+        long-running page feed does not accumulate page-locked memory and no view dangles after Engine.close()."""
+        nbytes = max(1, int(np.prod(shape)) * np.dtype(dtype).itemsize)
         ptr = self._L.b200ocr_host_alloc(nbytes)
         if not ptr:
             raise MemoryError("b200ocr_host_alloc(%d) failed" % nbytes)
-        self._pinned = getattr(self, "_pinned", [])
-        self._pinned.append(ptr)
         buf = (C.c_uint8 * nbytes).from_address(ptr)
-        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+        # every numpy view keeps `buf` alive through its .base chain; the finalizer runs once `buf` is unreachable
+        weakref.finalize(buf, self._L.b200ocr_host_free, ptr)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def launch_count(self):
         return int(self._L.b200ocr_launch_count(self._h))

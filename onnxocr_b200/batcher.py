@@ -30,16 +30,28 @@ class MicroBatcher(object):
         self._worker = threading.Thread(target=self._run, name="b200ocr-microbatcher", daemon=True)
         self._worker.start()
 
+    @staticmethod
+    def _validate(img):
+        """Rejects an input in the caller's own thread, before it can be merged with other requests' pages: the engine
+        takes H x W x 3 uint8 BGR arrays (what cv2.imread / cv2.imdecode yield; None = an undecodable image)."""
+        if img is None:
+            raise ValueError("ocr(): image is None (undecodable input?)")
+        if not isinstance(img, np.ndarray):
+            raise TypeError("ocr(): expected a numpy array, got %s" % type(img).__name__)
+        if img.ndim != 3 or img.shape[2] != 3 or img.dtype != np.uint8:
+            raise ValueError("ocr(): expected an H x W x 3 uint8 BGR image, got shape %s dtype %s" % (img.shape, img.dtype))
+        if img.shape[0] == 0 or img.shape[1] == 0:
+            raise ValueError("ocr(): empty image")
+
     # ---- the reference-facing call (onnx_paddleocr.py:28): blocks until this page's result is ready
     def ocr(self, img, det=True, rec=True, cls=True):
         if not (det and rec):
             return self.model.ocr(img, det=det, rec=rec, cls=cls)      # partial modes are not batched
-        fut = Future()
-        self._q.put((img, cls, fut))
-        return fut.result()
+        return self.submit(img, cls=cls).result()
 
     def submit(self, img, cls=True):
         """Non-blocking variant: a concurrent.futures.Future resolving to `model.ocr(img)`'s result."""
+        self._validate(img)
         fut = Future()
         self._q.put((img, cls, fut))
         return fut
@@ -79,9 +91,15 @@ class MicroBatcher(object):
                     results = self.model.ocr_batch([g[0] for g in group], cls=cls_flag)
                     for (_, _, fut), res in zip(group, results):
                         fut.set_result([res])                          # ocr() returns one list per image
-                except Exception as exc:                                # every waiting caller sees the error
-                    for _, _, fut in group:
-                        if not fut.done():
+                except Exception:
+                    # One bad page must fail only its own request (the reference's per-image model.ocr does): retry
+                    # every page of the group on its own, so that only the offending page's future gets the exception.
+                    for img, _, fut in group:
+                        if fut.done():
+                            continue
+                        try:
+                            fut.set_result([self.model.ocr_batch([img], cls=cls_flag)[0]])
+                        except Exception as exc:
                             fut.set_exception(exc)
             self.batches += 1
             self.pages += len(items)
@@ -102,7 +120,7 @@ def decode_pages(sources, engine=None, workers=8, flags=None):
         img = cv2.imdecode(buf, flags)
         if img is None or engine is None:
             return img
-        pinned = engine.pinned_array(img.shape, np.uint8)
+        pinned = engine.pinned_array(img.shape, np.uint8)   # page-locked; released when the array is garbage collected
         pinned[...] = img
         return pinned
 

@@ -402,7 +402,12 @@ std::unique_ptr<Plan> Model::build_plan(int n, int h, int w, bool head, int own_
     // they return (device memset; pageable H2D), so a plan's first launch could see unset counters.  Plans are built
     // rarely: drain the device once.
     B200_CUDA_CHECK(cudaDeviceSynchronize());
-    constexpr size_t kPrivateMax = (size_t)192 << 20, kPrivateBudget = (size_t)24 << 30;
+    constexpr size_t kPrivateMax = (size_t)192 << 20;
+    // B200OCR_PRIVATE_BUDGET_MB overrides the private-slab budget (tests use a tiny one to force the shared-slab fallback)
+    static const size_t kPrivateBudget = [] {
+        const char* e = getenv("B200OCR_PRIVATE_BUDGET_MB");
+        return e ? (size_t)atoll(e) << 20 : (size_t)24 << 30;
+    }();
     if ((own_arena == 2 || (own_arena == 1 && p->arena_bytes <= kPrivateMax)) && private_bytes_ + p->arena_bytes <= kPrivateBudget) {
         B200_CUDA_CHECK(cudaMalloc(&p->own_arena, p->arena_bytes));
         p->model_arena = &p->own_arena;
@@ -704,6 +709,7 @@ void Model::build_steps(Plan& p) {
                         wb_ptr = dw.pk_w; wb_rows = dw.pk_rows; wb_k = 64;
                         tbias = dw.pk_bias;
                     }
+                    tp.cinp = icp;
                     // weight-stationary kernel whenever the layer's weight slab fits in shared memory
                     const int nkb = tp.taps * tp.kchunks;
                     // k x k convolutions re-read the activation tile once per tap, which dominates: they keep the streaming

@@ -721,6 +721,16 @@ void Stages::det_on_pool(Model* det, const PagePool& pool, const uint8_t* const*
             ResizeJob* d_jobs = (ResizeJob*)d_lane_jobs_[lane].get(sizeof(ResizeJob) * max_group);
             B200_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(ResizeJob) * b, cudaMemcpyHostToDevice, st));
             Plan* pl = det->plan_for(b, g.dst_h, g.dst_w, false, /*own_arena=*/2, /*slot=*/lane);
+            if (!pl->own_arena) {
+                // The private-slab budget is exhausted and this plan lives in the model's shared slab: it must not run
+                // while another lane's network may be using that slab.  Drain the other lanes first; a later shared-slab
+                // chunk on another lane drains this one the same way, so shared-slab chunks run strictly one at a time.
+                for (int l = 0; l < kDetLanes; ++l)
+                    if (l != lane) {
+                        collect(l);
+                        B200_CUDA_CHECK(cudaStreamSynchronize(det_st_[l]));
+                    }
+            }
             dim3 grid((unsigned)ceil_div(g.dst_w, 256), g.dst_h, b);
             if (det->precision() == PREC_BF16)
                 resize_norm_kernel<bf16><<<grid, 256, 0, st>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());

@@ -31,6 +31,7 @@ struct Params {
     int TW, TH, tiles_x, tiles_y;
     int taps, kw, pad_t, pad_l;
     int kchunks;                 // ceil(CinP / 64)
+    int cinp;                    // input channels as stored (GEMM K per tap); K slices of 16 beyond it are all zero and skipped
     int Cout, CoutP;             // GEMM columns that carry data / padded (for convT: 4 * out channels padded)
     int convT;                   // 1: column = tap * ctC + co, stored pixel-shuffled to (2y + dy, 2x + dx)
     int ctC, ctCout;             // convT: padded / real output channels
@@ -47,6 +48,26 @@ struct Params {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Warp-role dispatch must be visibly warp-uniform and the single issuing lane must come from elect.sync: with a plain
+// `if (lane == 0)` ptxas cannot prove that one thread is active and wraps EVERY uniform-datapath instruction (UTCHMMA,
+// UTMALDG, UTCBAR) in an ELECT / PLOP3 / BRA.U.ANY loop over the active lanes — measured (tools/ubench/mma_rate.cu): the
+// bare tensor pipe takes 40 cycles for an M128 N32 K16 MMA, the wrapped issue loop of round 1 ran at ~107.
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0, laneid = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 %%rx;\n"
+        ".reg .pred %%px;\n"
+        "elect.sync %%rx|%%px, %2;\n"
+        "@%%px mov.s32 %1, 1;\n"
+        "mov.s32 %0, %%rx;\n"
+        "}\n"
+        : "+r"(laneid), "+r"(pred)
+        : "r"(0xFFFFFFFFu));
+    return pred != 0;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -253,7 +274,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     if (p.ct2)
         for (int i = threadIdx.x; i < 4 * p.ctC + 1; i += kThreads) w2s[i] = p.ct2_w[i];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int nkb = p.taps * p.kchunks;
     const int m_tiles = p.mode == 0 ? (p.M + BM - 1) / BM : p.tiles_x * p.tiles_y * p.N;
     const int n_tiles = (p.CoutP + BN - 1) / BN;
@@ -300,7 +321,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             uint32_t it = 0;                                // running k-block counter across tiles
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int n0, m0, img, y0, x0;
@@ -324,7 +345,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         __syncwarp();
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc = make_idesc(BN);
             uint32_t it = 0, t = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
@@ -340,10 +361,12 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     uint64_t adesc = make_smem_desc(a_base + s * A_BYTES);
                     uint64_t bdesc = make_smem_desc(b_base + s * B_BYTES);
+                    const int chunk = kb % p.kchunks;
+                    const int ks = min(BK / 16, (p.cinp - chunk * BK + 15) >> 4);   // the last chunk may be partly padding
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-                        umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        if (k < ks) umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                     }
                     umma_commit(empty_bar(s));              // frees the smem stage once these MMAs retire
                 }
@@ -783,7 +806,7 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
         if (threadIdx.x == 0) w2q[4 * p.ctC] = p.ct2_w[4 * p.ctC];
     }
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int m_tiles = p.mode == 0 ? (p.M + BM - 1) / BM : p.tiles_x * p.tiles_y * p.N;
     const int n_tiles = (p.CoutP + BN - 1) / BN;
     const int my_nt = blockIdx.x % n_tiles;
@@ -830,7 +853,7 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_expect_tx(b_bar, (uint32_t)nkb * B_KB_BYTES);
             for (int kb = 0; kb < nkb; ++kb) tma_load_2d(b_base + kb * B_KB_BYTES, &map_b, b_bar, kb * BK, n0);
             uint32_t it = 0;
@@ -866,7 +889,7 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
         __syncwarp();
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             const uint32_t idesc = make_idesc(BN);
             mbar_wait(b_bar, 0);
             uint32_t it = 0, t = 0;
@@ -892,12 +915,14 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
                         const uint64_t a0 = make_smem_desc_sbo(a_base + s0 * ASB, hw * 128u);
                         const uint64_t a1 = make_smem_desc_sbo(a_base + s1 * ASB, hw * 128u);
                         const uint64_t b0 = make_smem_desc(b_base + ch * B_KB_BYTES);
+                        const int ks = min(BK / 16, (p.cinp - ch * BK + 15) >> 4);
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
                             const uint64_t ao = (uint64_t)(((tap / 3) * (WS_HALO_TW + 2) + (tap % 3)) * 8);
                             const uint64_t bd = b0 + bstep * (uint64_t)tap;
 #pragma unroll
                             for (int k2 = 0; k2 < BK / 16; ++k2) {
+                                if (k2 >= ks) continue;
                                 umma_bf16(d0, a0 + ao + (uint64_t)(2 * k2), bd + (uint64_t)(2 * k2), idesc, (ch | tap | k2) != 0);
                                 if (two) umma_bf16(d1, a1 + ao + (uint64_t)(2 * k2), bd + (uint64_t)(2 * k2), idesc, (ch | tap | k2) != 0);
                             }
@@ -930,13 +955,14 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
                             const uint64_t a0 = make_smem_desc_sbo(a_base + s * ASB, hw * 128u);
                             const uint64_t b0 = make_smem_desc(b_base + ch * B_KB_BYTES);
                             const uint64_t bstep = (uint64_t)((uint32_t)(p.kchunks * B_KB_BYTES) >> 4);
+                            const int ks = min(BK / 16, (p.cinp - ch * BK + 15) >> 4);
 #pragma unroll
                             for (int tap = 0; tap < 9; ++tap) {
                                 const uint64_t ad = a0 + (uint64_t)(((tap / 3) * (WS_HALO_TW + 2) + (tap % 3)) * 8);
                                 const uint64_t bd = b0 + bstep * (uint64_t)tap;
 #pragma unroll
                                 for (int k2 = 0; k2 < BK / 16; ++k2)
-                                    umma_bf16(tmem_d, ad + (uint64_t)(2 * k2), bd + (uint64_t)(2 * k2), idesc, (ch | tap | k2) != 0);
+                                    if (k2 < ks) umma_bf16(tmem_d, ad + (uint64_t)(2 * k2), bd + (uint64_t)(2 * k2), idesc, (ch | tap | k2) != 0);
                             }
                         } else
                         for (int tap = 0; tap < p.taps; ++tap) {
@@ -944,9 +970,10 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
                             // rows of the A operand = pixels (ty + ky, tx + kx) of the halo tile: 8-pixel groups, one halo row apart
                             uint64_t adesc = make_smem_desc_sbo(a_base + s * ASB + ((uint32_t)ky * hw + (uint32_t)kx) * 128u, hw * 128u);
                             uint64_t bdesc = make_smem_desc(b_base + (tap * p.kchunks + ch) * B_KB_BYTES);
+                            const int ks = min(BK / 16, (p.cinp - ch * BK + 15) >> 4);
 #pragma unroll
                             for (int k2 = 0; k2 < BK / 16; ++k2)
-                                umma_bf16(tmem_d, adesc + (uint64_t)(2 * k2), bdesc + (uint64_t)(2 * k2), idesc, (ch | tap | k2) != 0);
+                                if (k2 < ks) umma_bf16(tmem_d, adesc + (uint64_t)(2 * k2), bdesc + (uint64_t)(2 * k2), idesc, (ch | tap | k2) != 0);
                         }
                         umma_commit(empty_bar(s));
                     }
@@ -958,9 +985,10 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     uint64_t adesc = make_smem_desc(a_base + s * WS_A_BYTES);
                     uint64_t bdesc = make_smem_desc(b_base + kb * B_KB_BYTES);
+                    const int ks = min(BK / 16, (p.cinp - (kb % p.kchunks) * BK + 15) >> 4);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        if (k < ks) umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                     umma_commit(empty_bar(s));
                 }
                 umma_commit(tmem_full_bar(acc));
@@ -1106,7 +1134,7 @@ __global__ void __launch_bounds__(kThreads) ctc_head_kernel(const __grid_constan
     uint32_t* tmem_slot_ptr = (uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* bias_sm = (float*)(smem_raw + (bias_base - smem_u32(smem_raw)));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM;
     const int t_begin = blockIdx.y * p.tiles_per_split;
     const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
@@ -1136,7 +1164,7 @@ __global__ void __launch_bounds__(kThreads) ctc_head_kernel(const __grid_constan
     pdl_wait();                                             // activations of the previous kernel are complete and visible
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_expect_tx(a_bar, KB * A_KB_BYTES);
             for (int kb = 0; kb < KB; ++kb) tma_load_2d(a_base + kb * A_KB_BYTES, &map_a, a_bar, kb * BK, m0);
             uint32_t it = 0;
@@ -1151,7 +1179,7 @@ __global__ void __launch_bounds__(kThreads) ctc_head_kernel(const __grid_constan
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc = make_idesc(HEAD_BN);
             mbar_wait(a_bar, 0);
             uint32_t it = 0;

@@ -5,6 +5,7 @@
 import argparse
 import copy
 import os
+import warnings
 
 import numpy as np
 
@@ -28,6 +29,14 @@ def default_args(**kwargs):
         # the recogniser's batches across pages (+20-30 % end to end); parity there is statistical anyway.
         d["rec_width_bucket"] = 32 if str(d["precision"]).lower() == "bf16" else 0
     if d["det_model_dir"] is None or d["rec_model_dir"] is None:
+        # The reference defaults to its shipped PP-OCRv5 det/rec graphs (utils.py:251-387); those blobs are not in this
+        # checkout, so the stand-ins are architecture-faithful graphs whose weights were fitted on rendered ASCII pages.
+        # They are meant for throughput runs and tests: say so loudly instead of returning nonsense on real images.
+        missing = [k for k in ("det_model_dir", "rec_model_dir") if d[k] is None]
+        warnings.warn("onnxocr_b200: %s not given - falling back to the SYNTHETIC PP-OCRv5 stand-in graph(s) "
+                      "(weights fitted on rendered ASCII pages; text read from real images will be meaningless). "
+                      "Pass the real det.onnx / rec.onnx paths for production use." % " and ".join(missing),
+                      RuntimeWarning, stacklevel=3)
         paths = synth_graphs.ensure_models()
         d["det_model_dir"] = d["det_model_dir"] or paths["det"]
         d["rec_model_dir"] = d["rec_model_dir"] or paths["rec"]

@@ -38,16 +38,35 @@ def test_concurrent_callers_are_batched_and_get_their_own_result():
     assert len(model.calls) < 24                     # at least some requests shared a call
 
 
-def test_error_reaches_every_caller_of_the_batch_and_batcher_survives():
+def test_one_bad_page_fails_only_its_own_request_and_batcher_survives():
+    """pages of unrelated requests share a call; a failing page must not fail its co-batched neighbours
+    (the reference's per-image model.ocr fails only the offending request)."""
     model = FakeModel(fail_on=3)
     mb = MicroBatcher(model, max_batch=4, max_wait_ms=50)
     futs = [mb.submit(np.full((2, 2, 3), i, np.uint8)) for i in range(4)]
-    for f in futs:
-        with pytest.raises(RuntimeError, match="boom"):
-            f.result(timeout=10)
+    for i, f in enumerate(futs):
+        if i == 3:
+            with pytest.raises(RuntimeError, match="boom"):
+                f.result(timeout=10)
+        else:
+            assert f.result(timeout=10)[0][1][0] == "page%d" % i
     ok = mb.ocr(np.full((2, 2, 3), 7, np.uint8))
     assert ok[0][1][0] == "page7"
     assert mb.ocr(np.zeros((2, 2, 3), np.uint8), det=True, rec=False) == ["partial"]
+    mb.close()
+
+
+def test_invalid_inputs_are_rejected_before_they_are_enqueued():
+    model = FakeModel()
+    mb = MicroBatcher(model, max_batch=4, max_wait_ms=5)
+    for bad, exc in ((None, ValueError), (np.zeros((4, 4), np.uint8), ValueError), (np.zeros((4, 4, 4), np.uint8), ValueError),
+                     (np.zeros((4, 4, 3), np.float32), ValueError), ([[1, 2, 3]], TypeError), (np.zeros((0, 4, 3), np.uint8), ValueError)):
+        with pytest.raises(exc):
+            mb.ocr(bad)
+        with pytest.raises(exc):
+            mb.submit(bad)
+    assert model.calls == []                          # nothing reached the model
+    assert mb.ocr(np.full((2, 2, 3), 5, np.uint8))[0][1][0] == "page5"
     mb.close()
 
 

@@ -16,6 +16,7 @@ eng.profile_plan(kind, n, h, w, iters=2)
 prof = eng.profile_plan(kind, n, h, w, iters=5)
 tot = sum(s["ms"] for s in prof)
 print("total %.3f ms over %d launches" % (tot, len(prof)))
-for s in sorted(prof, key=lambda s: -s["ms"])[:int(os.environ.get("TOP", "40"))]:
+rows = prof if os.environ.get("ORDER") == "1" else sorted(prof, key=lambda s: -s["ms"])[:int(os.environ.get("TOP", "40"))]
+for s in rows:
     print("%8.4f ms %5.1f%%  %8.2f TF/s %8.1f GB/s  %s" % (s["ms"], 100 * s["ms"] / tot, s["flops"] / max(s["ms"], 1e-9) / 1e9,
                                                        s["bytes"] / max(s["ms"], 1e-9) / 1e6, s["name"]))
