@@ -91,6 +91,13 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Channel sums for the SE gate, accumulated by the producing kernel (see se_fc_sums_kernel): 48.16 fixed point, 64-bit
+// integer atomics — associative, hence independent of the order in which tiles finish.
+constexpr float kGapFixScale = 65536.f;
+__device__ __forceinline__ void gap_fix_add(unsigned long long* dst, float v) {
+    if (v != 0.f) atomicAdd(dst, (unsigned long long)__float2ll_rn(v * kGapFixScale));
+}
+
 __device__ __forceinline__ float epi_act(float v, int type, float a, float b) {
     switch (type) {
         case EPI_RELU: return fmaxf(v, 0.f);

@@ -112,6 +112,24 @@ static bool pixel_pack_enabled() {        // B200OCR_NO_PIXEL_PACK=1 disables th
     return v == 1;
 }
 
+static bool se_lazy_enabled() {           // B200OCR_NO_SE_LAZY=1: always materialise x * gate (A/B measurements)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200OCR_NO_SE_LAZY");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+static bool se_sums_enabled() {           // B200OCR_NO_SE_SUMS=1: separate GAP pass instead of producer-side channel sums
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200OCR_NO_SE_SUMS");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 static bool dw_strip_enabled() {          // B200OCR_DW=tile selects the previous depthwise kernel (A/B measurements)
     static int v = -1;
     if (v < 0) {
@@ -126,10 +144,68 @@ struct TcState {            // per conv step: tensor maps, re-encoded when the a
     const void* a_ptr = nullptr;
 };
 
+// Two 1x1 convolutions in a row with nothing non-linear between them (and no other reader of the intermediate) are ONE
+// linear map: W = W_b W_a, b = W_b b_a + b_b, merged in float64 at load time.  The PP-LCNetV3 det backbone ends every
+// stage that way (a 1x1 "neck adapter" to 12..360 channels feeding RSEFPN's 1x1 ins_conv), so four launches and the
+// narrow intermediates disappear.  Only the bf16 fast mode does this: the fp32 mode executes the graph node by node.
+static int fuse_pointwise_chains(CGraph& g) {
+    auto is_pw = [](const CNode& c) {
+        return c.kind == C_CONV && !c.is_linear && c.kh == 1 && c.kw == 1 && c.sh == 1 && c.sw == 1 && c.pt == 0 && c.pl == 0 &&
+               c.pb == 0 && c.pr == 0 && c.groups == 1;
+    };
+    int fused = 0;
+    for (bool changed = true; changed;) {
+        changed = false;
+        std::map<std::string, int> nuse;
+        for (auto& c : g.nodes)
+            for (auto& in : c.in) nuse[in]++;
+        nuse[g.output_name]++;
+        for (size_t i = 0; i < g.nodes.size() && !changed; ++i) {
+            const CNode& a = g.nodes[i];
+            if (!is_pw(a) || a.epi.n != 0 || nuse[a.out] != 1) continue;
+            for (size_t j = i + 1; j < g.nodes.size(); ++j) {
+                CNode& b = g.nodes[j];
+                if (b.in.empty() || b.in[0] != a.out) continue;
+                if (!is_pw(b) || b.cin != a.cout) break;
+                const ConvWeights &wa = g.weights[a.weight_id], &wb = g.weights[b.weight_id];
+                ConvWeights wm;
+                wm.cin = a.cin; wm.cout = b.cout; wm.kh = wm.kw = 1;
+                wm.w.assign((size_t)a.cin * b.cout, 0.f);
+                wm.bias.assign(b.cout, 0.f);
+                for (int co = 0; co < b.cout; ++co) {
+                    for (int ci = 0; ci < a.cin; ++ci) {
+                        double acc = 0;
+                        for (int m = 0; m < a.cout; ++m) acc += (double)wa.w[(size_t)ci * a.cout + m] * (double)wb.w[(size_t)m * b.cout + co];
+                        wm.w[(size_t)ci * b.cout + co] = (float)acc;
+                    }
+                    double bb = wb.bias[co];
+                    for (int m = 0; m < a.cout; ++m) bb += (double)wa.bias[m] * (double)wb.w[(size_t)m * b.cout + co];
+                    wm.bias[co] = (float)bb;
+                }
+                g.weights.push_back(std::move(wm));
+                b.weight_id = (int)g.weights.size() - 1;
+                b.in[0] = a.in[0];
+                b.cin = a.cin;
+                g.nodes.erase(g.nodes.begin() + i);
+                ++fused;
+                changed = true;
+                break;
+            }
+        }
+    }
+    return fused;
+}
+
+static bool pw_fuse_enabled() {           // B200OCR_NO_PW_FUSE=1: keep consecutive 1x1 convolutions separate (A/B measurements)
+    const char* e = getenv("B200OCR_NO_PW_FUSE");
+    return !(e && e[0] == '1');
+}
+
 // ------------------------------------------------------------------------------------ load
 Model::Model(const std::string& path, int precision) : prec_(precision) {
     OnnxModel m = load_onnx(path);
     g_ = build_cgraph(m);
+    if (prec_ == PREC_BF16 && pw_fuse_enabled()) fuse_pointwise_chains(*g_);
     if (g_->input_shape.size() == 4 && g_->input_shape[1] > 0) in_c_ = (int)g_->input_shape[1];
     dw_.resize(g_->weights.size());
     // pre = (a0, b0) of the node's compiled epilogue: folded into the tensor-core operand pack (W * a0, bias * a0 + b0)
@@ -456,6 +532,7 @@ void Model::build_steps(Plan& p) {
         const PVal& pv = p.vals[v];
         if (pv.up_src >= 0) { use(pv.up_src); return; }
         if (pv.root >= 0) buf_last[pv.root] = std::max(buf_last[pv.root], cur);
+        if (pv.gate >= 0) buf_last[pv.gate] = std::max(buf_last[pv.gate], cur);
     };
     auto get = [&](const std::string& name, const CNode& c) -> int {
         auto it = vid.find(name);
@@ -473,8 +550,43 @@ void Model::build_steps(Plan& p) {
         cost_flops = cost_bytes = 0;
     };
     auto vbytes = [&](int v) { return (double)p.vals[v].n * p.vals[v].h * p.vals[v].w * p.vals[v].c * esz; };
-    // materialise a virtual upsample
+    // value without a pending SE gate: runs se_apply once per gated value (cached) when a consumer cannot apply it itself
+    std::map<int, int> ungated;
+    std::function<int(int)> plain = [&](int v) -> int {
+        if (p.vals[v].up_src >= 0) {
+            int src = p.vals[v].up_src, ps = plain(src);
+            if (ps == src) return v;
+            PVal nv = p.vals[v];
+            nv.up_src = ps;
+            p.vals.push_back(nv);
+            return (int)p.vals.size() - 1;
+        }
+        if (p.vals[v].gate < 0) return v;
+        auto it = ungated.find(p.vals[v].root * 4096 + p.vals[v].gate);
+        if (it != ungated.end()) return alias_val(it->second, p.vals[v].form, p.vals[v].h, p.vals[v].w);
+        const PVal gv = p.vals[v];
+        int out = new_val(gv.form, gv.n, gv.h, gv.w, gv.c);
+        use(v);
+        const int HW = gv.h * gv.w, CP = gv.cp, C = gv.c, residual = gv.gate_res, gbuf = gv.gate;
+        const int64_t total4 = (int64_t)gv.n * HW * (gv.cp / 4), total8 = (int64_t)gv.n * HW * (gv.cp / 8);
+        const bool x8 = std::is_same<T, bf16>::value && gv.cp % 8 == 0 && total8 < ((int64_t)1 << 31);
+        cost_bytes = 2.0 * (double)gv.n * HW * gv.c * esz;
+        Epilogue none;
+        emit("se_apply(materialise)", [=](cudaStream_t st) {
+            if (x8) {
+                launch_pdl(se_apply_bf16x8_kernel, grid_for(total8), 256, 0, st, (const bf16*)pp->ptr(v), (const float*)pp->bufptr(gbuf),
+                           (bf16*)pp->ptr(out), (uint32_t)HW, CP, C, (uint32_t)total8, residual, none);
+                return;
+            }
+            launch_pdl(se_apply_kernel<T>, grid_for(total4), 256, 0, st, (const T*)pp->ptr(v), (const float*)pp->bufptr(gbuf),
+                       (T*)pp->ptr(out), (int64_t)HW, CP, C, total4, residual, none);
+        });
+        ungated[gv.root * 4096 + gv.gate] = out;
+        return out;
+    };
+    // materialise a virtual upsample (and any pending gate)
     auto materialize = [&](int v) -> int {
+        v = plain(v);
         if (p.vals[v].up_src < 0) return v;
         PVal pv = p.vals[v];
         int src = pv.up_src;
@@ -720,7 +832,7 @@ void Model::build_steps(Plan& p) {
                     // for 3x3 96->24 @ 240^2 x 8): with N = 32 the 72 small UMMAs per tile are issue-bound on the single
                     // MMA thread and the streaming kernel runs two CTAs per SM.  Off by default until the issue loop is
                     // restructured.
-                    static const bool halo_on = [] { const char* e = getenv("B200OCR_TC_HALO"); return e && e[0] == '1'; }();
+                    static const int halo_on = [] { const char* e = getenv("B200OCR_TC_HALO"); return e ? atoi(e) : 0; }();
                     const bool halo = tp.mode == 1 && halo_on && c.kh <= 5 && c.kw <= 5;
                     size_t stage_bytes = tc::WS_A_BYTES;
                     if (halo) {
@@ -735,8 +847,22 @@ void Model::build_steps(Plan& p) {
                         bn = ws_bn;
                         tp.ws_bn = ws_bn;
                         tp.ws_stages = tc::ws_pick_stages(ws_bn, nkb, stage_bytes);
-                        tp.ws_halo = halo ? 1 : 0;
+                        tp.ws_halo = halo ? halo_on : 0;   // 2: two tiles' MMAs interleaved (needs 2 * kchunks + 1 stages)
                         tp.ws_stage_bytes = (int)stage_bytes;
+                    }
+                    // an SE gate follows: the epilogue accumulates the per-image channel sums (no separate GAP pass)
+                    if (ws_bn && !tc_ct && c.epi.fast && se_sums_enabled() && ni + 1 < g.nodes.size() && g.nodes[ni + 1].kind == C_SE &&
+                        g.nodes[ni + 1].in[0] == c.out && cp.CoutP <= kSeSumsThreads && cp.CoutP % 8 == 0) {
+                        unsigned long long* sums = nullptr;
+                        const size_t bytes = (size_t)iv.n * tc::kGapReplicas * cp.CoutP * sizeof(unsigned long long);
+                        B200_CUDA_CHECK(cudaMalloc(&sums, bytes));
+                        B200_CUDA_CHECK(cudaMemset(sums, 0, bytes));
+                        p.owned.push_back(std::shared_ptr<void>(sums, [](void* q) { cudaFree(q); }));
+                        p.vals[out].sums_replicas = tc::kGapReplicas;
+                        tp.gap = sums;
+                        tp.gap_mod = cp.CoutP;
+                        tp.gap_rows = tp.mode == 0 ? tp.M / iv.n : 0;
+                        p.vals[out].sums = sums;
                     }
                     std::shared_ptr<TcState> ts(new TcState());
                     {
@@ -767,7 +893,8 @@ void Model::build_steps(Plan& p) {
                             }
                             ts->a_ptr = x;
                         }
-                        int m_tiles = tp.mode == 0 ? (int)ceil_div(tp.M, tc::BM) : tp.tiles_x * tp.tiles_y * tp.N;
+                        int m_tiles = tp.mode == 0 ? (tp.gap ? tp.N * (int)ceil_div(tp.gap_rows, tc::BM) : (int)ceil_div(tp.M, tc::BM))
+                                                   : tp.tiles_x * tp.tiles_y * tp.N;
                         if (ws_bn) {
                             int n_tiles = (int)ceil_div(tp.CoutP, ws_bn);
                             int m_groups = std::max(1, std::min(m_tiles, 148 / n_tiles));
@@ -856,6 +983,18 @@ void Model::build_steps(Plan& p) {
                 int64_t total = (int64_t)iv.n * Ho * Wo * (iv.cp / 4);
                 cost_flops = 2.0 * iv.n * Ho * Wo * (double)c.cout * c.kh * c.kw;
                 cost_bytes = vbytes(in) + vbytes(out);
+                const bool strip_ok = std::is_same<T, bf16>::value && wb16 && dp.CP % 8 == 0 && dp.kh == dp.kw && (dp.kw == 3 || dp.kw == 5) &&
+                                      (dp.sw == 1 || dp.sw == 2) && (dp.sh == 1 || dp.sh == 2) && dw_strip_enabled();
+                if (strip_ok && se_sums_enabled() && ni + 1 < g.nodes.size() && g.nodes[ni + 1].kind == C_SE && g.nodes[ni + 1].in[0] == c.out &&
+                    iv.cp <= kSeSumsThreads) {
+                    unsigned long long* sums = nullptr;
+                    const size_t bytes = (size_t)iv.n * iv.cp * sizeof(unsigned long long);
+                    B200_CUDA_CHECK(cudaMalloc(&sums, bytes));
+                    B200_CUDA_CHECK(cudaMemset(sums, 0, bytes));
+                    p.owned.push_back(std::shared_ptr<void>(sums, [](void* q) { cudaFree(q); }));
+                    dp.gap = sums;
+                    p.vals[out].sums = sums;
+                }
                 emit("dwconv " + c.name, [=](cudaStream_t st) {
                     if (std::is_same<T, bf16>::value && wb16 && dp.CP % 8 == 0 && dp.kh == dp.kw && (dp.kw == 3 || dp.kw == 5) &&
                         (dp.sw == 1 || dp.sw == 2) && (dp.sh == 1 || dp.sh == 2)) {
@@ -906,8 +1045,10 @@ void Model::build_steps(Plan& p) {
                 int N = iv.n, CP = iv.cp, C = iv.c;
                 use(in);
                 cost_bytes = vbytes(in);
+                // the producer already accumulated the channel sums in its epilogue: no pass over the tensor at all
+                const bool from_sums = c.kind == C_SE && iv.sums != nullptr && c.se_mid <= kSeSumsThreads && iv.cp <= kSeSumsThreads;
                 const bool fuse_gap_se = c.kind == C_SE && iv.cp <= kGapSeThreads && c.se_mid <= kGapSeThreads && gap_se_fused();
-                if (!fuse_gap_se)
+                if (!fuse_gap_se && !from_sums)
                     emit("gap_partial " + c.name, [=](cudaStream_t st) {
                         launch_pdl(gap_partial_kernel<T>, dim3(chunks, N), 256, smem, st, (const T*)pp->ptr(in),
                                    (float*)pp->bufptr(partial), HW, CP, chunks);
@@ -935,12 +1076,25 @@ void Model::build_steps(Plan& p) {
                         skip[ni + 1] = 1;
                     }
                 }
-                int out = new_val(F_NCHW, iv.n, iv.h, iv.w, iv.c);
+                // The gate stays pending on the value (PVal::gate) when nothing has to be applied after the multiplication:
+                // consumers that can apply it on the fly read the un-gated tensor, the others materialise it (plain()).
+                const bool lazy = std::is_same<T, bf16>::value && iv.cp % 8 == 0 && epi.n == 0 && se_lazy_enabled();
+                int out = lazy ? alias_val(in, iv.form, iv.h, iv.w) : new_val(F_NCHW, iv.n, iv.h, iv.w, iv.c);
+                if (lazy) { p.vals[out].gate = scale; p.vals[out].gate_res = residual; p.vals[out].sums = nullptr; p.vals[out].sums_replicas = 1; }
                 const DevWeights &w1 = dw_[c.se_w1], &w2 = dw_[c.se_w2];
                 int mid = c.se_mid;
                 float alpha = c.scale, beta = c.eps;
                 size_t smem2 = (size_t)(iv.cp + mid + kSeThreads) * sizeof(float);
-                if (fuse_gap_se) {
+                if (from_sums) {
+                    unsigned long long* sums = iv.sums;
+                    const int reps = iv.sums_replicas;
+                    const size_t smem4 = (size_t)(iv.cp + mid + kSeSumsThreads) * sizeof(float);
+                    cost_bytes = (double)iv.n * iv.cp * 8 + 2.0 * (double)iv.c * mid * 4;
+                    emit("se_fc_sums " + c.name, [=](cudaStream_t st) {
+                        launch_pdl(se_fc_sums_kernel, N, kSeSumsThreads, smem4, st, sums, reps, HW, C, CP, mid, w1.w, w1.ColsW, w1.bias, w2.w,
+                                   w2.ColsW, w2.bias, alpha, beta, (float*)pp->bufptr(scale));
+                    });
+                } else if (fuse_gap_se) {
                     int* dt = nullptr;                              // one ticket counter per image, self-resetting
                     B200_CUDA_CHECK(cudaMalloc(&dt, (size_t)N * sizeof(int)));
                     B200_CUDA_CHECK(cudaMemset(dt, 0, (size_t)N * sizeof(int)));
@@ -962,6 +1116,7 @@ void Model::build_steps(Plan& p) {
                 cost_bytes = vbytes(in) + vbytes(out);
                 const int64_t total8 = (int64_t)iv.n * HW * (iv.cp / 8);
                 const bool se_x8 = std::is_same<T, bf16>::value && iv.cp % 8 == 0 && total8 < ((int64_t)1 << 31);
+                if (!lazy)
                 emit("se_apply " + c.name, [=](cudaStream_t st) {
                     if (se_x8) {
                         launch_pdl(se_apply_bf16x8_kernel, grid_for(total8), 256, 0, st, (const bf16*)pp->ptr(in), (const float*)pp->bufptr(scale),
@@ -1003,11 +1158,13 @@ void Model::build_steps(Plan& p) {
                 break;
             }
             case C_RESIZE: {
-                int in = materialize(get(c.in[0], c));
-                PVal v = p.vals[in];
+                int in = get(c.in[0], c);
+                if (p.vals[in].up_src >= 0) in = materialize(in);   // nested upsample: the inner one becomes real
+                PVal v = p.vals[in];                                // a pending SE gate stays with the source (up_src)
                 if (v.form != F_NCHW) throw std::runtime_error("Resize input is not NCHW-shaped: " + c.name);
                 v.up_src = in;
                 v.root = -1;
+                v.gate = -1; v.gate_res = 0; v.sums = nullptr;
                 v.fh = c.fh; v.fw = c.fw;
                 v.h *= c.fh; v.w *= c.fw;
                 p.vals.push_back(v);
@@ -1030,6 +1187,57 @@ void Model::build_steps(Plan& p) {
                 }
                 int out = new_val(v0.form, v0.n, v0.h, v0.w, ctot);
                 int cdp = p.vals[out].cp;
+                {
+                    // bf16, every input a multiple of 8 channels: all inputs in one launch that writes whole rows, SE gates
+                    // applied on the fly
+                    bool multi = std::is_same<T, bf16>::value && (int)ins.size() <= kCatMaxIn && cdp % 8 == 0 && cdp / 8 <= kCatMaxChunks &&
+                                 v0.h <= 65535 && v0.n <= 65535 &&
+                                 (int64_t)v0.n * v0.h * v0.w * (cdp / 8) < ((int64_t)1 << 31);
+                    auto log2i = [](int f) { int l = 0; while ((1 << l) < f) ++l; return (1 << l) == f ? l : -1; };
+                    for (int v : ins) {
+                        const PVal& q = p.vals[v];
+                        multi = multi && q.c % 8 == 0 && q.cp == q.c && (q.up_src < 0 || (log2i(q.fh) >= 0 && log2i(q.fw) >= 0));
+                    }
+                    if (multi) {
+                        CatP cp0;
+                        memset(&cp0, 0, sizeof(cp0));
+                        memset(cp0.kmap, 255, sizeof(cp0.kmap));
+                        cp0.N = v0.n; cp0.H = v0.h; cp0.W = v0.w; cp0.CdP = cdp; cp0.nin = (int)ins.size();
+                        std::vector<int> srcs, gates;
+                        int off8 = 0;
+                        double bytes = (double)v0.n * v0.h * v0.w * ctot * esz;
+                        for (size_t k = 0; k < ins.size(); ++k) {
+                            const PVal pv = p.vals[ins[k]];
+                            const int src = pv.up_src >= 0 ? pv.up_src : ins[k];
+                            use(ins[k]);
+                            srcs.push_back(src);
+                            gates.push_back(p.vals[src].gate);
+                            cp0.fh[k] = pv.up_src >= 0 ? log2i(pv.fh) : 0;
+                            cp0.fw[k] = pv.up_src >= 0 ? log2i(pv.fw) : 0;
+                            cp0.CsP[k] = pv.cp;
+                            cp0.g0[k] = off8;
+                            for (int q = 0; q < pv.c / 8; ++q) cp0.kmap[off8 + q] = (unsigned char)k;
+                            cp0.res[k] = p.vals[src].gate_res;
+                            off8 += pv.c / 8;
+                            bytes += vbytes(src);
+                        }
+                        const uint32_t total8 = (uint32_t)((int64_t)v0.n * v0.h * v0.w * (cdp / 8));
+                        cost_bytes = bytes;
+                        emit("concat " + c.name, [=](cudaStream_t st) {
+                            CatP cp = cp0;
+                            for (int k = 0; k < cp.nin; ++k) {
+                                cp.src[k] = (const bf16*)pp->ptr(srcs[k]);
+                                cp.scale[k] = gates[k] >= 0 ? (const float*)pp->bufptr(gates[k]) : nullptr;
+                            }
+                            (void)total8;
+                            dim3 grid((unsigned)ceil_div((int64_t)cp.W * (cp.CdP / 8), 256), (unsigned)cp.H, (unsigned)cp.N);
+                            launch_pdl(concat_multi_bf16_kernel, grid, 256, 0, st, (bf16*)pp->ptr(out), cp);
+                        });
+                        vid[c.out] = out;
+                        break;
+                    }
+                }
+                for (int& v : ins) v = plain(v);
                 if (cdp != ctot) {
                     int64_t tot = p.vals[out].elems();
                     emit("concat_zero " + c.name, [=](cudaStream_t st) {
@@ -1066,7 +1274,12 @@ void Model::build_steps(Plan& p) {
                 };
                 if (p.vals[a].up_src >= 0 && p.vals[b].up_src < 0) std::swap(a, b);
                 if (is_bcast(b, a)) std::swap(a, b);
-                a = materialize(a);
+                // pending SE gates are applied by the bf16x8 kernel itself; every other kernel gets plain operands
+                const bool gate_ok = std::is_same<T, bf16>::value && c.kind == C_ADD && p.vals[a].up_src < 0 && p.vals[a].cp % 8 == 0 &&
+                                     !is_bcast(a, b) &&
+                                     (int64_t)p.vals[a].n * p.vals[a].h * p.vals[a].w * (p.vals[a].cp / 8) < ((int64_t)1 << 31);
+                if (!gate_ok) { a = plain(a); b = plain(b); }
+                if (p.vals[a].up_src >= 0) a = materialize(a);
                 if (p.vals[b].up_src >= 0 && is_bcast(a, b)) b = materialize(b);
                 const PVal av = p.vals[a], bv = p.vals[b];
                 bool bc = is_bcast(a, b);
@@ -1095,10 +1308,32 @@ void Model::build_steps(Plan& p) {
                     cost_bytes = vbytes(a) + vbytes(bsrc) + vbytes(out);
                     const int64_t tot8 = (int64_t)av.n * av.h * av.w * (av.cp / 8);
                     const bool x8 = std::is_same<T, bf16>::value && av.cp % 8 == 0 && !bc && tot8 < ((int64_t)1 << 31);
+                    const int gate_a = av.gate, gate_b = p.vals[bsrc].gate;
+                    ep.res_a = av.gate_res;
+                    ep.res_b = p.vals[bsrc].gate_res;
+                    if ((gate_a >= 0 || gate_b >= 0) && !x8) throw std::runtime_error("internal: pending SE gate on a non-vector element-wise at " + c.name);
+                    auto log2i = [](int f) { int l = 0; while ((1 << l) < f) ++l; return (1 << l) == f ? l : -1; };
+                    const bool fpn = x8 && c.kind == C_ADD && c.epi.n == 0 && av.c == av.cp && log2i(ep.fh) >= 0 && log2i(ep.fw) >= 0 &&
+                                     av.h <= 65535 && av.n <= 65535 && (ep.fh > 1 || ep.fw > 1 || gate_a >= 0 || gate_b >= 0);
+                    const int bh = av.h / ep.fh, bw = av.w / ep.fw;
                     emit("eltwise " + c.name, [=](cudaStream_t st) {
+                        if (fpn) {
+                            FpnAddP fp;
+                            fp.W = ep.W; fp.Hb = bh; fp.Wb = bw; fp.cg = ep.CP / 8; fp.sh = log2i(ep.fh); fp.sw = log2i(ep.fw);
+                            fp.sa = gate_a >= 0 ? (const float*)pp->bufptr(gate_a) : nullptr;
+                            fp.sb = gate_b >= 0 ? (const float*)pp->bufptr(gate_b) : nullptr;
+                            fp.res_a = ep.res_a; fp.res_b = ep.res_b;
+                            dim3 grid((unsigned)ceil_div((int64_t)ep.W * fp.cg, 256), (unsigned)ep.H, (unsigned)ep.N);
+                            launch_pdl(fpn_add_bf16_kernel, grid, 256, 0, st, (const bf16*)pp->ptr(a), (const bf16*)pp->ptr(bsrc),
+                                       (bf16*)pp->ptr(out), fp);
+                            return;
+                        }
                         if (x8) {
+                            EltP e2 = ep;
+                            e2.sa = gate_a >= 0 ? (const float*)pp->bufptr(gate_a) : nullptr;
+                            e2.sb = gate_b >= 0 ? (const float*)pp->bufptr(gate_b) : nullptr;
                             launch_pdl(eltwise_bf16x8_kernel, grid_for(tot8), 256, 0, st, (const bf16*)pp->ptr(a), (const bf16*)pp->ptr(bsrc),
-                                                                                  (bf16*)pp->ptr(out), ep, (uint32_t)tot8);
+                                                                                  (bf16*)pp->ptr(out), e2, (uint32_t)tot8);
                             return;
                         }
                         launch_pdl(eltwise_kernel<T>, grid_for(tot), 256, 0, st, (const T*)pp->ptr(a), (const T*)pp->ptr(bsrc),

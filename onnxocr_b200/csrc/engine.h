@@ -31,6 +31,12 @@ struct PVal {
     int root = -1;                 // buffer id
     // virtual nearest-upsample of `up_src` (a C_RESIZE that was not materialised)
     int up_src = -1, fh = 1, fw = 1;
+    // lazily applied SE gate: the logical value is x * gate[n][c] (+ x when gate_res) with x = this buffer; consumers that
+    // can apply it on the fly (element-wise add, concat) read x and the gate, everyone else gets it materialised
+    int gate = -1, gate_res = 0;
+    // per (image, channel) sums of this tensor accumulated by its producer (fixed point, see common.cuh) for an SE gate
+    unsigned long long* sums = nullptr;
+    int sums_replicas = 1;
     std::vector<int64_t> host;
     std::vector<int64_t> logical() const;
     int64_t elems() const { return (int64_t)n * h * w * cp; }
@@ -59,6 +65,7 @@ struct Plan {
     size_t arena_bytes = 0;
     char** model_arena = nullptr;  // the owning Model's activation slab (shared by all of its plans) or &own_arena
     char* own_arena = nullptr;     // private slab: lets this plan run concurrently with other plans on another stream
+    std::vector<std::shared_ptr<void>> owned;     // small device allocations that live as long as the plan
     std::vector<std::function<void(cudaStream_t)>> steps;
     std::vector<std::string> step_names;
     std::vector<double> step_flops, step_bytes;   // algorithmic work per launch (unique in+out+weight bytes)

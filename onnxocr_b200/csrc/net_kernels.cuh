@@ -224,6 +224,7 @@ struct DwP {
     int Ho, Wo;
     int kh, kw, sh, sw, pt, pl;
     Epilogue epi;
+    unsigned long long* gap = nullptr;   // strip kernel: per (image, channel) sums of the stored outputs for a following SE gate
 };
 
 template <typename T>
@@ -424,7 +425,7 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 template <int K, int SH, int SW, int WPP, int TY, int ACT>
 __device__ __forceinline__ void dw_strip_rows(const uint32_t* __restrict__ col, const f32x2_t (&wf)[K * K], f32x2_t bb,
                                               bf16* __restrict__ yo, int64_t ystride, int rows_in, bool live0, bool live1,
-                                              const Epilogue& epi) {
+                                              const Epilogue& epi, bool gap, float& g0, float& g1) {
     constexpr int TX = 256 / WPP;
     constexpr int IR = (TY - 1) * SH + K, IC = (TX - 1) * SW + K;
     constexpr int PS = (SW == 2 && WPP < 32) ? WPP * 3 / 2 : WPP;
@@ -448,7 +449,12 @@ __device__ __forceinline__ void dw_strip_rows(const uint32_t* __restrict__ col, 
                 float o0 = live0 ? epi_fast<ACT>(a0, epi) : 0.f;
                 float o1 = live1 ? epi_fast<ACT>(a1, epi) : 0.f;
                 __nv_bfloat162 pk = __floats2bfloat162_rn(o0, o1);
-                *reinterpret_cast<uint32_t*>(yo + (int64_t)oy * ystride) = *reinterpret_cast<uint32_t*>(&pk);
+                const uint32_t u = *reinterpret_cast<uint32_t*>(&pk);
+                *reinterpret_cast<uint32_t*>(yo + (int64_t)oy * ystride) = u;
+                if (gap) {                                           // sums of the values as stored (rows in order)
+                    g0 += __uint_as_float(u << 16);
+                    g1 += __uint_as_float(u & 0xffff0000u);
+                }
             }
         }
     }
@@ -505,17 +511,36 @@ __global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restric
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    if (!active) return;
-    const bool live0 = c < p.C, live1 = c + 1 < p.C;
-    const uint32_t* col = dw_tile + (tc * SW) * PS + wl;
-    bf16* yo = y + (((int64_t)n * p.Ho + y0) * p.Wo + (x0 + tc)) * p.CP + c;
-    const int64_t ystride = (int64_t)p.Wo * p.CP;
-    // the activation is a launch constant: branch once, run a body compiled for it
-    switch (p.epi.fast ? p.epi.act : -1) {
-        case 0: dw_strip_rows<K, SH, SW, WPP, TY, 0>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi); break;
-        case EPI_RELU: dw_strip_rows<K, SH, SW, WPP, TY, EPI_RELU>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi); break;
-        case EPI_HSWISH: dw_strip_rows<K, SH, SW, WPP, TY, EPI_HSWISH>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi); break;
-        default: dw_strip_rows<K, SH, SW, WPP, TY, -1>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi); break;
+    const bool gap = p.gap != nullptr;
+    if (!active && !gap) return;
+    float g0 = 0.f, g1 = 0.f;
+    if (active) {
+        const bool live0 = c < p.C, live1 = c + 1 < p.C;
+        const uint32_t* col = dw_tile + (tc * SW) * PS + wl;
+        bf16* yo = y + (((int64_t)n * p.Ho + y0) * p.Wo + (x0 + tc)) * p.CP + c;
+        const int64_t ystride = (int64_t)p.Wo * p.CP;
+        // the activation is a launch constant: branch once, run a body compiled for it
+        switch (p.epi.fast ? p.epi.act : -1) {
+            case 0: dw_strip_rows<K, SH, SW, WPP, TY, 0>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi, gap, g0, g1); break;
+            case EPI_RELU: dw_strip_rows<K, SH, SW, WPP, TY, EPI_RELU>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi, gap, g0, g1); break;
+            case EPI_HSWISH: dw_strip_rows<K, SH, SW, WPP, TY, EPI_HSWISH>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi, gap, g0, g1); break;
+            default: dw_strip_rows<K, SH, SW, WPP, TY, -1>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi, gap, g0, g1); break;
+        }
+    }
+    if (!gap) return;
+    // channel sums for the SE gate that follows: per-thread column sums -> shared memory -> one value per channel of this
+    // tile (columns in fixed order) -> fixed-point atomics (common.cuh)
+    __syncthreads();                              // every thread has finished reading the tile
+    float* red = reinterpret_cast<float*>(dw_tile);          // [TX][2 * WPP]
+    red[tc * (2 * WPP) + 2 * wl] = g0;
+    red[tc * (2 * WPP) + 2 * wl + 1] = g1;
+    __syncthreads();
+    if (threadIdx.x < 2 * WPP) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < TX; ++q) s += red[q * (2 * WPP) + threadIdx.x];
+        const int cc = c0 + (int)threadIdx.x;
+        if (cc < p.C) gap_fix_add(p.gap + (size_t)n * p.CP + cc, s);
     }
 }
 
@@ -667,6 +692,91 @@ __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(const float* __restri
     pdl_start();
     extern __shared__ float sm[];                   // mean[CP] + hidden[mid] + part[blockDim.x]
     se_fc_body(partial, blockIdx.x, chunks, HW, C, CP, mid, w1, w1_ld, b1, w2, w2_ld, b2, alpha, beta, scale, sm);
+}
+
+// ---- SE gate from channel sums that the PRODUCING kernel accumulated (no GAP pass over the tensor at all).
+// The producer (tensor-core conv epilogue, depthwise strip kernel) adds, per image and channel, the sum of the bf16 values
+// it stored as 48.16 fixed point with 64-bit integer atomics: integer addition is associative, so the total does not
+// depend on the order in which tiles finish (deterministic run to run) nor on where the image sits in the batch (every
+// tile belongs to one image and its partial sum is formed in a fixed order).  This kernel turns the sums into means,
+// re-zeroes them for the next launch, and runs the two small matrix-vector products with all loads of a slice issued up
+// front (the gate is pure latency: one block per image).
+constexpr int kSeSumsThreads = 1024;
+__global__ void __launch_bounds__(kSeSumsThreads) se_fc_sums_kernel(unsigned long long* __restrict__ sums, int replicas, int HW, int C, int CP,
+                                                                    int mid, const float* __restrict__ w1, int w1_ld,
+                                                                    const float* __restrict__ b1, const float* __restrict__ w2,
+                                                                    int w2_ld, const float* __restrict__ b2, float alpha, float beta,
+                                                                    float* __restrict__ scale) {
+    pdl_start();
+    extern __shared__ float sm[];                   // mean[CP] + hidden[mid] + part[blockDim.x]
+    float* mean = sm;
+    float* hid = sm + CP;
+    float* part = hid + mid;
+    const int n = blockIdx.x, NT = blockDim.x, tid = threadIdx.x;
+    for (int c = tid; c < CP; c += NT) {
+        long long v = 0;
+        for (int r = 0; r < replicas; ++r) {        // producers spread their atomics over `replicas` copies
+            unsigned long long* q = sums + ((size_t)n * replicas + r) * CP + c;
+            v += (long long)__ldcg(q);
+            *q = 0ull;                              // ready for the next launch of the plan
+        }
+        mean[c] = c < C ? (float)((double)v * (1.0 / (double)kGapFixScale) / (double)HW) : 0.f;
+    }
+    __syncthreads();
+    {   // hidden = relu(W1^T mean + b1): thread (j, slice) takes channels slice, slice + S, ...
+        const int S = max(1, NT / mid);
+        const int j = tid % mid, sl = tid / mid;
+        float s = 0.f;
+        if (sl < S) {
+            int c = sl;
+            for (; c + 3 * S < C; c += 4 * S) {     // four independent loads in flight
+                const float a0 = w1[(int64_t)c * w1_ld + j], a1 = w1[(int64_t)(c + S) * w1_ld + j];
+                const float a2 = w1[(int64_t)(c + 2 * S) * w1_ld + j], a3 = w1[(int64_t)(c + 3 * S) * w1_ld + j];
+                s = fmaf(mean[c], a0, s);
+                s = fmaf(mean[c + S], a1, s);
+                s = fmaf(mean[c + 2 * S], a2, s);
+                s = fmaf(mean[c + 3 * S], a3, s);
+            }
+            for (; c < C; c += S) s = fmaf(mean[c], w1[(int64_t)c * w1_ld + j], s);
+            part[sl * mid + j] = s;
+        }
+        __syncthreads();
+        for (int jj = tid; jj < mid; jj += NT) {
+            float t = 0.f;
+            for (int q = 0; q < S; ++q) t += part[q * mid + jj];
+            hid[jj] = fmaxf(t + b1[jj], 0.f);
+        }
+        __syncthreads();
+    }
+    {   // scale = hsigmoid(W2^T hidden + b2)
+        const int S = max(1, min(mid, NT / CP));
+        const int c = tid % CP, sl = tid / CP;
+        float s = 0.f;
+        if (sl < S) {
+            if (c < C) {
+                int j = sl;
+                for (; j + 3 * S < mid; j += 4 * S) {
+                    const float a0 = w2[(int64_t)j * w2_ld + c], a1 = w2[(int64_t)(j + S) * w2_ld + c];
+                    const float a2 = w2[(int64_t)(j + 2 * S) * w2_ld + c], a3 = w2[(int64_t)(j + 3 * S) * w2_ld + c];
+                    s = fmaf(hid[j], a0, s);
+                    s = fmaf(hid[j + S], a1, s);
+                    s = fmaf(hid[j + 2 * S], a2, s);
+                    s = fmaf(hid[j + 3 * S], a3, s);
+                }
+                for (; j < mid; j += S) s = fmaf(hid[j], w2[(int64_t)j * w2_ld + c], s);
+            }
+            part[sl * CP + c] = s;
+        }
+        __syncthreads();
+        for (int cc = tid; cc < CP; cc += NT) {
+            float t = 0.f;
+            if (cc < C) {
+                for (int q = 0; q < S; ++q) t += part[q * CP + cc];
+                t = fminf(fmaxf(fmaf(t + b2[cc], alpha, beta), 0.f), 1.f);
+            }
+            scale[(int64_t)n * CP + cc] = t;
+        }
+    }
 }
 
 // GAP partial sums and the SE gate in ONE launch: every block reduces its pixel chunk; the block that finishes last for
@@ -828,6 +938,10 @@ struct EltP {
     int b_bcast;          // 1: b is [N,1,1,CP]
     int op;               // 0 add, 1 mul
     Epilogue epi;
+    // lazily applied SE gates (bf16x8 kernel): a' = a * sa[n][c] (+ a when res_a), likewise b; nullptr = plain operand
+    const float* sa = nullptr;
+    const float* sb = nullptr;
+    int res_a = 0, res_b = 0;
 };
 template <typename T>
 __global__ void eltwise_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, const EltP p) {
@@ -857,6 +971,72 @@ __global__ void eltwise_kernel(const T* __restrict__ a, const T* __restrict__ b,
 }
 
 // bf16 fast path of eltwise_kernel: 8 channels (16 bytes) per thread, 32-bit index arithmetic, a plain add runs as four
+// FPN top-down add, y = a' + up(b'): b nearest-upsampled by powers of two, a' / b' optionally carrying a pending SE gate
+// (x * s[n][c], + x when res).  One block row per image row: grid (row chunks, H, N), so the only division left per thread
+// is the split of its in-row index into (pixel, 16-byte chunk); gates are applied in fp32, one rounding at the end.
+struct FpnAddP {
+    int W, Hb, Wb, cg, sh, sw;     // cg = CP / 8; b is [N][Hb][Wb][CP], sh / sw = log2 of the upsample factors
+    const float* sa;
+    const float* sb;
+    int res_a, res_b;
+};
+__global__ void __launch_bounds__(256) fpn_add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
+                                                           bf16* __restrict__ y, const FpnAddP p) {
+    pdl_start();
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (uint32_t)p.W * (uint32_t)p.cg) return;
+    const uint32_t xw = j / (uint32_t)p.cg, g = j - xw * (uint32_t)p.cg;
+    const uint32_t yh = blockIdx.y, n = blockIdx.z, H = gridDim.y;
+    const size_t ia = ((size_t)(n * H + yh) * p.W) * p.cg + j;
+    const size_t ib = ((size_t)(n * p.Hb + (yh >> p.sh)) * p.Wb + (xw >> p.sw)) * p.cg + g;
+    const uint4 va = reinterpret_cast<const uint4*>(a)[ia];
+    const uint4 vb = reinterpret_cast<const uint4*>(b)[ib];
+    uint4 o;
+    if (!p.sa && !p.sb) {
+        const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&va);
+        const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&vb);
+        __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) po[q] = __hadd2(pa[q], pb[q]);
+    } else {
+        const int CP = p.cg * 8;
+        float ga[8], gb[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { ga[q] = 0.f; gb[q] = 0.f; }
+        if (p.sa) {
+            const float4 s0 = *reinterpret_cast<const float4*>(p.sa + (size_t)n * CP + g * 8);
+            const float4 s1 = *reinterpret_cast<const float4*>(p.sa + (size_t)n * CP + g * 8 + 4);
+            ga[0] = s0.x; ga[1] = s0.y; ga[2] = s0.z; ga[3] = s0.w; ga[4] = s1.x; ga[5] = s1.y; ga[6] = s1.z; ga[7] = s1.w;
+        }
+        if (p.sb) {
+            const float4 s0 = *reinterpret_cast<const float4*>(p.sb + (size_t)n * CP + g * 8);
+            const float4 s1 = *reinterpret_cast<const float4*>(p.sb + (size_t)n * CP + g * 8 + 4);
+            gb[0] = s0.x; gb[1] = s0.y; gb[2] = s0.z; gb[3] = s0.w; gb[4] = s1.x; gb[5] = s1.y; gb[6] = s1.z; gb[7] = s1.w;
+        }
+        const uint32_t* ua = &va.x;
+        const uint32_t* ub = &vb.x;
+        uint32_t* uo = &o.x;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float a0 = __uint_as_float(ua[q] << 16), a1 = __uint_as_float(ua[q] & 0xffff0000u);
+            float b0 = __uint_as_float(ub[q] << 16), b1 = __uint_as_float(ub[q] & 0xffff0000u);
+            if (p.sa) {
+                const float t0 = a0 * ga[2 * q], t1 = a1 * ga[2 * q + 1];
+                a0 = p.res_a ? a0 + t0 : t0;
+                a1 = p.res_a ? a1 + t1 : t1;
+            }
+            if (p.sb) {
+                const float t0 = b0 * gb[2 * q], t1 = b1 * gb[2 * q + 1];
+                b0 = p.res_b ? b0 + t0 : t0;
+                b1 = p.res_b ? b1 + t1 : t1;
+            }
+            __nv_bfloat162 r = __floats2bfloat162_rn(a0 + b0, a1 + b1);
+            uo[q] = *reinterpret_cast<uint32_t*>(&r);
+        }
+    }
+    reinterpret_cast<uint4*>(y)[ia] = o;
+}
+
 // packed bf16x2 adds (fp32 inside, one rounding — identical to add-in-fp32-then-round).  Needs CP % 8 == 0, no
 // channel broadcast, fewer than 2^31 16-byte chunks.
 __global__ void __launch_bounds__(256) eltwise_bf16x8_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
@@ -865,7 +1045,9 @@ __global__ void __launch_bounds__(256) eltwise_bf16x8_kernel(const bf16* __restr
     const uint32_t cg = (uint32_t)p.CP >> 3;
     const uint32_t Hb = p.H / p.fh, Wb = p.W / p.fw;
     const bool same = p.fh == 1 && p.fw == 1;
-    const bool plain_add = p.op == 0 && p.epi.n == 0 && p.C == p.CP;
+    const bool gated = p.sa != nullptr || p.sb != nullptr;
+    const bool plain_add = p.op == 0 && p.epi.n == 0 && p.C == p.CP && !gated;
+    const uint32_t per_img = (uint32_t)p.H * (uint32_t)p.W * cg;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += gridDim.x * blockDim.x) {
         uint32_t bi = i;
         uint32_t g = 0;
@@ -883,7 +1065,51 @@ __global__ void __launch_bounds__(256) eltwise_bf16x8_kernel(const bf16* __restr
         const uint4 va = reinterpret_cast<const uint4*>(a)[i];
         const uint4 vb = reinterpret_cast<const uint4*>(b)[bi];
         uint4 o;
-        if (plain_add) {
+        if (gated) {
+            // SE gates applied on the fly: the gated tensors themselves never exist in memory
+            const uint32_t n = i / per_img;
+            float ga[8], gb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ga[j] = 1.f; gb[j] = 1.f; }
+            if (p.sa) {
+                const float4 s0 = *reinterpret_cast<const float4*>(p.sa + (size_t)n * p.CP + g * 8);
+                const float4 s1 = *reinterpret_cast<const float4*>(p.sa + (size_t)n * p.CP + g * 8 + 4);
+                const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ga[j] = sv[j];
+            }
+            if (p.sb) {
+                const float4 s0 = *reinterpret_cast<const float4*>(p.sb + (size_t)n * p.CP + g * 8);
+                const float4 s1 = *reinterpret_cast<const float4*>(p.sb + (size_t)n * p.CP + g * 8 + 4);
+                const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) gb[j] = sv[j];
+            }
+            const uint32_t* ua = &va.x;
+            const uint32_t* ub = &vb.x;
+            uint32_t* uo = &o.x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float a0 = __uint_as_float(ua[j] << 16), a1 = __uint_as_float(ua[j] & 0xffff0000u);
+                float b0 = __uint_as_float(ub[j] << 16), b1 = __uint_as_float(ub[j] & 0xffff0000u);
+                if (p.sa) {
+                    const float t0 = a0 * ga[2 * j], t1 = a1 * ga[2 * j + 1];
+                    a0 = p.res_a ? a0 + t0 : t0;
+                    a1 = p.res_a ? a1 + t1 : t1;
+                }
+                if (p.sb) {
+                    const float t0 = b0 * gb[2 * j], t1 = b1 * gb[2 * j + 1];
+                    b0 = p.res_b ? b0 + t0 : t0;
+                    b1 = p.res_b ? b1 + t1 : t1;
+                }
+                float t0 = p.op == 0 ? a0 + b0 : a0 * b0, t1 = p.op == 0 ? a1 + b1 : a1 * b1;
+                int c = (int)g * 8 + 2 * j;
+                t0 = c < p.C ? epi_apply(t0, p.epi) : 0.f;
+                t1 = c + 1 < p.C ? epi_apply(t1, p.epi) : 0.f;
+                __nv_bfloat162 r = __floats2bfloat162_rn(t0, t1);
+                uo[j] = *reinterpret_cast<uint32_t*>(&r);
+            }
+        } else if (plain_add) {
             const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&va);
             const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&vb);
             __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
@@ -951,6 +1177,56 @@ __global__ void concat_slice_kernel(const T* __restrict__ src, T* __restrict__ d
         dst[(((int64_t)n * H + yh) * W + xw) * CdP + c_off + c] =
             src[(((int64_t)n * Hs + yh / fh) * Ws + xw / fw) * CsP + c];
     }
+}
+
+// All inputs of a channel concat in ONE launch (bf16, every input's channel count a multiple of 8): one thread per
+// (pixel, 16-byte chunk of the destination row), so a warp writes whole destination lines instead of every input writing
+// its own slice of each row in a separate pass.  Inputs may be nearest-upsampled (fh, fw) and carry a lazily applied SE
+// gate (scale[n][c], + x when res); destination pad chunks beyond the last input are zeroed here as well.
+constexpr int kCatMaxIn = 8;
+constexpr int kCatMaxChunks = 128;               // destination row <= 1024 channels
+struct CatP {
+    int N, H, W, CdP, nin;
+    const bf16* src[kCatMaxIn];
+    const float* scale[kCatMaxIn];
+    int fh[kCatMaxIn], fw[kCatMaxIn];            // log2 of the nearest-upsample factors (powers of two only)
+    int CsP[kCatMaxIn], g0[kCatMaxIn], res[kCatMaxIn];   // g0: first destination chunk of the input
+    unsigned char kmap[kCatMaxChunks];           // destination chunk -> input index (255: pad chunk, written as zeros)
+};
+__global__ void __launch_bounds__(256) concat_multi_bf16_kernel(bf16* __restrict__ dst, const CatP p) {
+    pdl_start();
+    // grid (row chunks, H, N): one division per thread (in-row index -> pixel, chunk); upsampling by shifts.  The input a
+    // chunk comes from is looked up (kmap) and its parameters are read with a run-time index, so the lanes of a warp —
+    // which span several inputs — all execute the same instruction stream instead of one branch per input.
+    const uint32_t cg = (uint32_t)p.CdP >> 3;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (uint32_t)p.W * cg) return;
+    const uint32_t xw = j / cg, g = j - xw * cg;
+    const uint32_t yh = blockIdx.y, n = blockIdx.z;
+    const int k = p.kmap[g];
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (k != 255) {
+        const int fh = p.fh[k], fw = p.fw[k], csp = p.CsP[k];
+        const uint32_t Hs = (uint32_t)p.H >> fh, Ws = (uint32_t)p.W >> fw;
+        const uint32_t c = (g - (uint32_t)p.g0[k]) * 8u;
+        v = *reinterpret_cast<const uint4*>(p.src[k] + ((size_t)(n * Hs + (yh >> fh)) * Ws + (xw >> fw)) * csp + c);
+        const float* sc = p.scale[k];
+        if (sc) {
+            const float4 s0 = *reinterpret_cast<const float4*>(sc + (size_t)n * csp + c);
+            const float4 s1 = *reinterpret_cast<const float4*>(sc + (size_t)n * csp + c + 4);
+            const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float keep = p.res[k] ? 1.f : 0.f;      // x * s + x  ==  x * s + keep * x  (same two roundings)
+            uint32_t* u = &v.x;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float a0 = __uint_as_float(u[q] << 16), a1 = __uint_as_float(u[q] & 0xffff0000u);
+                const float t0 = a0 * sv[2 * q] + keep * a0, t1 = a1 * sv[2 * q + 1] + keep * a1;
+                __nv_bfloat162 rr = __floats2bfloat162_rn(t0, t1);
+                u[q] = *reinterpret_cast<uint32_t*>(&rr);
+            }
+        }
+    }
+    reinterpret_cast<uint4*>(dst)[((size_t)(n * p.H + yh) * p.W) * cg + j] = v;
 }
 
 // 16-byte vector version (channel counts and offset multiples of 16 / sizeof(T))

@@ -41,6 +41,12 @@ struct Params {
     int ws_bn, ws_stages;        // weight-stationary kernel: output-channel tile width and activation ring depth
     int ws_halo, ws_stage_bytes; // halo mode (k x k): bytes per ring stage; kh for the halo height
     int kh;
+    // SE producer: per (image, channel) sums of the stored outputs, accumulated by the epilogue (common.cuh gap_fix_add).
+    // gap_rows = GEMM rows per image (mode 0 is then tiled per image so that no tile straddles two images),
+    // gap_mod = channels per pixel (a pixel-packed GEMM row carries several pixels: column % gap_mod = channel)
+    unsigned long long* gap;
+    int gap_rows, gap_mod;
+    unsigned long long* dbg;     // tools/ubench only: per-CTA cycle counters of the MMA / TMA threads (nullptr in the engine)
     int ct2;
     const float* ct2_w;
     float* ct2_out;
@@ -458,7 +464,11 @@ constexpr int WS_MAX_ACC = 8;
 constexpr int WS_A_BYTES = BM * BK * 2;
 constexpr size_t WS_SMEM_LIMIT = 225 * 1024;
 
-inline size_t ws_tail_bytes() { return 1024 /*alignment*/ + 512 /*barriers*/ + (4 * CT2_MAX_C + 4) * 4 + 64 + 256 * 4 /*bias slice*/; }
+constexpr int kGapReplicas = 16;          // channel-sum buffers are replicated (CTA % 16) so that the atomics spread over lines
+inline size_t ws_tail_bytes() {
+    return 1024 /*alignment*/ + 512 /*barriers*/ + (4 * CT2_MAX_C + 4) * 4 + 64 + 256 * 4 /*bias slice*/ +
+           (size_t)kWsEpiWarps * 128 * 8 /*per-warp channel-sum accumulators*/;
+}
 // epilogue staging: 16 warps x 32 rows x (their column part in bf16 + 16 bytes of padding against bank conflicts)
 inline int ws_parts(int bn) { (void)bn; return kWsEpiWarps / 4; }             // column parts (each a multiple of 16 columns)
 inline size_t ws_stage_row_bytes(int bn) { return (size_t)(bn / ws_parts(bn)) * 2 + 16; }
@@ -607,7 +617,7 @@ __device__ __forceinline__ uint32_t epi_pair(uint32_t acc_lo, uint32_t acc_hi, f
 template <int ACT>
 __device__ __forceinline__ void epilogue_cols_staged(uint32_t trow, const float* __restrict__ bias_s, bf16* __restrict__ y,
                                                      uint32_t off8, bool valid, int n0, int c_begin, int c_end, const Params& p,
-                                                     uint8_t* stage, int row_bytes, int lane) {
+                                                     uint8_t* stage, int row_bytes, int lane, unsigned long long* gacc = nullptr) {
     const int c_lim = min(c_end, p.CoutP - n0);              // columns that exist in the output tensor
     uint8_t* my = stage + (size_t)lane * row_bytes;
     const bool post = p.epi.a1 != 1.f || p.epi.b1 != 0.f;
@@ -642,6 +652,53 @@ __device__ __forceinline__ void epilogue_cols_staged(uint32_t trow, const float*
         }
     }
     __syncwarp();
+    if (gacc) {
+        // Column sums of the staged (bf16-rounded) values over this warp's valid rows.  All 32 lanes work: a lane owns one
+        // pair of columns and, when the part has fewer than 32 pairs, one group of rows (partial sums then meet through
+        // xor shuffles — a fixed tree, so the result is reproducible).  Loads are unconditional (rows that do not exist
+        // are masked to zero), fully unrolled, conflict-free (consecutive lanes read consecutive words of a row).  The
+        // tile's sums go as fixed point into this warp's own accumulators in shared memory (integer adds are associative:
+        // the total does not depend on which tiles a CTA happens to process); they are flushed per image.
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        const int npairs = (c_lim - c_begin) >> 1;
+        int lgp = 0;
+        while ((1 << lgp) < npairs && lgp < 5) ++lgp;         // lanes per row group = min(32, next pow2 >= npairs)
+        const int lanes_pp = 1 << lgp, groups = 32 >> lgp, rows_pg = 32 / groups;
+        const int rg = lane >> lgp, pl = lane & (lanes_pp - 1);
+        const uint32_t sbase = smem_u32(stage);
+        const uint32_t gbase = smem_u32(gacc);
+        for (int p0 = 0; p0 < npairs; p0 += lanes_pp) {
+            const int cp = p0 + pl;
+            const bool live = cp < npairs;
+            float s0 = 0.f, s1 = 0.f;
+            const uint32_t a0 = sbase + (uint32_t)(rg * rows_pg) * (uint32_t)row_bytes + (uint32_t)(live ? cp : 0) * 4u;
+            const uint32_t vm = vmask >> (rg * rows_pg);
+#pragma unroll 8
+            for (int r = 0; r < rows_pg; ++r) {
+                uint32_t u;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(a0 + (uint32_t)r * (uint32_t)row_bytes));
+                u &= 0u - ((vm >> r) & 1u);
+                s0 += __uint_as_float(u << 16);
+                s1 += __uint_as_float(u & 0xffff0000u);
+            }
+            for (int d = lanes_pp; d < 32; d <<= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+            }
+            if (live && rg == 0) {
+                // 48.16 fixed point from two 32-bit conversions: integer part + fraction (s - rint(s) is exact in fp32)
+                const float h0 = rintf(s0), h1 = rintf(s1);
+                const long long v0 = (long long)__float2int_rn(h0) * 65536ll + (long long)__float2int_rn((s0 - h0) * kGapFixScale);
+                const long long v1 = (long long)__float2int_rn(h1) * 65536ll + (long long)__float2int_rn((s1 - h1) * kGapFixScale);
+                unsigned long long c0, c1;
+                const uint32_t ga = gbase + (uint32_t)cp * 16u;
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(c0), "=l"(c1) : "r"(ga));
+                c0 += (unsigned long long)v0;
+                c1 += (unsigned long long)v1;
+                asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(ga), "l"(c0), "l"(c1) : "memory");
+            }
+        }
+    }
     const int chunks = (c_lim - c_begin) >> 3;               // 16-byte chunks per row (CoutP % 8 == 0)
     if (chunks > 0) {
         int lg = 0;
@@ -768,6 +825,28 @@ __device__ __forceinline__ void epilogue_ct2_tap_fixed(uint32_t trow, const floa
     __syncwarp();
 }
 
+// One 64-channel chunk of a 3x3 halo tile: 9 taps x KS K-slices of 16 channels, issued with RUNNING descriptors (every
+// step is one 64-bit add on the descriptor that the previous MMA used) — the issuing thread is the bottleneck of the
+// small-N layers (measured 65 cycles per MMA with descriptors rebuilt from a base each time against 40 for the tensor
+// pipe), so the loop body must stay at "add, add, mma".  A: the taps of one halo row are 8 units (128 bytes = 64
+// channels) apart = exactly 4 K-slices, a row step is (TW + 2) * 8 units.  B: the chunk's taps lie b_tap units apart.
+template <int KS>
+__device__ __forceinline__ void issue_halo3x3(uint32_t tmem_d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc_first,
+                                              uint64_t b_tap) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+        for (int k2 = 0; k2 < KS; ++k2) {
+            umma_bf16(tmem_d, ad, bd, idesc, (tap | k2) ? 1u : acc_first);
+            if (k2 + 1 < KS) { ad += 2; bd += 2; }
+        }
+        if (tap < 8) {
+            ad += (tap % 3 == 2) ? (uint64_t)((WS_HALO_TW + 2) * 8 - 16 - 2 * (KS - 1)) : (uint64_t)(8 - 2 * (KS - 1));
+            bd += b_tap - (uint64_t)(2 * (KS - 1));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 const float* __restrict__ bias, bf16* __restrict__ y,
@@ -797,6 +876,7 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
     uint32_t* tmem_slot_ptr = (uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* w2q = (float*)(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));
     float* bias_s = w2q + (4 * CT2_MAX_C + 4);              // this CTA's bias slice [BN] (its output-channel tile is fixed)
+    unsigned long long* gacc_all = reinterpret_cast<unsigned long long*>(bias_s + 256);   // [epilogue warp][128 columns]
     {
         const int nt0 = (blockIdx.x % ((p.CoutP + BN - 1) / BN)) * BN;
         for (int i = threadIdx.x; i < BN; i += kWsThreads) bias_s[i] = bias[nt0 + i];
@@ -807,7 +887,8 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
     }
 
     const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
-    const int m_tiles = p.mode == 0 ? (p.M + BM - 1) / BM : p.tiles_x * p.tiles_y * p.N;
+    const int tpi = (p.gap_rows + BM - 1) / BM;            // mode 0 with channel sums: tiles per image
+    const int m_tiles = p.mode == 0 ? (p.gap ? p.N * tpi : (p.M + BM - 1) / BM) : p.tiles_x * p.tiles_y * p.N;
     const int n_tiles = (p.CoutP + BN - 1) / BN;
     const int my_nt = blockIdx.x % n_tiles;
     const int n0 = my_nt * BN;
@@ -841,6 +922,12 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
     auto tile_origin = [&](int mt, int& m0, int& img, int& y0, int& x0) {
         m0 = mt * BM;
         img = 0; y0 = 0; x0 = 0;
+        if (p.mode == 0 && p.gap) {                         // y0 = rows of this tile that belong to the image
+            img = mt / tpi;
+            const int tl = mt - img * tpi;
+            m0 = img * p.gap_rows + tl * BM;
+            y0 = p.gap_rows - tl * BM;
+        }
         if (p.mode == 1) {
             int tx = mt % p.tiles_x;
             int r = mt / p.tiles_x;
@@ -855,7 +942,12 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
         // ---------------------------------------------------------------- TMA producer
         if (elect_one_sync()) {
             mbar_expect_tx(b_bar, (uint32_t)nkb * B_KB_BYTES);
-            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(b_base + kb * B_KB_BYTES, &map_b, b_bar, kb * BK, n0);
+            // slab slot of K block kb (= tap * kchunks + chunk in the packed weights): halo mode walks chunk-major, so a
+            // chunk's taps are made contiguous there
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int slot = p.ws_halo ? (kb % p.kchunks) * p.taps + kb / p.kchunks : kb;
+                tma_load_2d(b_base + slot * B_KB_BYTES, &map_b, b_bar, kb * BK, n0);
+            }
             uint32_t it = 0;
             for (int mt = m_first; mt < m_tiles; mt += m_step) {
                 int m0, img, y0, x0;
@@ -865,7 +957,9 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
                     for (int ch = 0; ch < p.kchunks; ++ch, ++it) {
                         int s = it % STG;
                         uint32_t ph = (it / STG) & 1;
+                        const long long c3 = p.dbg ? clock64() : 0;
                         mbar_wait(empty_bar(s), ph ^ 1);
+                        if (p.dbg) p.dbg[(size_t)blockIdx.x * 8 + 6] += (unsigned long long)(clock64() - c3);   // producer: waiting for a free stage
                         mbar_expect_tx(full_bar(s), halo_bytes);
                         tma_load_4d(a_base + s * ASB, &map_a, full_bar(s), ch * BK, x0 - p.pad_l, y0 - p.pad_t, img);
                     }
@@ -891,14 +985,17 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
         // ---------------------------------------------------------------- MMA issuer
         if (elect_one_sync()) {
             const uint32_t idesc = make_idesc(BN);
+            long long dbg_acc = 0, dbg_full = 0;
+            const long long dbg_t0 = p.dbg ? clock64() : 0;
             mbar_wait(b_bar, 0);
+            const long long dbg_t1 = p.dbg ? clock64() : 0;
             uint32_t it = 0, t = 0;
-            if (p.ws_halo && p.taps == 9 && p.kw == 3 && STG >= 2 * p.kchunks + 1 && NACC >= 2) {
+            if (p.ws_halo == 2 && p.taps == 9 && p.kw == 3 && STG >= 2 * p.kchunks + 1 && NACC >= 2) {
                 // 3x3 halo mode, TWO tiles in flight: the 72 small MMAs of a tile all accumulate into the same TMEM
                 // columns, so back-to-back they run at the pipeline latency, not its throughput (measured ~100 cycles per
                 // N = 32 MMA).  Alternating between two tiles' accumulators gives the tensor pipe independent work.
                 const uint32_t hw = (uint32_t)(p.TW + p.kw - 1);
-                const uint64_t bstep = (uint64_t)((uint32_t)(p.kchunks * B_KB_BYTES) >> 4);
+                const uint64_t bstep = (uint64_t)((uint32_t)B_KB_BYTES >> 4);
                 for (int mt = m_first; mt < m_tiles; mt += 2 * m_step, t += 2) {
                     const bool two = mt + m_step < m_tiles;
                     const int acc0 = t % NACC, acc1 = (t + 1) % NACC;
@@ -914,7 +1011,7 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint64_t a0 = make_smem_desc_sbo(a_base + s0 * ASB, hw * 128u);
                         const uint64_t a1 = make_smem_desc_sbo(a_base + s1 * ASB, hw * 128u);
-                        const uint64_t b0 = make_smem_desc(b_base + ch * B_KB_BYTES);
+                        const uint64_t b0 = make_smem_desc(b_base + ch * 9 * B_KB_BYTES);
                         const int ks = min(BK / 16, (p.cinp - ch * BK + 15) >> 4);
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
@@ -938,7 +1035,9 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
             for (int mt = m_first; mt < m_tiles; mt += m_step, ++t) {
                 int acc = t % NACC;
                 uint32_t aph = (t / NACC) & 1;
+                long long c0 = p.dbg ? clock64() : 0;
                 mbar_wait(tmem_empty_bar(acc), aph ^ 1);
+                if (p.dbg) dbg_acc += clock64() - c0;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
                 if (p.ws_halo) {
@@ -946,30 +1045,29 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
                     for (int ch = 0; ch < p.kchunks; ++ch, ++it) {
                         int s = it % STG;
                         uint32_t ph = (it / STG) & 1;
+                        long long c1 = p.dbg ? clock64() : 0;
                         mbar_wait(full_bar(s), ph);
+                        if (p.dbg) dbg_full += clock64() - c1;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (p.taps == 9 && p.kw == 3) {
                             // 3x3: descriptor arithmetic hoisted — one base descriptor per stage / chunk, per-tap offsets are
                             // compile-time (A: (ky * 10 + kx) halo rows of 128 bytes) or one multiply (B); the single
                             // issuing thread would otherwise spend more time building descriptors than the MMAs take
                             const uint64_t a0 = make_smem_desc_sbo(a_base + s * ASB, hw * 128u);
-                            const uint64_t b0 = make_smem_desc(b_base + ch * B_KB_BYTES);
-                            const uint64_t bstep = (uint64_t)((uint32_t)(p.kchunks * B_KB_BYTES) >> 4);
+                            const uint64_t b0 = make_smem_desc(b_base + ch * 9 * B_KB_BYTES);
+                            const uint64_t b_tap = (uint64_t)((uint32_t)B_KB_BYTES >> 4);
                             const int ks = min(BK / 16, (p.cinp - ch * BK + 15) >> 4);
-#pragma unroll
-                            for (int tap = 0; tap < 9; ++tap) {
-                                const uint64_t ad = a0 + (uint64_t)(((tap / 3) * (WS_HALO_TW + 2) + (tap % 3)) * 8);
-                                const uint64_t bd = b0 + bstep * (uint64_t)tap;
-#pragma unroll
-                                for (int k2 = 0; k2 < BK / 16; ++k2)
-                                    if (k2 < ks) umma_bf16(tmem_d, ad + (uint64_t)(2 * k2), bd + (uint64_t)(2 * k2), idesc, (ch | tap | k2) != 0);
-                            }
+                            const uint32_t accf = ch != 0 ? 1u : 0u;
+                            if (ks == 4) issue_halo3x3<4>(tmem_d, a0, b0, idesc, accf, b_tap);
+                            else if (ks == 2) issue_halo3x3<2>(tmem_d, a0, b0, idesc, accf, b_tap);
+                            else if (ks == 3) issue_halo3x3<3>(tmem_d, a0, b0, idesc, accf, b_tap);
+                            else issue_halo3x3<1>(tmem_d, a0, b0, idesc, accf, b_tap);
                         } else
                         for (int tap = 0; tap < p.taps; ++tap) {
                             int ky = tap / p.kw, kx = tap - ky * p.kw;
                             // rows of the A operand = pixels (ty + ky, tx + kx) of the halo tile: 8-pixel groups, one halo row apart
                             uint64_t adesc = make_smem_desc_sbo(a_base + s * ASB + ((uint32_t)ky * hw + (uint32_t)kx) * 128u, hw * 128u);
-                            uint64_t bdesc = make_smem_desc(b_base + (tap * p.kchunks + ch) * B_KB_BYTES);
+                            uint64_t bdesc = make_smem_desc(b_base + (ch * p.taps + tap) * B_KB_BYTES);
                             const int ks = min(BK / 16, (p.cinp - ch * BK + 15) >> 4);
 #pragma unroll
                             for (int k2 = 0; k2 < BK / 16; ++k2)
@@ -981,7 +1079,9 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     int s = it % STG;
                     uint32_t ph = (it / STG) & 1;
+                    long long c1 = p.dbg ? clock64() : 0;
                     mbar_wait(full_bar(s), ph);
+                    if (p.dbg) dbg_full += clock64() - c1;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     uint64_t adesc = make_smem_desc(a_base + s * WS_A_BYTES);
                     uint64_t bdesc = make_smem_desc(b_base + kb * B_KB_BYTES);
@@ -993,6 +1093,13 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
                 }
                 umma_commit(tmem_full_bar(acc));
             }
+            if (p.dbg) {
+                unsigned long long* d = p.dbg + (size_t)blockIdx.x * 8;
+                d[0] = (unsigned long long)(clock64() - dbg_t0);   // MMA thread: total
+                d[1] = (unsigned long long)(dbg_t1 - dbg_t0);      //   waiting for the weight slab
+                d[2] = (unsigned long long)dbg_acc;                //   waiting for a free accumulator
+                d[3] = (unsigned long long)dbg_full;               //   waiting for activation stages
+            }
         }
         __syncwarp();
     } else {
@@ -1003,18 +1110,44 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
         const int c_begin = part * (BN / parts), c_end = part < parts ? c_begin + BN / parts : c_begin;
         const int act_code = p.epi.fast ? p.epi.act : -1;
         uint32_t t = 0;
+        long long dbg_wait = 0;
+        const long long dbg_e0 = p.dbg ? clock64() : 0;
+        // channel sums (SE producer): this warp's accumulators for its column part, flushed whenever the image changes
+        unsigned long long* gacc = p.gap ? gacc_all + (size_t)(warp - 2) * 128 : nullptr;
+        int gap_cur = -1;
+        auto gap_flush = [&](int img_done) {
+            __syncwarp();
+            unsigned long long* dst = p.gap + ((size_t)img_done * kGapReplicas + (blockIdx.x % kGapReplicas)) * p.gap_mod;
+            for (int cl = lane; cl < c_end - c_begin; cl += 32) {
+                const unsigned long long v = gacc[cl];
+                const int col = n0 + c_begin + cl;
+                if (v != 0ull && col < p.CoutP) atomicAdd(dst + col % p.gap_mod, v);
+                gacc[cl] = 0ull;
+            }
+            __syncwarp();
+        };
+        if (gacc) {
+            for (int cl = lane; cl < 128; cl += 32) gacc[cl] = 0ull;
+            __syncwarp();
+        }
         for (int mt = m_first; mt < m_tiles; mt += m_step, ++t) {
             int m0, img, y0, x0;
             tile_origin(mt, m0, img, y0, x0);
+            if (gacc && img != gap_cur) {
+                if (gap_cur >= 0) gap_flush(gap_cur);
+                gap_cur = img;
+            }
             int acc = t % NACC;
             uint32_t aph = (t / NACC) & 1;
+            const long long c2 = p.dbg ? clock64() : 0;
             mbar_wait(tmem_full_bar(acc), aph);
+            if (p.dbg) dbg_wait += clock64() - c2;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             bool valid;
             int64_t off;
             if (p.mode == 0) {
                 int m = m0 + row;
-                valid = m < p.M;
+                valid = p.gap ? row < y0 : m < p.M;
                 off = (int64_t)m * p.CoutP;
             } else {
                 int ty = row / p.TW, tx = row - ty * p.TW;
@@ -1058,7 +1191,7 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
                     }
                 } else {
                     uint8_t* stg = smem_raw + (stage_base - smem_u32(smem_raw)) + (size_t)(warp - 2) * 32 * stage_row;
-#define B200_EPI(A) epilogue_cols_staged<A>(trow, bias_s, y, (uint32_t)(off >> 3), valid, n0, c_begin, c_end, p, stg, stage_row, lane)
+#define B200_EPI(A) epilogue_cols_staged<A>(trow, bias_s, y, (uint32_t)(off >> 3), valid, n0, c_begin, c_end, p, stg, stage_row, lane, gacc)
                     switch (act_code) {
                         case 0: B200_EPI(0); break;
                         case EPI_RELU: B200_EPI(EPI_RELU); break;
@@ -1074,6 +1207,11 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        }
+        if (gacc && gap_cur >= 0) gap_flush(gap_cur);
+        if (p.dbg && warp == 2 && lane == 0) {
+            p.dbg[(size_t)blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - dbg_e0);   // epilogue warp 2: total
+            p.dbg[(size_t)blockIdx.x * 8 + 5] = (unsigned long long)dbg_wait;               //   waiting for accumulators
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
