@@ -52,15 +52,19 @@ B200_HD int key_i(uint64_t k) { return (int)(k & 0xFFFFF); }
 // Follows one border starting at (sx, sy) exactly like OpenCV's icvFetchContour with
 // CV_CHAIN_APPROX_SIMPLE; writes keys[idx] = pack(x, y, idx) when `keys` is non-null.
 // Returns the number of contour points (may exceed cap; only the first cap are stored).
+// 8-neighbourhood step of direction s (0 = east, counter-clockwise on the image with y down: {1,1,0,-1,-1,-1,0,1} /
+// {0,-1,-1,-1,0,1,1,1}) as arithmetic on packed 2-bit fields: a run-time indexed table would live in LOCAL memory on the
+// device, i.e. several dependent L1 round trips in every step of the (inherently serial) border following.
+B200_HD int dir_dx(int s) { return (int)((0x901Au >> (2 * (s & 7))) & 3u) - 1; }
+B200_HD int dir_dy(int s) { return (int)((0xA901u >> (2 * (s & 7))) & 3u) - 1; }
+
 B200_HDN int trace_contour(const Bitmap& img, int sx, int sy, bool is_hole, uint64_t* keys, int cap) {
-    const int dx8[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-    const int dy8[8] = {0, -1, -1, -1, 0, 1, 1, 1};
     int s_end = is_hole ? 0 : 4, s = s_end;
     int i1x, i1y;
     do {
         s = (s - 1) & 7;
-        i1x = sx + dx8[s];
-        i1y = sy + dy8[s];
+        i1x = sx + dir_dx(s);
+        i1y = sy + dir_dy(s);
     } while (img.at(i1x, i1y) == 0 && s != s_end);
     int n = 0;
     if (s == s_end) {               // single pixel domain
@@ -74,8 +78,8 @@ B200_HDN int trace_contour(const Bitmap& img, int sx, int sy, bool is_hole, uint
         s_end = s;
         while (s < 15) {
             ++s;
-            i4x = i3x + dx8[s & 7];
-            i4y = i3y + dy8[s & 7];
+            i4x = i3x + dir_dx(s & 7);
+            i4y = i3y + dir_dy(s & 7);
             if (img.at(i4x, i4y) != 0) break;
         }
         s &= 7;
@@ -84,8 +88,8 @@ B200_HDN int trace_contour(const Bitmap& img, int sx, int sy, bool is_hole, uint
             ++n;
             prev_s = s;
         }
-        ptx += dx8[s];
-        pty += dy8[s];
+        ptx += dir_dx(s);
+        pty += dir_dy(s);
         if (i4x == sx && i4y == sy && i3x == i1x && i3y == i1y) break;
         i3x = i4x;
         i3y = i4y;

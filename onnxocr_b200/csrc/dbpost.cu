@@ -232,17 +232,13 @@ constexpr int kWarpsPerBlock = 4;
 constexpr size_t kWarpSmem = (size_t)kWarpCap * 8 + (size_t)(kWarpCap + 2) * 4 + (size_t)kWarpCap * 4 + (size_t)kWarpHull * 20;
 
 __device__ __forceinline__ unsigned neighbour_mask(const Bitmap& img, int x, int y, int lane) {
-    const int dx8[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-    const int dy8[8] = {0, -1, -1, -1, 0, 1, 1, 1};
     int v = 0;
-    if (lane < 8) v = img.at(x + dx8[lane], y + dy8[lane]);
+    if (lane < 8) v = img.at(x + dir_dx(lane), y + dir_dy(lane));
     return __ballot_sync(0xffffffffu, v != 0) & 0xffu;
 }
 
 // Warp-cooperative twin of geom::trace_contour (identical point sequence); all lanes return the point count.
 __device__ int warp_trace_contour(const Bitmap& img, int sx, int sy, bool is_hole, uint64_t* keys, int cap, int lane) {
-    const int dx8[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-    const int dy8[8] = {0, -1, -1, -1, 0, 1, 1, 1};
     int s_end = is_hole ? 0 : 4, s = s_end;
     unsigned mask = neighbour_mask(img, sx, sy, lane);
     do {
@@ -253,7 +249,7 @@ __device__ int warp_trace_contour(const Bitmap& img, int sx, int sy, bool is_hol
         if (lane == 0 && cap > 0) keys[0] = pack_key(sx, sy, 0);
         return 1;
     }
-    const int i1x = sx + dx8[s], i1y = sy + dy8[s];
+    const int i1x = sx + dir_dx(s), i1y = sy + dir_dy(s);
     int i3x = sx, i3y = sy;
     int prev_s = s ^ 4;
     int ptx = sx, pty = sy;
@@ -262,17 +258,39 @@ __device__ int warp_trace_contour(const Bitmap& img, int sx, int sy, bool is_hol
         unsigned rot = ((mask | (mask << 8)) >> ((s + 1) & 7)) & 0xffu;
         int step = __ffs(rot) - 1;
         s = (s + 1 + step) & 7;
-        int i4x = i3x + dx8[s], i4y = i3y + dy8[s];
-        if (s != prev_s) {
+        int i4x = i3x + dir_dx(s), i4y = i3y + dir_dy(s);
+        const bool turned = s != prev_s;
+        if (turned) {
             if (lane == 0 && n < cap) keys[n] = pack_key(ptx, pty, n);
             ++n;
             prev_s = s;
         }
-        ptx += dx8[s];
-        pty += dy8[s];
+        ptx += dir_dx(s);
+        pty += dir_dy(s);
         if (i4x == sx && i4y == sy && i3x == i1x && i3y == i1y) break;
         i3x = i4x;
         i3y = i4y;
+        // Straight horizontal runs, many pixels per round trip.  Border following is serial (one dependent memory round
+        // trip per pixel) and the longest contour of a page IS the latency of DBPostProcess; text lines are long
+        // horizontal blobs.  Moving east (s == 0) the walk is on a bottom edge: it keeps going east exactly while the
+        // pixels SW, S, SE are empty and E is set (the scan from the reversed direction 4 visits 5, 6, 7, 0); moving west
+        // (s == 4) it is on a top edge: NE, N, NW empty and W set.  32 lanes test the next 32 pixels of both rows, the
+        // walk jumps over the whole stretch that satisfies the condition — no direction change, so no contour point is
+        // lost (CHAIN_APPROX_SIMPLE) and the point sequence is identical to the pixel-by-pixel walk.
+        if (!turned && (s == 0 || s == 4)) {
+            const int dir = s == 0 ? 1 : -1, oy = s == 0 ? 1 : -1;
+            const int a = img.at(i3x + dir * (1 + lane), i3y), b = img.at(i3x + dir * (lane - 1), i3y + oy);
+            const unsigned A = __ballot_sync(0xffffffffu, a != 0), B = __ballot_sync(0xffffffffu, b != 0);
+            const int ones = ~A ? __ffs(~A) - 1 : 32, zeros = B ? __ffs(B) - 1 : 32;
+            int k = min(ones, zeros - 2);
+            // never run over the start pixel or the first step's pixel: the termination test belongs to the ordinary step
+            if (i3y == sy && (sx - i3x) * dir > 0) k = min(k, (sx - i3x) * dir - 1);
+            if (i3y == i1y && (i1x - i3x) * dir > 0) k = min(k, (i1x - i3x) * dir - 1);
+            if (k > 0) {
+                i3x += dir * k;
+                ptx += dir * k;
+            }
+        }
         s = (s + 4) & 7;
         mask = neighbour_mask(img, i3x, i3y, lane);
     }

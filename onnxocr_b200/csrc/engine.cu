@@ -851,18 +851,18 @@ void Model::build_steps(Plan& p) {
                         tp.ws_stage_bytes = (int)stage_bytes;
                     }
                     // an SE gate follows: the epilogue accumulates the per-image channel sums (no separate GAP pass)
+                    int gap_buf = -1;
                     if (ws_bn && !tc_ct && c.epi.fast && se_sums_enabled() && ni + 1 < g.nodes.size() && g.nodes[ni + 1].kind == C_SE &&
                         g.nodes[ni + 1].in[0] == c.out && cp.CoutP <= kSeSumsThreads && cp.CoutP % 8 == 0) {
-                        unsigned long long* sums = nullptr;
                         const size_t bytes = (size_t)iv.n * tc::kGapReplicas * cp.CoutP * sizeof(unsigned long long);
-                        B200_CUDA_CHECK(cudaMalloc(&sums, bytes));
-                        B200_CUDA_CHECK(cudaMemset(sums, 0, bytes));
-                        p.owned.push_back(std::shared_ptr<void>(sums, [](void* q) { cudaFree(q); }));
+                        gap_buf = new_buf(bytes);
                         p.vals[out].sums_replicas = tc::kGapReplicas;
-                        tp.gap = sums;
+                        tp.gap = reinterpret_cast<unsigned long long*>(1);   // resolved at launch (the slab may move)
                         tp.gap_mod = cp.CoutP;
                         tp.gap_rows = tp.mode == 0 ? tp.M / iv.n : 0;
-                        p.vals[out].sums = sums;
+                        p.vals[out].sums = gap_buf;
+                        const int gb = gap_buf;
+                        emit("zero_sums " + c.name, [=](cudaStream_t st) { cudaMemsetAsync(pp->bufptr(gb), 0, bytes, st); });
                     }
                     std::shared_ptr<TcState> ts(new TcState());
                     {
@@ -877,6 +877,7 @@ void Model::build_steps(Plan& p) {
                         (void)ct2_w;                                    // keeps the second-stage weights alive with the plan
                         tc::Params tp = tp0;
                         tp.ct2_out = pp->out_dense;
+                        if (gap_buf >= 0) tp.gap = (unsigned long long*)pp->bufptr(gap_buf);
                         const void* x = pp->ptr(in);
                         if (ts->a_ptr != x) {
                             if (tp.mode == 0) {
@@ -985,17 +986,19 @@ void Model::build_steps(Plan& p) {
                 cost_bytes = vbytes(in) + vbytes(out);
                 const bool strip_ok = std::is_same<T, bf16>::value && wb16 && dp.CP % 8 == 0 && dp.kh == dp.kw && (dp.kw == 3 || dp.kw == 5) &&
                                       (dp.sw == 1 || dp.sw == 2) && (dp.sh == 1 || dp.sh == 2) && dw_strip_enabled();
+                int dw_gap_buf = -1;
                 if (strip_ok && se_sums_enabled() && ni + 1 < g.nodes.size() && g.nodes[ni + 1].kind == C_SE && g.nodes[ni + 1].in[0] == c.out &&
                     iv.cp <= kSeSumsThreads) {
-                    unsigned long long* sums = nullptr;
                     const size_t bytes = (size_t)iv.n * iv.cp * sizeof(unsigned long long);
-                    B200_CUDA_CHECK(cudaMalloc(&sums, bytes));
-                    B200_CUDA_CHECK(cudaMemset(sums, 0, bytes));
-                    p.owned.push_back(std::shared_ptr<void>(sums, [](void* q) { cudaFree(q); }));
-                    dp.gap = sums;
-                    p.vals[out].sums = sums;
+                    dw_gap_buf = new_buf(bytes);
+                    p.vals[out].sums = dw_gap_buf;
+                    const int gb = dw_gap_buf;
+                    emit("zero_sums " + c.name, [=](cudaStream_t st) { cudaMemsetAsync(pp->bufptr(gb), 0, bytes, st); });
                 }
+                const DwP dp0 = dp;
                 emit("dwconv " + c.name, [=](cudaStream_t st) {
+                    DwP dp = dp0;
+                    if (dw_gap_buf >= 0) dp.gap = (unsigned long long*)pp->bufptr(dw_gap_buf);
                     if (std::is_same<T, bf16>::value && wb16 && dp.CP % 8 == 0 && dp.kh == dp.kw && (dp.kw == 3 || dp.kw == 5) &&
                         (dp.sw == 1 || dp.sw == 2) && (dp.sh == 1 || dp.sh == 2)) {
                         const bf16* xi = (const bf16*)pp->ptr(in);
@@ -1046,7 +1049,7 @@ void Model::build_steps(Plan& p) {
                 use(in);
                 cost_bytes = vbytes(in);
                 // the producer already accumulated the channel sums in its epilogue: no pass over the tensor at all
-                const bool from_sums = c.kind == C_SE && iv.sums != nullptr && c.se_mid <= kSeSumsThreads && iv.cp <= kSeSumsThreads;
+                const bool from_sums = c.kind == C_SE && iv.sums >= 0 && c.se_mid <= kSeSumsThreads && iv.cp <= kSeSumsThreads;
                 const bool fuse_gap_se = c.kind == C_SE && iv.cp <= kGapSeThreads && c.se_mid <= kGapSeThreads && gap_se_fused();
                 if (!fuse_gap_se && !from_sums)
                     emit("gap_partial " + c.name, [=](cudaStream_t st) {
@@ -1080,18 +1083,19 @@ void Model::build_steps(Plan& p) {
                 // consumers that can apply it on the fly read the un-gated tensor, the others materialise it (plain()).
                 const bool lazy = std::is_same<T, bf16>::value && iv.cp % 8 == 0 && epi.n == 0 && se_lazy_enabled();
                 int out = lazy ? alias_val(in, iv.form, iv.h, iv.w) : new_val(F_NCHW, iv.n, iv.h, iv.w, iv.c);
-                if (lazy) { p.vals[out].gate = scale; p.vals[out].gate_res = residual; p.vals[out].sums = nullptr; p.vals[out].sums_replicas = 1; }
+                if (lazy) { p.vals[out].gate = scale; p.vals[out].gate_res = residual; p.vals[out].sums = -1; p.vals[out].sums_replicas = 1; }
                 const DevWeights &w1 = dw_[c.se_w1], &w2 = dw_[c.se_w2];
                 int mid = c.se_mid;
                 float alpha = c.scale, beta = c.eps;
                 size_t smem2 = (size_t)(iv.cp + mid + kSeThreads) * sizeof(float);
                 if (from_sums) {
-                    unsigned long long* sums = iv.sums;
+                    const int sums_buf = iv.sums;
+                    buf_last[sums_buf] = std::max(buf_last[sums_buf], cur);
                     const int reps = iv.sums_replicas;
                     const size_t smem4 = (size_t)(iv.cp + mid + kSeSumsThreads) * sizeof(float);
                     cost_bytes = (double)iv.n * iv.cp * 8 + 2.0 * (double)iv.c * mid * 4;
                     emit("se_fc_sums " + c.name, [=](cudaStream_t st) {
-                        launch_pdl(se_fc_sums_kernel, N, kSeSumsThreads, smem4, st, sums, reps, HW, C, CP, mid, w1.w, w1.ColsW, w1.bias, w2.w,
+                        launch_pdl(se_fc_sums_kernel, N, kSeSumsThreads, smem4, st, (unsigned long long*)pp->bufptr(sums_buf), reps, HW, C, CP, mid, w1.w, w1.ColsW, w1.bias, w2.w,
                                    w2.ColsW, w2.bias, alpha, beta, (float*)pp->bufptr(scale));
                     });
                 } else if (fuse_gap_se) {
@@ -1164,7 +1168,7 @@ void Model::build_steps(Plan& p) {
                 if (v.form != F_NCHW) throw std::runtime_error("Resize input is not NCHW-shaped: " + c.name);
                 v.up_src = in;
                 v.root = -1;
-                v.gate = -1; v.gate_res = 0; v.sums = nullptr;
+                v.gate = -1; v.gate_res = 0; v.sums = -1;
                 v.fh = c.fh; v.fw = c.fw;
                 v.h *= c.fh; v.w *= c.fw;
                 p.vals.push_back(v);

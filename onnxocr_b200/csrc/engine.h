@@ -35,7 +35,7 @@ struct PVal {
     // can apply it on the fly (element-wise add, concat) read x and the gate, everyone else gets it materialised
     int gate = -1, gate_res = 0;
     // per (image, channel) sums of this tensor accumulated by its producer (fixed point, see common.cuh) for an SE gate
-    unsigned long long* sums = nullptr;
+    int sums = -1;                 // buffer id (zeroed by a memset node right before the producer runs)
     int sums_replicas = 1;
     std::vector<int64_t> host;
     std::vector<int64_t> logical() const;

@@ -422,10 +422,10 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
 
-template <int K, int SH, int SW, int WPP, int TY, int ACT>
+template <int K, int SH, int SW, int WPP, int TY, int ACT, bool GAP>
 __device__ __forceinline__ void dw_strip_rows(const uint32_t* __restrict__ col, const f32x2_t (&wf)[K * K], f32x2_t bb,
                                               bf16* __restrict__ yo, int64_t ystride, int rows_in, bool live0, bool live1,
-                                              const Epilogue& epi, bool gap, float& g0, float& g1) {
+                                              const Epilogue& epi, float& g0, float& g1) {
     constexpr int TX = 256 / WPP;
     constexpr int IR = (TY - 1) * SH + K, IC = (TX - 1) * SW + K;
     constexpr int PS = (SW == 2 && WPP < 32) ? WPP * 3 / 2 : WPP;
@@ -451,7 +451,7 @@ __device__ __forceinline__ void dw_strip_rows(const uint32_t* __restrict__ col, 
                 __nv_bfloat162 pk = __floats2bfloat162_rn(o0, o1);
                 const uint32_t u = *reinterpret_cast<uint32_t*>(&pk);
                 *reinterpret_cast<uint32_t*>(yo + (int64_t)oy * ystride) = u;
-                if (gap) {                                           // sums of the values as stored (rows in order)
+                if (GAP) {                                           // sums of the values as stored (rows in order)
                     g0 += __uint_as_float(u << 16);
                     g1 += __uint_as_float(u & 0xffff0000u);
                 }
@@ -460,7 +460,7 @@ __device__ __forceinline__ void dw_strip_rows(const uint32_t* __restrict__ col, 
     }
 }
 
-template <int K, int SH, int SW, int WPP, int TY>
+template <int K, int SH, int SW, int WPP, int TY, bool GAP>
 __global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ bias, bf16* __restrict__ y, const DwP p,
                                                             int tiles_x, int tiles_y) {
@@ -511,8 +511,7 @@ __global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restric
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    const bool gap = p.gap != nullptr;
-    if (!active && !gap) return;
+    if (!active && !GAP) return;
     float g0 = 0.f, g1 = 0.f;
     if (active) {
         const bool live0 = c < p.C, live1 = c + 1 < p.C;
@@ -521,13 +520,13 @@ __global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restric
         const int64_t ystride = (int64_t)p.Wo * p.CP;
         // the activation is a launch constant: branch once, run a body compiled for it
         switch (p.epi.fast ? p.epi.act : -1) {
-            case 0: dw_strip_rows<K, SH, SW, WPP, TY, 0>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi, gap, g0, g1); break;
-            case EPI_RELU: dw_strip_rows<K, SH, SW, WPP, TY, EPI_RELU>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi, gap, g0, g1); break;
-            case EPI_HSWISH: dw_strip_rows<K, SH, SW, WPP, TY, EPI_HSWISH>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi, gap, g0, g1); break;
-            default: dw_strip_rows<K, SH, SW, WPP, TY, -1>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi, gap, g0, g1); break;
+            case 0: dw_strip_rows<K, SH, SW, WPP, TY, 0, GAP>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi, g0, g1); break;
+            case EPI_RELU: dw_strip_rows<K, SH, SW, WPP, TY, EPI_RELU, GAP>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi, g0, g1); break;
+            case EPI_HSWISH: dw_strip_rows<K, SH, SW, WPP, TY, EPI_HSWISH, GAP>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi, g0, g1); break;
+            default: dw_strip_rows<K, SH, SW, WPP, TY, -1, GAP>(col, wf, bb, yo, ystride, rows_in, live0, live1, p.epi, g0, g1); break;
         }
     }
-    if (!gap) return;
+    if (!GAP) return;
     // channel sums for the SE gate that follows: per-thread column sums -> shared memory -> one value per channel of this
     // tile (columns in fixed order) -> fixed-point atomics (common.cuh)
     __syncthreads();                              // every thread has finished reading the tile
@@ -555,12 +554,15 @@ inline void launch_dwconv_strip_w(const bf16* x, const float* w, const float* bi
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr[dev & 15]) {
-        cudaFuncSetAttribute(dwconv_strip_kernel<K, SH, SW, WPP, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(dwconv_strip_kernel<K, SH, SW, WPP, TY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(dwconv_strip_kernel<K, SH, SW, WPP, TY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr[dev & 15] = true;
     }
     int tiles_x = (p.Wo + TX - 1) / TX, tiles_y = (p.Ho + TY - 1) / TY;
     dim3 grid((unsigned)(tiles_x * tiles_y * p.N), (unsigned)((p.CP + 2 * WPP - 1) / (2 * WPP)));
-    launch_pdl(dwconv_strip_kernel<K, SH, SW, WPP, TY>, grid, 256, smem, st, x, w, bias, y, p, tiles_x, tiles_y);
+    // the channel-sum variant is a separate instantiation: its extra registers would cost every other layer occupancy
+    if (p.gap) launch_pdl(dwconv_strip_kernel<K, SH, SW, WPP, TY, true>, grid, 256, smem, st, x, w, bias, y, p, tiles_x, tiles_y);
+    else launch_pdl(dwconv_strip_kernel<K, SH, SW, WPP, TY, false>, grid, 256, smem, st, x, w, bias, y, p, tiles_x, tiles_y);
 }
 
 template <int K, int SH, int SW>

@@ -46,6 +46,7 @@ struct Params {
     // gap_mod = channels per pixel (a pixel-packed GEMM row carries several pixels: column % gap_mod = channel)
     unsigned long long* gap;
     int gap_rows, gap_mod;
+    int epi_variant;             // tools/ubench A/B: bit 0 = 16-column TMEM loads only, bit 1 = shuffle-based store loop
     unsigned long long* dbg;     // tools/ubench only: per-CTA cycle counters of the MMA / TMA threads (nullptr in the engine)
     int ct2;
     const float* ct2_w;
@@ -456,7 +457,10 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 // BN (32..256) is a run-time parameter chosen so that the slab fits; with BN = 256 a 240-channel layer reads its
 // activations exactly once.  Eight epilogue warps (two per TMEM lane quarter, each taking half of the columns) drain
 // the double-buffered accumulators.
-constexpr int kWsEpiWarps = 8;           // two per TMEM lane quarter, each taking half of the tile's columns (more warps
+#ifndef B200_WS_EPI_WARPS
+#define B200_WS_EPI_WARPS 8
+#endif
+constexpr int kWsEpiWarps = B200_WS_EPI_WARPS;           // two per TMEM lane quarter, each taking half of the tile's columns (more warps
                                          // measured slower: the waiting warps' barrier polling competes for issue slots)
 constexpr int kWsThreads = 64 + 32 * kWsEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr int WS_MAX_STAGES = 12;
@@ -470,7 +474,7 @@ inline size_t ws_tail_bytes() {
            (size_t)kWsEpiWarps * 128 * 8 /*per-warp channel-sum accumulators*/;
 }
 // epilogue staging: 16 warps x 32 rows x (their column part in bf16 + 16 bytes of padding against bank conflicts)
-inline int ws_parts(int bn) { (void)bn; return kWsEpiWarps / 4; }             // column parts (each a multiple of 16 columns)
+inline int ws_parts(int bn) { return std::min(kWsEpiWarps / 4, bn / 16); }             // column parts (each a multiple of 16 columns)
 inline size_t ws_stage_row_bytes(int bn) { return (size_t)(bn / ws_parts(bn)) * 2 + 16; }
 inline size_t ws_staging_bytes(int bn) { return (size_t)kWsEpiWarps * 32 * ws_stage_row_bytes(bn); }
 inline size_t ws_slab_bytes(int bn, int nkb) { return (size_t)nkb * bn * BK * 2 + ws_staging_bytes(bn); }
@@ -614,45 +618,11 @@ __device__ __forceinline__ uint32_t epi_pair(uint32_t acc_lo, uint32_t acc_hi, f
 // shared-memory tile owned by this warp -> 16-byte global stores in which consecutive lanes write consecutive chunks of
 // a row (full 128-byte lines) instead of every lane writing into its own row.  `bias_s` is the CTA's bias slice in
 // shared memory (index = column inside the tile); off8 / valid describe this lane's row (offset in 8-element units).
-template <int ACT>
-__device__ __forceinline__ void epilogue_cols_staged(uint32_t trow, const float* __restrict__ bias_s, bf16* __restrict__ y,
-                                                     uint32_t off8, bool valid, int n0, int c_begin, int c_end, const Params& p,
-                                                     uint8_t* stage, int row_bytes, int lane, unsigned long long* gacc = nullptr) {
-    const int c_lim = min(c_end, p.CoutP - n0);              // columns that exist in the output tensor
-    uint8_t* my = stage + (size_t)lane * row_bytes;
-    const bool post = p.epi.a1 != 1.f || p.epi.b1 != 0.f;
-    const f2_t a1 = f2_pack(p.epi.a1, p.epi.a1), b1 = f2_pack(p.epi.b1, p.epi.b1);
-#pragma unroll 1
-    for (int c = c_begin; c < c_lim; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(trow + (uint32_t)c, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int cl = c + 8 * h;                         // column inside the tile
-            if (cl < c_lim) {
-                const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cl);
-                const float4 b1v = *reinterpret_cast<const float4*>(bias_s + cl + 4);
-                uint4 pk;
-                pk.x = epi_pair<ACT>(v[8 * h + 0], v[8 * h + 1], f2_pack(b0.x, b0.y), a1, b1, post, p.epi);
-                pk.y = epi_pair<ACT>(v[8 * h + 2], v[8 * h + 3], f2_pack(b0.z, b0.w), a1, b1, post, p.epi);
-                pk.z = epi_pair<ACT>(v[8 * h + 4], v[8 * h + 5], f2_pack(b1v.x, b1v.y), a1, b1, post, p.epi);
-                pk.w = epi_pair<ACT>(v[8 * h + 6], v[8 * h + 7], f2_pack(b1v.z, b1v.w), a1, b1, post, p.epi);
-                const int lim = p.Cout - (n0 + cl);           // pad lanes of the last group stay zero
-                if (lim < 8) {
-                    uint32_t* w = &pk.x;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (2 * j >= lim) w[j] = 0u;
-                        else if (2 * j + 1 >= lim) w[j] &= 0x0000ffffu;
-                    }
-                }
-                *reinterpret_cast<uint4*>(my + (size_t)(cl - c_begin) * 2) = pk;
-            }
-        }
-    }
-    __syncwarp();
-    if (gacc) {
+// Channel sums of one staged tile part (see epilogue_cols_staged); deliberately not inlined: one copy of this code for all
+// activation variants of the epilogue keeps the kernel's instruction footprint down (small layers are launch-latency bound
+// and start with a cold instruction cache).
+__device__ __noinline__ void gap_accumulate_tile(const uint8_t* stage, int row_bytes, int ncols, bool valid, int lane,
+                                                 unsigned long long* gacc) {
         // Column sums of the staged (bf16-rounded) values over this warp's valid rows.  All 32 lanes work: a lane owns one
         // pair of columns and, when the part has fewer than 32 pairs, one group of rows (partial sums then meet through
         // xor shuffles — a fixed tree, so the result is reproducible).  Loads are unconditional (rows that do not exist
@@ -660,7 +630,7 @@ __device__ __forceinline__ void epilogue_cols_staged(uint32_t trow, const float*
         // tile's sums go as fixed point into this warp's own accumulators in shared memory (integer adds are associative:
         // the total does not depend on which tiles a CTA happens to process); they are flushed per image.
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-        const int npairs = (c_lim - c_begin) >> 1;
+        const int npairs = ncols >> 1;
         int lgp = 0;
         while ((1 << lgp) < npairs && lgp < 5) ++lgp;         // lanes per row group = min(32, next pow2 >= npairs)
         const int lanes_pp = 1 << lgp, groups = 32 >> lgp, rows_pg = 32 / groups;
@@ -698,21 +668,103 @@ __device__ __forceinline__ void epilogue_cols_staged(uint32_t trow, const float*
                 asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(ga), "l"(c0), "l"(c1) : "memory");
             }
         }
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+
+// eight accumulator columns -> bias, activation, bf16 -> one 16-byte store into the lane's staged row
+template <int ACT>
+__device__ __forceinline__ void epi_group8(const uint32_t* v, const float* __restrict__ bias8, f2_t a1, f2_t b1, bool post,
+                                           const Params& p, int lim, uint8_t* dst) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias8);
+    const float4 b1v = *reinterpret_cast<const float4*>(bias8 + 4);
+    uint4 pk;
+    pk.x = epi_pair<ACT>(v[0], v[1], f2_pack(b0.x, b0.y), a1, b1, post, p.epi);
+    pk.y = epi_pair<ACT>(v[2], v[3], f2_pack(b0.z, b0.w), a1, b1, post, p.epi);
+    pk.z = epi_pair<ACT>(v[4], v[5], f2_pack(b1v.x, b1v.y), a1, b1, post, p.epi);
+    pk.w = epi_pair<ACT>(v[6], v[7], f2_pack(b1v.z, b1v.w), a1, b1, post, p.epi);
+    if (lim < 8) {                                           // pad lanes of the last group stay zero
+        uint32_t* w = &pk.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (2 * j >= lim) w[j] = 0u;
+            else if (2 * j + 1 >= lim) w[j] &= 0x0000ffffu;
+        }
     }
+    *reinterpret_cast<uint4*>(dst) = pk;
+}
+
+// Coalesced epilogue: columns [c_begin, c_end) of the warp's 32 accumulator rows -> bias, activation, bf16 -> a padded
+// shared-memory tile owned by this warp -> 16-byte global stores in which consecutive lanes write consecutive chunks of
+// a row (full 128-byte lines) instead of every lane writing into its own row.  `bias_s` is the CTA's bias slice in
+// shared memory (index = column inside the tile); off8 / valid describe this lane's row (offset in 8-element units).
+// The accumulator is read 32 columns per TMEM load (16 independent packed chains in flight per lane: the epilogue is
+// latency-, not throughput-bound); LINEAR: the rows of the warp are consecutive GEMM rows (mode 0), so a row's offset and
+// validity follow from its index and the store loop needs no shuffles.
+template <int ACT>
+__device__ __forceinline__ void epilogue_cols_staged(uint32_t trow, const float* __restrict__ bias_s, bf16* __restrict__ y,
+                                                     uint32_t off8, bool valid, int n0, int c_begin, int c_end, const Params& p,
+                                                     uint8_t* stage, int row_bytes, int lane, unsigned long long* gacc, bool LINEAR) {
+    const int c_lim = min(c_end, p.CoutP - n0);              // columns that exist in the output tensor
+    uint8_t* my = stage + (size_t)lane * row_bytes;
+    const bool post = p.epi.a1 != 1.f || p.epi.b1 != 0.f;
+    const f2_t a1 = f2_pack(p.epi.a1, p.epi.a1), b1 = f2_pack(p.epi.b1, p.epi.b1);
+    int c = c_begin;
+#pragma unroll 1
+    for (; c < c_lim; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + (uint32_t)c, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int cl = c + 8 * h;
+            if (cl < c_lim) epi_group8<ACT>(v + 8 * h, bias_s + cl, a1, b1, post, p, p.Cout - (n0 + cl), my + (size_t)(cl - c_begin) * 2);
+        }
+    }
+    __syncwarp();
+    if (gacc) gap_accumulate_tile(stage, row_bytes, c_lim - c_begin, valid, lane, gacc);
     const int chunks = (c_lim - c_begin) >> 3;               // 16-byte chunks per row (CoutP % 8 == 0)
     if (chunks > 0) {
         int lg = 0;
         while ((1 << lg) < chunks) ++lg;                      // lanes per row = next power of two (<= 16 for BN <= 256)
         const int cc = lane & ((1 << lg) - 1), rsub = lane >> lg, rows_per_pass = 32 >> lg;
         const uint32_t col8 = (uint32_t)(n0 + c_begin) >> 3;
+        if (LINEAR) {
+            // consecutive GEMM rows: row rr sits rr * (CoutP / 8) chunks after the warp's first row and the valid rows are
+            // a prefix of the warp's 32
+            const uint32_t base8 = __shfl_sync(0xffffffffu, off8, 0) + col8 + (uint32_t)cc;
+            const int nvalid = __popc(__ballot_sync(0xffffffffu, valid));
+            const uint32_t rstride8 = (uint32_t)p.CoutP >> 3;
+            const uint8_t* src = stage + (size_t)rsub * row_bytes + (size_t)cc * 16;
+            if (cc < chunks) {
+#pragma unroll 4
+                for (int r0 = 0; r0 < 32; r0 += rows_per_pass) {
+                    const int rr = r0 + rsub;
+                    if (rr < nvalid) {
+                        const uint4 val = *reinterpret_cast<const uint4*>(src + (size_t)r0 * row_bytes);
+                        *reinterpret_cast<uint4*>(y + ((size_t)(base8 + (uint32_t)rr * rstride8) << 3)) = val;
+                    }
+                }
+            }
+        } else {
 #pragma unroll 1
-        for (int r0 = 0; r0 < 32; r0 += rows_per_pass) {
-            const int rr = r0 + rsub;
-            const uint32_t o_rr = __shfl_sync(0xffffffffu, off8, rr);
-            const int v_rr = __shfl_sync(0xffffffffu, (int)valid, rr);
-            if (cc < chunks && v_rr) {
-                uint4 val = *reinterpret_cast<const uint4*>(stage + (size_t)rr * row_bytes + (size_t)cc * 16);
-                *reinterpret_cast<uint4*>(y + ((size_t)(o_rr + col8 + cc) << 3)) = val;
+            for (int r0 = 0; r0 < 32; r0 += rows_per_pass) {
+                const int rr = r0 + rsub;
+                const uint32_t o_rr = __shfl_sync(0xffffffffu, off8, rr);
+                const int v_rr = __shfl_sync(0xffffffffu, (int)valid, rr);
+                if (cc < chunks && v_rr) {
+                    uint4 val = *reinterpret_cast<const uint4*>(stage + (size_t)rr * row_bytes + (size_t)cc * 16);
+                    *reinterpret_cast<uint4*>(y + ((size_t)(o_rr + col8 + cc) << 3)) = val;
+                }
             }
         }
     }
@@ -847,7 +899,7 @@ __device__ __forceinline__ void issue_halo3x3(uint32_t tmem_d, uint64_t ad, uint
     }
 }
 
-__global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 const float* __restrict__ bias, bf16* __restrict__ y,
                                                                 const Params p) {
@@ -861,7 +913,7 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
     const uint32_t a_base = b_base + (uint32_t)nkb * B_KB_BYTES;
     const uint32_t ASB = p.ws_halo ? (uint32_t)p.ws_stage_bytes : (uint32_t)WS_A_BYTES;   // bytes per activation stage
     const uint32_t stage_base = a_base + (uint32_t)STG * ASB;
-    const int parts = kWsEpiWarps / 4;                      // column parts of the tile shared out among the epilogue warps
+    const int parts = min(kWsEpiWarps / 4, BN / 16);        // column parts of the tile shared out among the epilogue warps
     const int stage_row = (BN / parts) * 2 + 16;            // bytes per staged row (one part in bf16 + padding)
     const uint32_t bar_base = (stage_base + (uint32_t)kWsEpiWarps * 32u * (uint32_t)stage_row + 63u) & ~63u;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -1191,14 +1243,15 @@ __global__ void __launch_bounds__(kWsThreads) conv_tc_ws_kernel(const __grid_con
                     }
                 } else {
                     uint8_t* stg = smem_raw + (stage_base - smem_u32(smem_raw)) + (size_t)(warp - 2) * 32 * stage_row;
-#define B200_EPI(A) epilogue_cols_staged<A>(trow, bias_s, y, (uint32_t)(off >> 3), valid, n0, c_begin, c_end, p, stg, stage_row, lane, gacc)
+                    const bool linear_rows = p.mode == 0 && !(p.epi_variant & 2);
+#define B200_EPI(A) epilogue_cols_staged<A>(trow, bias_s, y, (uint32_t)(off >> 3), valid, n0, c_begin, c_end, p, stg, stage_row, lane, gacc, linear_rows)
                     switch (act_code) {
                         case 0: B200_EPI(0); break;
                         case EPI_RELU: B200_EPI(EPI_RELU); break;
                         case EPI_HSWISH: B200_EPI(EPI_HSWISH); break;
-                        case EPI_SIGMOID: B200_EPI(EPI_SIGMOID); break;
-                        case EPI_SWISH: B200_EPI(EPI_SWISH); break;
-                        case EPI_HSIGMOID: B200_EPI(EPI_HSIGMOID); break;
+                        case EPI_SIGMOID:
+                        case EPI_SWISH:
+                        case EPI_HSIGMOID: B200_EPI(99); break;           // rare on convolutions: one variant, activation chosen at run time
                         default: epilogue_cols<-1>(trow, bias, dst, valid, n0, c_begin, c_end, p, ctb); break;   // interpreted chain
                     }
 #undef B200_EPI

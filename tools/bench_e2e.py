@@ -22,10 +22,14 @@ dt = (time.perf_counter() - t0) / reps
 stages = ocr.engine.ocr_stage_times()
 lines = sum(len(r) for r in res)
 t1 = time.perf_counter()
-single = [ocr.ocr(p)[0] for p in pages]
+single, per_page_ms = [], []
+for p in pages:
+    tp0 = time.perf_counter()
+    single.append(ocr.ocr(p)[0])
+    per_page_ms.append(round((time.perf_counter() - tp0) * 1e3, 2))
 dt1 = time.perf_counter() - t1
 same = sum(1 for a, b in zip(res, single) if [x[1][0] for x in a] == [x[1][0] for x in b])
 print(json.dumps({"config": "C4 end-to-end det+cls+rec, %d mixed-size pages" % n, "precision": prec, "rec_width_bucket": bucket,
                   "batched_pages_per_s": n / dt, "batched_lines_per_s": lines / dt, "lines": lines,
                   "one_page_per_call_pages_per_s": n / dt1, "pages_identical_to_single_calls": "%d/%d" % (same, n),
-                  "launches": ocr.engine.launch_count(), "stage_ms_last_batch": {k: round(v, 2) for k, v in stages.items()}}))
+                  "one_page_ms": per_page_ms, "launches": ocr.engine.launch_count(), "stage_ms_last_batch": {k: round(v, 2) for k, v in stages.items()}}))

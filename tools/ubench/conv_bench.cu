@@ -73,6 +73,7 @@ int main(int argc, char** argv) {
     if (ws_bn) { tp.ws_bn = ws_bn; tp.ws_stages = tc::ws_pick_stages(ws_bn, nkb, stage_bytes); tp.ws_halo = halo ? mode : 0; tp.ws_stage_bytes = (int)stage_bytes; }
     if (getenv("STAGES")) tp.ws_stages = atoi(getenv("STAGES"));
     tp.dbg = dbg;
+    if (getenv("EPI")) tp.epi_variant = atoi(getenv("EPI"));
     if (getenv("GAP")) {          // SE producer: channel sums in the epilogue; GAP = channels per pixel (gap_mod)
         unsigned long long* sums;
         cudaMalloc(&sums, (size_t)n * tc::kGapReplicas * 1024 * 8);
