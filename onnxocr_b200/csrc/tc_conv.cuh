@@ -969,7 +969,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(const __grid_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
-    pdl_wait();                                             // activations of the previous kernel are complete and visible
+    // Programmatic dependent launch: everything up to here — and the producer's weight-slab loads below — overlaps the tail
+    // of the previous kernel.  The producer waits for it right before its first ACTIVATION load, the other roles before
+    // they touch anything (their first action depends on the producer's loads anyway).
+    if (warp != 0) pdl_wait();
 
     auto tile_origin = [&](int mt, int& m0, int& img, int& y0, int& x0) {
         m0 = mt * BM;
@@ -1000,6 +1003,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(const __grid_
                 const int slot = p.ws_halo ? (kb % p.kchunks) * p.taps + kb / p.kchunks : kb;
                 tma_load_2d(b_base + slot * B_KB_BYTES, &map_b, b_bar, kb * BK, n0);
             }
+            pdl_wait();                                     // activations of the previous kernel are complete and visible
             uint32_t it = 0;
             for (int mt = m_first; mt < m_tiles; mt += m_step) {
                 int m0, img, y0, x0;
@@ -1032,6 +1036,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_tc_ws_kernel(const __grid_
                 }
             }
         }
+        else pdl_wait();                                    // the other 31 lanes of the producer warp
         __syncwarp();
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
