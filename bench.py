@@ -8,9 +8,14 @@ batch of 16 synthetic 960x960 pages per GPU.  Pages shard across GPUs as indepen
 (weak scaling, no collective on the data path); torch.distributed is used for the barrier and the max-over-ranks
 of the device time only.
 
-  value     pages/s with the page bytes already resident in HBM (CUDA events on the engine stream)
-  e2e       pages/s through the public API (`Engine.det_pages`) with HOST page buffers: H2D of the page
+  value     pages/s with the page bytes already resident in HBM (CUDA events on the engine stream), through the
+            streaming entry points (b200ocr_det_submit / _collect: two batches in flight, so the DBPostProcess tail
+            and box read-back of step k overlap the network of step k+1).  Steps rotate through 4 resident page sets
+            (177 MB > the 126 MB L2).
+  e2e       pages/s through the public API (`Engine.det_pages_stream`) with HOST page buffers: H2D of the page
             bytes from pinned memory and D2H of the boxes are inside the timed region
+  sync      the same two numbers with one blocking `det_pages` call per step (nothing overlaps across steps; L2
+            flushed between the device-timed steps)
   roofline  dominant kernel class of the step, timed live per launch with CUDA events
   cpu_baseline / --impl reference: the oracle port of the reference's CPU path (reference pre/post-processing
             restated with cv2/numpy, network through the torch-CPU fp32 interpreter: onnxruntime is not
@@ -33,7 +38,16 @@ sys.path.insert(0, ROOT)
 PAGES_PER_GPU = 16
 SIDE = 960
 LINES = 40
+SETS = 4            # page sets a rank rotates through: 4 x 16 x 2.76 MB = 177 MB of inputs > 126 MB L2
 METRIC = "PP-OCRv5 mobile det pages/sec (960x960 pages, batch 16, prob map + DBPostProcess boxes)"
+# the same dict is printed by both arms (the reference arm runs a bounded sample of this workload on the host cores)
+CONFIG = {"workload": "C2 det-only: 16 synthetic 960x960 pages per GPU per step (synthetic-weight PP-OCRv5 mobile det graph, "
+                      "fitted on rendered pages), prob map + DBPostProcess boxes",
+          "pages_per_gpu": PAGES_PER_GPU,
+          "l2": "inputs larger than L2: the steps rotate through %d page sets (%d pages, 177 MB > 126 MB L2) and every step "
+                "rewrites ~2 GB of activations" % (SETS, SETS * PAGES_PER_GPU),
+          "pipeline": "streaming det: two batches in flight (submit / collect), each as two 8-page sub-batches on its own "
+                      "pair of det lanes; uploads, network and DBPostProcess of neighbouring steps overlap"}
 
 
 def load_peaks():
@@ -94,9 +108,9 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def make_pages(rank):
+def make_pages(rank, sets=SETS):
     from onnxocr_b200 import synth_pages
-    return synth_pages.det_pages_c2(PAGES_PER_GPU, SIDE, LINES, seed=rank)
+    return synth_pages.det_pages_c2(PAGES_PER_GPU * sets, SIDE, LINES, seed=rank)
 
 
 def oracle_det_pages(pages, graph):
@@ -152,14 +166,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        pages = make_pages(0)
+        pages = make_pages(0, sets=1)
         r = cpu_arm(pages, max(1, args.steps), min(warmup, 1), sample_pages=4)
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "pages/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2 det-only: 960x960 synthetic pages, prob map + DBPostProcess boxes",
-                       "pages_per_step": 4},
+            "config": CONFIG,
             "cpu_baseline": {"value": r["value"], "unit": "pages/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -194,22 +207,15 @@ def main():
     pages = make_pages(rank)
     params = _lib.det_params()
 
-    # ---- device-resident timing ("value")
+    # ---- device-resident timing ("value"): K steps through the streaming path, one device-timed region
     eng.det_resident_upload(pages)
-    for _ in range(max(warmup, 3)):
-        eng.det_resident_run(params, 1)
+    eng.det_resident_stream(params, max(warmup, 3) + 1, PAGES_PER_GPU)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = eng.launch_count()
     barrier()
-    dev_ms = 0.0
-    n_boxes = 0
-    for _ in range(args.steps):
-        eng.l2_flush()
-        ms, nb, _ = eng.det_resident_run(params, 1)
-        dev_ms += ms
-        n_boxes += nb
+    dev_ms, n_boxes = eng.det_resident_stream(params, args.steps, PAGES_PER_GPU)
     barrier()
     launches = eng.launch_count() - launches0
     dev_ms = max_over_ranks(dev_ms)
@@ -221,18 +227,40 @@ def main():
         a = eng.pinned_array(p.shape, np.uint8)
         a[...] = p
         pinned.append(a)
-    for _ in range(max(warmup, 3)):
-        eng.det_pages(pinned, params)
+    sets = [pinned[k * PAGES_PER_GPU:(k + 1) * PAGES_PER_GPU] for k in range(SETS)]
+    for _ in eng.det_pages_stream([sets[k % SETS] for k in range(max(warmup, 3) + 1)], params):
+        pass
     barrier()
     t0 = time.perf_counter()
     d2h = 0
-    for _ in range(args.steps):
-        out = eng.det_pages(pinned, params)
+    for out in eng.det_pages_stream((sets[k % SETS] for k in range(args.steps)), params):
         d2h = sum(b.nbytes for b in out) + 4 * len(out)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = PAGES_PER_GPU * world * args.steps / e2e_s
-    h2d = sum(p.nbytes for p in pages)
+    h2d = sum(p.nbytes for p in sets[0])
+
+    # ---- one blocking call per step (no overlap across steps), L2 flushed between the device-timed steps
+    sync_steps = min(args.steps, 10)
+    eng.det_resident_upload(pages[:PAGES_PER_GPU])
+    for _ in range(3):
+        eng.det_resident_run(params, 1)
+    barrier()
+    sync_ms = 0.0
+    for _ in range(sync_steps):
+        eng.l2_flush()
+        sync_ms += eng.det_resident_run(params, 1)[0]
+    sync_ms = max_over_ranks(sync_ms)
+    for _ in range(3):
+        eng.det_pages(sets[0], params)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(sync_steps):
+        eng.det_pages(sets[k % SETS], params)
+    barrier()
+    sync_e2e_s = max_over_ranks(time.perf_counter() - t0)
+    sync = {"value": PAGES_PER_GPU * world * sync_steps / (sync_ms / 1e3), "ms_per_step": sync_ms / sync_steps,
+            "e2e": PAGES_PER_GPU * world * sync_steps / sync_e2e_s, "steps": sync_steps, "unit": "pages/s"}
     if rank == 0:
         sampler.stop()
 
@@ -294,13 +322,10 @@ def main():
         "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": "C2 det-only: 16 synthetic 960x960 pages per GPU per step (synthetic-weight PP-OCRv5 mobile "
-                               "det graph, fitted on rendered pages), prob map + DBPostProcess boxes",
-                   "pages_per_gpu": PAGES_PER_GPU, "l2": "flushed between timed iterations (256 MiB write)",
-                   "pipeline": "two det lanes: sub-batches of 8 pages alternate between two streams, DBPostProcess of one "
-                               "overlaps the network of the other",
-                   "boxes_per_step": n_boxes / max(args.steps, 1)},
+        "config": CONFIG,
+        "boxes_per_step": n_boxes / max(args.steps, 1),
         "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "sync": sync,
         "gpu_launches": int(launches),
         "network_ms_per_step": net_ms,
         "network_algorithmic": {"gbytes_per_step": 2 * net_bytes / 1e9, "gflop_per_step": 2 * net_flops / 1e9,
@@ -311,7 +336,7 @@ def main():
         "clocks": sampler.summary(),
     }
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_arm(pages, 8, 1, sample_pages=PAGES_PER_GPU)          # ~10-25 s of CPU work on the box's cores
+        r = cpu_arm(pages[:PAGES_PER_GPU], 8, 1, sample_pages=PAGES_PER_GPU)          # ~10-25 s of CPU work on the box's cores
         out["cpu_baseline"] = {"value": r["value"], "unit": "pages/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     print(json.dumps(out))
     if world > 1:

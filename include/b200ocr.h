@@ -104,6 +104,18 @@ int b200ocr_det_pages(b200ocr_engine* e, const uint8_t* const* pages, const int*
                       const int* strides, int n, const b200ocr_det_params* p, float* boxes_out, int max_boxes,
                       int* n_boxes_out, float* probmap_out, size_t probmap_capacity, int* probmap_dims_out);
 
+/* Streaming form of b200ocr_det_pages for callers that keep the GPU fed (the reference runs model.ocr from a
+ * ThreadPoolExecutor(max_workers=4), ocr_images_pdfs.py:106,154, and under Semaphore(MODEL_CONCURRENCY), app/engine.py:111-120;
+ * here the overlap is explicit and single-threaded).  b200ocr_det_submit enqueues the uploads, the network and
+ * DBPostProcess of one batch on a free slot (two det lanes of its own) and returns a ticket without waiting for the
+ * GPU; b200ocr_det_collect blocks until that batch's boxes are on the host and writes them exactly as
+ * b200ocr_det_pages would.  Up to two batches may be in flight (a third submit returns B200OCR_E_CAPACITY): the upload
+ * and network of batch k+1 then overlap the DBPostProcess tail and box read-back of batch k.  The page buffers of a
+ * batch must stay valid and unchanged until it has been collected.  Results are identical to b200ocr_det_pages. */
+int b200ocr_det_submit(b200ocr_engine* e, const uint8_t* const* pages, const int* hs, const int* ws,
+                       const int* strides, int n, const b200ocr_det_params* p, int* ticket_out);
+int b200ocr_det_collect(b200ocr_engine* e, int ticket, float* boxes_out, int max_boxes, int* n_boxes_out);
+
 /* get_rotate_crop_image (utils.py:12-53) for a batch of quads on one page: bicubic perspective warp
  * with BORDER_REPLICATE, rot90 when h/w >= 1.5.  boxes: float32 [n][4][2].  Crops are written
  * back-to-back into crops_out (HWC uint8); crop_dims_out: int32 [n][2] = (h, w) after rotation. */
@@ -196,6 +208,11 @@ int b200ocr_det_resident_upload(b200ocr_engine* e, const uint8_t* const* pages, 
                                 const int* strides, int n);
 int b200ocr_det_resident_run(b200ocr_engine* e, const b200ocr_det_params* p, int iters, float* ms_total,
                              int* n_boxes_total, float* net_ms_total);
+/* The same through the streaming path (submit / collect, two batches in flight): step k processes resident pages
+ * [k*pages_per_step, (k+1)*pages_per_step) modulo the resident set, so uploading more page sets than the L2 holds
+ * makes every step read its pages from HBM.  ms_total = device time of all `iters` steps (CUDA events). */
+int b200ocr_det_resident_stream(b200ocr_engine* e, const b200ocr_det_params* p, int iters, int pages_per_step,
+                                float* ms_total, int* n_boxes_total);
 
 #ifdef __cplusplus
 }

@@ -100,6 +100,9 @@ def lib():
         L.b200ocr_ocr_stage_times.argtypes = [vp, pf]
         L.b200ocr_det_resident_upload.argtypes = [vp, C.POINTER(vp), pi, pi, pi, i]
         L.b200ocr_det_resident_run.argtypes = [vp, C.POINTER(DetParams), i, pf, pi, pf]
+        L.b200ocr_det_resident_stream.argtypes = [vp, C.POINTER(DetParams), i, i, pf, pi]
+        L.b200ocr_det_submit.argtypes = [vp, C.POINTER(vp), pi, pi, pi, i, C.POINTER(DetParams), pi]
+        L.b200ocr_det_collect.argtypes = [vp, i, vp, i, pi]
         _lib = L
         return L
 
@@ -291,6 +294,39 @@ class Engine(object):
             off += h * w
         return out, maps
 
+    def det_submit(self, pages, params=None):
+        """Enqueues TextDetector.__call__ for a batch of pages without waiting for the GPU -> ticket (b200ocr_det_submit).
+        Up to two batches may be in flight; the page arrays are kept alive by the ticket until det_collect."""
+        params = params or det_params()
+        pages = [np.ascontiguousarray(p, dtype=np.uint8) for p in pages]
+        n = len(pages)
+        ptrs = (C.c_void_p * n)(*[p.ctypes.data for p in pages])
+        t = C.c_int()
+        self._check(self._L.b200ocr_det_submit(self._h, ptrs, _int_arr([p.shape[0] for p in pages]),
+                                               _int_arr([p.shape[1] for p in pages]),
+                                               _int_arr([p.strides[0] for p in pages]), n, C.byref(params), C.byref(t)))
+        return (t.value, pages)
+
+    def det_collect(self, ticket, max_boxes=1000):
+        """Blocks until the batch of `ticket` is done -> list of float32 [n_i,4,2], as det_pages returns."""
+        tid, pages = ticket
+        n = len(pages)
+        boxes = np.zeros((n, max_boxes, 4, 2), np.float32)
+        counts = (C.c_int * n)()
+        self._check(self._L.b200ocr_det_collect(self._h, tid, _ptr(boxes), max_boxes, counts))
+        return [boxes[i, :counts[i]].copy() for i in range(n)]
+
+    def det_pages_stream(self, batches, params=None, max_boxes=1000, depth=2):
+        """Generator over an iterable of page batches: yields each batch's boxes in order while keeping `depth` (<= 2)
+        batches in flight, so uploads and the network of the next batch overlap the post-processing of this one."""
+        pending = []
+        for b in batches:
+            if len(pending) >= max(1, min(depth, 2)):
+                yield self.det_collect(pending.pop(0), max_boxes)
+            pending.append(self.det_submit(b, params))
+        while pending:
+            yield self.det_collect(pending.pop(0), max_boxes)
+
     def crop_boxes(self, img, boxes):
         """-> list of HWC uint8 crops (get_rotate_crop_image per box, utils.py:12-53)."""
         img = np.ascontiguousarray(img, dtype=np.uint8)
@@ -407,6 +443,14 @@ class Engine(object):
         nb = C.c_int()
         self._check(self._L.b200ocr_det_resident_run(self._h, C.byref(params), iters, C.byref(ms), C.byref(nb), C.byref(net)))
         return ms.value, nb.value, net.value
+
+    def det_resident_stream(self, params=None, iters=1, pages_per_step=16):
+        """-> (device ms of all `iters` steps, boxes found): the resident benchmark through det_submit / det_collect."""
+        params = params or det_params()
+        ms = C.c_float()
+        nb = C.c_int()
+        self._check(self._L.b200ocr_det_resident_stream(self._h, C.byref(params), iters, pages_per_step, C.byref(ms), C.byref(nb)))
+        return ms.value, nb.value
 
 
 def _det_hw(h, w, params):

@@ -200,6 +200,26 @@ int b200ocr_det_pages(b200ocr_engine* e, const uint8_t* const* pages, const int*
     });
 }
 
+int b200ocr_det_submit(b200ocr_engine* e, const uint8_t* const* pages, const int* hs, const int* ws,
+                       const int* strides, int n, const b200ocr_det_params* p, int* ticket_out) {
+    return guarded(e, [&]() {
+        if (!pages || !hs || !ws || !p || n <= 0 || !ticket_out) throw std::runtime_error("bad argument to det_submit");
+        Model* m = need(e, B200OCR_DET);
+        std::lock_guard<std::mutex> lk(e->mu);
+        *ticket_out = e->stages->det_submit(m, pages, hs, ws, strides, n, *p);
+        return B200OCR_OK;
+    });
+}
+
+int b200ocr_det_collect(b200ocr_engine* e, int ticket, float* boxes_out, int max_boxes, int* n_boxes_out) {
+    return guarded(e, [&]() {
+        if (!boxes_out || !n_boxes_out || max_boxes <= 0) throw std::runtime_error("bad argument to det_collect");
+        std::lock_guard<std::mutex> lk(e->mu);
+        e->stages->det_collect(ticket, boxes_out, max_boxes, n_boxes_out);
+        return B200OCR_OK;
+    });
+}
+
 int b200ocr_crop_boxes(b200ocr_engine* e, const uint8_t* bgr, int h, int w, int row_stride, const float* boxes,
                        int n, uint8_t* crops_out, size_t crops_capacity, int* crop_dims_out) {
     return guarded(e, [&]() {
@@ -398,6 +418,17 @@ int b200ocr_det_resident_run(b200ocr_engine* e, const b200ocr_det_params* p, int
         Model* m = need(e, B200OCR_DET);
         std::lock_guard<std::mutex> lk(e->mu);
         e->stages->resident_run(m, *p, iters, ms_total, n_boxes_total, net_ms_total);
+        return B200OCR_OK;
+    });
+}
+
+int b200ocr_det_resident_stream(b200ocr_engine* e, const b200ocr_det_params* p, int iters, int pages_per_step,
+                                float* ms_total, int* n_boxes_total) {
+    return guarded(e, [&]() {
+        if (!p || iters <= 0) throw std::runtime_error("bad argument to det_resident_stream");
+        Model* m = need(e, B200OCR_DET);
+        std::lock_guard<std::mutex> lk(e->mu);
+        e->stages->resident_stream(m, *p, iters, pages_per_step, ms_total, n_boxes_total);
         return B200OCR_OK;
     });
 }

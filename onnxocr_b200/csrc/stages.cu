@@ -597,16 +597,16 @@ static int filter_boxes(const int32_t* in, int n, int img_h, int img_w, std::vec
 // staging area by several host threads (a single-threaded pageable cudaMemcpy tops out near 6 GB/s, far below PCIe 5),
 // then DMA'd asynchronously, so the staging copy of the next page overlaps the DMA of this one.  Pinned sources
 // (b200ocr_host_alloc) go straight to the DMA engine.
-void Stages::upload_page(uint8_t* dst, const uint8_t* src, size_t bytes, cudaStream_t st) {
+void Stages::upload_page(uint8_t* dst, const uint8_t* src, size_t bytes, cudaStream_t st, PageStore* store) {
     cudaPointerAttributes attr;
     bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    if (pinned || bytes < ((size_t)1 << 20) || stage_used_ + bytes > stage_cap_) {
+    if (pinned || bytes < ((size_t)1 << 20) || store->used + bytes > store->cap) {
         B200_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
         return;
     }
-    uint8_t* hp = (uint8_t*)h_stage_.p + stage_used_;
-    stage_used_ += (bytes + 4095) & ~(size_t)4095;
+    uint8_t* hp = (uint8_t*)store->h.p + store->used;
+    store->used += (bytes + 4095) & ~(size_t)4095;
     static const int n_threads = [] {
         unsigned hc = std::thread::hardware_concurrency();
         return (int)std::max(1u, std::min(8u, hc / 2));
@@ -625,9 +625,9 @@ void Stages::upload_page(uint8_t* dst, const uint8_t* src, size_t bytes, cudaStr
 }
 
 // All pages of a call go to the device once and stay there until their crops are cut (the warp samples the
-// full-resolution original, predict_system.py:36,51).  plan_pool lays the pool out; det_on_pool uploads each page right
+// full-resolution original, predict_system.py:36,51).  plan_pool lays the pool out; det_enqueue uploads each page right
 // before the sub-batch that needs it is enqueued, so the copy of the next sub-batch overlaps the network of this one.
-void Stages::plan_pool(const int* hs, const int* ws, const int* strides, int n, PagePool* pool) {
+void Stages::plan_pool(const int* hs, const int* ws, const int* strides, int n, PagePool* pool, PageStore* store) {
     pool->off.assign(n, 0);
     pool->stride.assign(n, 0);
     size_t total = 0;
@@ -638,23 +638,53 @@ void Stages::plan_pool(const int* hs, const int* ws, const int* strides, int n, 
         pool->off[i] = total;
         total += ((size_t)hs[i] * pool->stride[i] + 255) & ~(size_t)255;
     }
-    pool->base = (uint8_t*)d_img_.get(total);
-    // pinned staging for pageable sources: the previous call has completed (every entry point drains its streams), so the
-    // area is free; bounded so that a huge batch falls back to direct copies for its tail
-    stage_cap_ = std::min<size_t>(total + (size_t)n * 4096, (size_t)2 << 30);
-    h_stage_.get(stage_cap_);
-    stage_used_ = 0;
+    pool->base = (uint8_t*)store->d.get(total);
+    // pinned staging for pageable sources: the previous user of this store has completed (every synchronous entry point
+    // drains its streams, a streaming slot is reused only after its batch was collected), so the area is free; bounded
+    // so that a huge batch falls back to direct copies for its tail
+    store->cap = std::min<size_t>(total + (size_t)n * 4096, (size_t)2 << 30);
+    store->h.get(store->cap);
+    store->used = 0;
+}
+
+// One lane's sub-batch: boxes to the host (the only host synchronisation of the det path), reference tail on the host.
+void Stages::det_collect_lane(DetTicket* t, int k) {
+    if (!t->pend[k].active) return;
+    std::vector<int32_t> boxes;
+    std::vector<double> scores;
+    std::vector<int> counts;
+    db_post_collect(&t->pend[k], &boxes, &scores, &counts);
+    const DetChunk& c = t->pend_chunk[k];
+    size_t bo = 0;
+    for (int j = 0; j < c.b; ++j) {
+        int i = t->idx[c.g0 + j];
+        filter_boxes(boxes.data() + bo * 8, counts[j], c.h, c.w, &t->boxes[i]);
+        bo += counts[j];
+    }
+}
+
+void Stages::det_finish(DetTicket* t) {
+    for (int k = 0; k < kLanesPerSlot; ++k) det_collect_lane(t, (t->turn + k) % kLanesPerSlot);   // oldest first
+}
+
+void Stages::drain_tickets() {
+    for (auto& t : tickets_)
+        if (t.busy) det_finish(&t);
 }
 
 // TextDetector.__call__ for a batch of pages: equal-shaped pages run as sub-batches of up to 8 that alternate between
-// two lanes (stream + activation slab + DBPostProcess scratch each).  A lane's boxes are collected (the only host
-// synchronisation) just before the lane is reused, i.e. while the other lane's network is executing.
-// boxes[i] receives page i's filtered float32 quads (cv2 contour order), 8 floats each.
-void Stages::det_on_pool(Model* det, const PagePool& pool, const uint8_t* const* pages, const int* hs, const int* ws, int n,
-                         const b200ocr_det_params& p, std::vector<std::vector<float>>* boxes_pp, float* probmap_out,
-                         size_t probmap_capacity, int* probmap_dims_out) {
-    boxes_pp->assign(n, {});
-    std::vector<int> idx(n);
+// the two lanes of the ticket's slot (stream + activation slab + DBPostProcess scratch each).  A lane's boxes are
+// collected just before the lane is reused, i.e. while the other lane's network is executing; whatever is still pending
+// when this returns is collected by det_finish.  t->boxes[i] receives page i's filtered float32 quads (cv2 contour
+// order), 8 floats each.
+void Stages::det_enqueue(DetTicket* t, Model* det, const PagePool& pool, const uint8_t* const* pages, const int* hs,
+                         const int* ws, int n, const b200ocr_det_params& p, float* probmap_out, size_t probmap_capacity,
+                         int* probmap_dims_out, cudaStream_t resident_src) {
+    t->n = n;
+    t->turn = 0;
+    t->boxes.assign(n, {});
+    std::vector<int>& idx = t->idx;
+    idx.resize(n);
     std::iota(idx.begin(), idx.end(), 0);
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
         return hs[a] != hs[b] ? hs[a] < hs[b] : ws[a] < ws[b];
@@ -670,33 +700,21 @@ void Stages::det_on_pool(Model* det, const PagePool& pool, const uint8_t* const*
         }
     }
     if (probmap_out && prob_off[n] > probmap_capacity) throw std::runtime_error("probability-map buffer too small");
-    // resident pages were uploaded on the engine stream: make them visible to the lanes.  When the lanes upload the
+    const int lane0 = t->slot * kLanesPerSlot;
+    // resident pages were uploaded on another stream: make them visible to the lanes.  When the lanes upload the
     // pages themselves nothing on the engine stream concerns them, and NOT waiting lets this detection overlap the
     // recogniser work of the previous wave that is still queued there.
-    if (!pages) {
-        B200_CUDA_CHECK(cudaEventRecord(ev_fork_, st_));
-        for (int l = 0; l < kDetLanes; ++l) B200_CUDA_CHECK(cudaStreamWaitEvent(det_st_[l], ev_fork_, 0));
+    if (!pages && resident_src) {
+        B200_CUDA_CHECK(cudaEventRecord(ev_fork_, resident_src));
+        for (int l = 0; l < kLanesPerSlot; ++l) B200_CUDA_CHECK(cudaStreamWaitEvent(det_st_[lane0 + l], ev_fork_, 0));
     }
 
-    struct Chunk { int g0, b, h, w; };
-    DbPending pend[kDetLanes];
-    Chunk pend_chunk[kDetLanes];
-    auto collect = [&](int lane) {
-        if (!pend[lane].active) return;
-        std::vector<int32_t> boxes;
-        std::vector<double> scores;
-        std::vector<int> counts;
-        db_post_collect(&pend[lane], &boxes, &scores, &counts);
-        const Chunk& c = pend_chunk[lane];
-        size_t bo = 0;
-        for (int k = 0; k < c.b; ++k) {
-            int i = idx[c.g0 + k];
-            filter_boxes(boxes.data() + bo * 8, counts[k], c.h, c.w, &(*boxes_pp)[i]);
-            bo += counts[k];
-        }
-    };
-    const int max_group = 16, sub = 8;
-    int turn = 0;
+    static const int sub = [] {
+        const char* e = getenv("B200OCR_DET_SUB");
+        int v = e ? atoi(e) : 8;
+        return v >= 1 && v <= 16 ? v : 8;
+    }();
+    const int max_group = 16;
     for (int g0 = 0; g0 < n;) {
         int g1 = g0;
         while (g1 < n && hs[idx[g1]] == hs[idx[g0]] && ws[idx[g1]] == ws[idx[g0]] && g1 - g0 < max_group) ++g1;
@@ -704,32 +722,36 @@ void Stages::det_on_pool(Model* det, const PagePool& pool, const uint8_t* const*
         const int step = group > sub + sub / 2 ? sub : group;          // 16 pages -> 8 + 8; up to 12 stay together
         for (int c0 = g0; c0 < g1; c0 += step) {
             const int b = std::min(step, g1 - c0);
-            const int lane = turn++ % kDetLanes;
-            collect(lane);                                            // frees the lane's scratch, slab and job table
+            const int k = t->turn++ % kLanesPerSlot;
+            const int lane = lane0 + k;
+            det_collect_lane(t, k);                                   // frees the lane's scratch, slab and job table
             cudaStream_t st = det_st_[lane];
             const DetGeom& g = geo[idx[c0]];
             const int h = hs[idx[c0]], w = ws[idx[c0]];
             std::vector<ResizeJob> jobs(b);
-            for (int k = 0; k < b; ++k) {
-                int i = idx[c0 + k];
+            for (int j = 0; j < b; ++j) {
+                int i = idx[c0 + j];
                 if (pages) {
                     if (!pages[i]) throw std::runtime_error("bad argument: null page at index " + std::to_string(i));
-                    upload_page(pool.base + pool.off[i], pages[i], (size_t)h * pool.stride[i], st);
+                    upload_page(pool.base + pool.off[i], pages[i], (size_t)h * pool.stride[i], st, &t->store);
                 }
-                jobs[k] = make_job(pool.base + pool.off[i], h, w, pool.stride[i], g.pad_h, g.pad_w, g.dst_h, g.dst_w, 0);
+                jobs[j] = make_job(pool.base + pool.off[i], h, w, pool.stride[i], g.pad_h, g.pad_w, g.dst_h, g.dst_w, 0);
             }
             ResizeJob* d_jobs = (ResizeJob*)d_lane_jobs_[lane].get(sizeof(ResizeJob) * max_group);
             B200_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(ResizeJob) * b, cudaMemcpyHostToDevice, st));
             Plan* pl = det->plan_for(b, g.dst_h, g.dst_w, false, /*own_arena=*/2, /*slot=*/lane);
             if (!pl->own_arena) {
                 // The private-slab budget is exhausted and this plan lives in the model's shared slab: it must not run
-                // while another lane's network may be using that slab.  Drain the other lanes first; a later shared-slab
-                // chunk on another lane drains this one the same way, so shared-slab chunks run strictly one at a time.
+                // while anything else may be using that slab (another lane's network, or the DBPostProcess tail of
+                // another sub-batch, which reads the probability map out of the slab).  Finish everything else first; a
+                // later shared-slab chunk drains this one the same way, so shared-slab chunks run strictly one at a time.
+                for (int l = 0; l < kLanesPerSlot; ++l)
+                    if (l != k) det_collect_lane(t, l);
+                for (auto& o : tickets_)
+                    if (&o != t && o.busy) det_finish(&o);
+                if (t != &sync_ticket_) det_finish(&sync_ticket_);
                 for (int l = 0; l < kDetLanes; ++l)
-                    if (l != lane) {
-                        collect(l);
-                        B200_CUDA_CHECK(cudaStreamSynchronize(det_st_[l]));
-                    }
+                    if (l != lane) B200_CUDA_CHECK(cudaStreamSynchronize(det_st_[l]));
             }
             dim3 grid((unsigned)ceil_div(g.dst_w, 256), g.dst_h, b);
             if (det->precision() == PREC_BF16)
@@ -741,19 +763,30 @@ void Stages::det_on_pool(Model* det, const PagePool& pool, const uint8_t* const*
             B200_CUDA_CHECK(cudaGetLastError());
             // the dense output is [b,1,H,W] fp32 == the probability maps
             if (probmap_out)
-                for (int k = 0; k < b; ++k)
-                    B200_CUDA_CHECK(cudaMemcpyAsync(probmap_out + prob_off[idx[c0 + k]],
-                                                    pl->out_dense + (size_t)k * g.dst_h * g.dst_w,
+                for (int j = 0; j < b; ++j)
+                    B200_CUDA_CHECK(cudaMemcpyAsync(probmap_out + prob_off[idx[c0 + j]],
+                                                    pl->out_dense + (size_t)j * g.dst_h * g.dst_w,
                                                     (size_t)g.dst_h * g.dst_w * sizeof(float), cudaMemcpyDeviceToHost, st));
             std::vector<int> sh(b, h), sw(b, w);
-            db_post_enqueue(lane, pl->out_dense, b, g.dst_h, g.dst_w, sh.data(), sw.data(), p, p.max_candidates, &pend[lane]);
-            pend_chunk[lane] = {c0, b, h, w};
+            db_post_enqueue(lane, pl->out_dense, b, g.dst_h, g.dst_w, sh.data(), sw.data(), p, p.max_candidates, &t->pend[k]);
+            t->pend_chunk[k] = {c0, b, h, w};
         }
         g0 = g1;
     }
-    for (int k = 0; k < kDetLanes; ++k) collect((turn + k) % kDetLanes);   // oldest first
+}
+
+// The synchronous form used by det_pages / ocr_pages / resident_run: enqueue on the lanes of slot 0, collect everything.
+void Stages::det_on_pool(Model* det, const PagePool& pool, const uint8_t* const* pages, const int* hs, const int* ws, int n,
+                         const b200ocr_det_params& p, std::vector<std::vector<float>>* boxes_pp, float* probmap_out,
+                         size_t probmap_capacity, int* probmap_dims_out) {
+    drain_tickets();                                   // streaming batches may own the lanes of slot 0
+    DetTicket* t = &sync_ticket_;
+    t->slot = 0;
+    det_enqueue(t, det, pool, pages, hs, ws, n, p, probmap_out, probmap_capacity, probmap_dims_out, st_);
+    det_finish(t);
+    boxes_pp->swap(t->boxes);
     // later work on the engine stream (crops, cls, rec) reads the pages the lanes uploaded
-    for (int l = 0; l < kDetLanes; ++l) {
+    for (int l = 0; l < kLanesPerSlot; ++l) {
         B200_CUDA_CHECK(cudaEventRecord(ev_det_done_[l], det_st_[l]));
         B200_CUDA_CHECK(cudaStreamWaitEvent(st_, ev_det_done_[l], 0));
     }
@@ -764,8 +797,9 @@ void Stages::det_pages(Model* det, const uint8_t* const* pages, const int* hs, c
                        const b200ocr_det_params& p, float* boxes_out, int max_boxes, int* n_boxes_out, float* probmap_out,
                        size_t probmap_capacity, int* probmap_dims_out) {
     if (n == 0) return;
+    drain_tickets();
     PagePool pool;
-    plan_pool(hs, ws, strides, n, &pool);
+    plan_pool(hs, ws, strides, n, &pool, &sync_ticket_.store);
     std::vector<std::vector<float>> boxes;
     det_on_pool(det, pool, pages, hs, ws, n, p, &boxes, probmap_out, probmap_capacity, probmap_dims_out);
     B200_CUDA_CHECK(cudaStreamSynchronize(st_));
@@ -774,6 +808,36 @@ void Stages::det_pages(Model* det, const uint8_t* const* pages, const int* hs, c
         if (m > max_boxes) throw std::runtime_error("box capacity too small: page " + std::to_string(i) + " has " + std::to_string(m));
         n_boxes_out[i] = m;
         if (m) memcpy(boxes_out + (size_t)i * max_boxes * 8, boxes[i].data(), boxes[i].size() * sizeof(float));
+    }
+}
+
+// ---- streaming detection
+int Stages::det_submit(Model* det, const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n,
+                       const b200ocr_det_params& p) {
+    DetTicket* t = nullptr;
+    for (auto& c : tickets_)
+        if (!c.busy) { t = &c; break; }
+    if (!t) throw std::runtime_error("capacity: " + std::to_string(kDetSlots) + " det batches are already in flight (collect one first)");
+    if (sync_ticket_.busy) throw std::runtime_error("internal: synchronous det call in progress");
+    t->slot = (int)(t - tickets_);
+    t->id = ++ticket_seq_ * kDetSlots + t->slot;
+    PagePool pool;
+    plan_pool(hs, ws, strides, n, &pool, &t->store);
+    det_enqueue(t, det, pool, pages, hs, ws, n, p, nullptr, 0, nullptr, nullptr);
+    t->busy = true;
+    return t->id;
+}
+
+void Stages::det_collect(int ticket, float* boxes_out, int max_boxes, int* n_boxes_out) {
+    DetTicket* t = ticket >= 0 ? &tickets_[ticket % kDetSlots] : nullptr;
+    if (!t || !t->busy || t->id != ticket) throw std::runtime_error("bad argument: unknown or already collected det ticket");
+    det_finish(t);
+    t->busy = false;
+    for (int i = 0; i < t->n; ++i) {
+        int m = (int)(t->boxes[i].size() / 8);
+        if (m > max_boxes) throw std::runtime_error("box capacity too small: page " + std::to_string(i) + " has " + std::to_string(m));
+        n_boxes_out[i] = m;
+        if (m) memcpy(boxes_out + (size_t)i * max_boxes * 8, t->boxes[i].data(), t->boxes[i].size() * sizeof(float));
     }
 }
 
@@ -836,7 +900,8 @@ void Stages::ocr_pages(Model* det, Model* cls, Model* rec, const uint8_t* const*
     for (float& v : ocr_ms) v = 0.f;
     auto t0 = now();
     PagePool pool;
-    plan_pool(hs, ws, strides, n, &pool);
+    drain_tickets();
+    plan_pool(hs, ws, strides, n, &pool, &sync_ticket_.store);
     ocr_ms[0] = ms_since(t0);
     const bool use_cls = op.use_angle_cls && cls != nullptr;
     const int img_h = 48, img_w0 = 320;
@@ -1084,6 +1149,51 @@ void Stages::resident_run(Model* det, const b200ocr_det_params& p, int iters, fl
     if (ms_total) *ms_total = total;
     if (n_boxes_total) *n_boxes_total = boxes_total;
     if (net_ms_total) *net_ms_total = 0.f;             // the lanes overlap network and post-processing: see b200ocr_time_plan
+}
+
+// The same benchmark through the streaming path: two batches in flight, step k on pages [k*pps, (k+1)*pps) modulo the
+// resident set (upload more page sets than the 126 MB L2 holds and no flush is needed between steps).
+void Stages::resident_stream(Model* det, const b200ocr_det_params& p, int iters, int pps, float* ms_total, int* n_boxes_total) {
+    const int n = (int)res_h_.size();
+    if (n == 0) throw std::runtime_error("bad argument: no resident pages uploaded");
+    if (pps <= 0 || pps > n || n % pps) throw std::runtime_error("bad argument: pages_per_step must divide the resident page count");
+    drain_tickets();
+    for (auto& t : tickets_)
+        if (t.busy) throw std::runtime_error("bad argument: collect the det batches in flight first");
+    int boxes_total = 0;
+    auto finish = [&](DetTicket* t) {
+        det_finish(t);
+        t->busy = false;
+        for (auto& b : t->boxes) boxes_total += (int)(b.size() / 8);
+    };
+    B200_CUDA_CHECK(cudaEventRecord(ev_[0], st_));
+    for (int it = 0; it < iters; ++it) {
+        DetTicket* t = &tickets_[it % kDetSlots];
+        if (t->busy) finish(t);
+        t->slot = it % kDetSlots;
+        const int first = (int)(((int64_t)it * pps) % n);
+        PagePool pool;
+        pool.base = (uint8_t*)d_res_.p;
+        pool.off.assign(res_off_.begin() + first, res_off_.begin() + first + pps);
+        pool.stride.assign(res_stride_.begin() + first, res_stride_.begin() + first + pps);
+        det_enqueue(t, det, pool, nullptr, res_h_.data() + first, res_w_.data() + first, pps, p, nullptr, 0, nullptr,
+                    it < kDetSlots ? st_ : nullptr);
+        t->busy = true;
+    }
+    for (int k = 0; k < kDetSlots; ++k) {
+        DetTicket* t = &tickets_[(iters + k) % kDetSlots];
+        if (t->busy) finish(t);
+    }
+    for (int l = 0; l < kDetLanes; ++l) {
+        B200_CUDA_CHECK(cudaEventRecord(ev_det_done_[l], det_st_[l]));
+        B200_CUDA_CHECK(cudaStreamWaitEvent(st_, ev_det_done_[l], 0));
+    }
+    B200_CUDA_CHECK(cudaEventRecord(ev_[3], st_));
+    B200_CUDA_CHECK(cudaEventSynchronize(ev_[3]));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev_[0], ev_[3]);
+    if (ms_total) *ms_total = ms;
+    if (n_boxes_total) *n_boxes_total = boxes_total;
 }
 
 }  // namespace b200ocr

@@ -65,6 +65,16 @@ public:
     void resident_upload(const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n);
     void resident_run(Model* det, const b200ocr_det_params& p, int iters, float* ms_total, int* n_boxes_total,
                       float* net_ms_total);
+    // Streaming detection: det_submit enqueues a batch (uploads, network, DBPostProcess) on a free slot (two det lanes
+    // of its own) and returns without waiting for the GPU; det_collect blocks until that batch's boxes are on the host.
+    // With two batches in flight the upload and network of batch k+1 overlap the DBPostProcess tail and the box
+    // read-back of batch k.  Host page buffers must stay valid until the batch is collected.
+    int det_submit(Model* det, const uint8_t* const* pages, const int* hs, const int* ws, const int* strides, int n,
+                   const b200ocr_det_params& p);
+    void det_collect(int ticket, float* boxes_out, int max_boxes, int* n_boxes_out);
+    // the resident benchmark through the streaming path: step k runs pages [k*pages_per_step ...) (mod the resident set)
+    void resident_stream(Model* det, const b200ocr_det_params& p, int iters, int pages_per_step, float* ms_total,
+                         int* n_boxes_total);
 
     void l2_flush();
 
@@ -80,15 +90,16 @@ private:
         std::vector<size_t> off;
         std::vector<int> stride;
     };
-    void upload_page(uint8_t* dst, const uint8_t* src, size_t bytes, cudaStream_t st);
-    PinBuf h_stage_;
-    size_t stage_cap_ = 0, stage_used_ = 0;
-    void plan_pool(const int* hs, const int* ws, const int* strides, int n, PagePool* pool);
-    // pages == nullptr: the pool already holds the pixels (resident benchmark path)
-    void det_on_pool(Model* det, const PagePool& pool, const uint8_t* const* pages, const int* hs, const int* ws, int n,
-                     const b200ocr_det_params& p, std::vector<std::vector<float>>* boxes_pp, float* probmap_out,
-                     size_t probmap_capacity, int* probmap_dims_out);
-    // Two det lanes (stream + DBPostProcess scratch + job table each): while the host waits for the boxes of one
+    // device page pool + pinned staging area of one call (the synchronous entry points share one, every streaming slot
+    // has its own)
+    struct PageStore {
+        DevBuf d;
+        PinBuf h;
+        size_t cap = 0, used = 0;
+    };
+    void upload_page(uint8_t* dst, const uint8_t* src, size_t bytes, cudaStream_t st, PageStore* store);
+    void plan_pool(const int* hs, const int* ws, const int* strides, int n, PagePool* pool, PageStore* store);
+    // Det lanes (stream + DBPostProcess scratch + job table each): while the host waits for the boxes of one
     // sub-batch, the network of the next one is already running on the other lane.
     struct DbPending {
         int lane = 0, n = 0, h = 0, w = 0, maxc = 0, nt = 0;
@@ -96,12 +107,37 @@ private:
         b200ocr_det_params p;
         bool active = false;
     };
+    static constexpr int kLanesPerSlot = 2;
+    static constexpr int kDetSlots = 2;                      // batches in flight through det_submit
+    static constexpr int kDetLanes = kLanesPerSlot * kDetSlots;
+    struct DetChunk { int g0, b, h, w; };
+    struct DetTicket {                                       // the host-side state of one enqueued batch
+        bool busy = false;                                   // submitted, not yet collected
+        int slot = 0, id = 0, n = 0, turn = 0;
+        std::vector<int> idx;
+        std::vector<std::vector<float>> boxes;
+        DbPending pend[kLanesPerSlot];
+        DetChunk pend_chunk[kLanesPerSlot];
+        PageStore store;
+    };
+    DetTicket tickets_[kDetSlots];
+    DetTicket sync_ticket_;                                  // det_on_pool (lanes of slot 0)
+    int ticket_seq_ = 0;
+    // pages == nullptr: the pool already holds the pixels (resident benchmark path)
+    void det_enqueue(DetTicket* t, Model* det, const PagePool& pool, const uint8_t* const* pages, const int* hs, const int* ws,
+                     int n, const b200ocr_det_params& p, float* probmap_out, size_t probmap_capacity, int* probmap_dims_out,
+                     cudaStream_t resident_src);
+    void det_collect_lane(DetTicket* t, int k);
+    void det_finish(DetTicket* t);
+    void drain_tickets();                                    // finish every streaming batch (results stay in its ticket)
+    void det_on_pool(Model* det, const PagePool& pool, const uint8_t* const* pages, const int* hs, const int* ws, int n,
+                     const b200ocr_det_params& p, std::vector<std::vector<float>>* boxes_pp, float* probmap_out,
+                     size_t probmap_capacity, int* probmap_dims_out);
     void db_post_enqueue(int lane, const float* d_prob, int n, int h, int w, const int* src_hs, const int* src_ws,
                          const b200ocr_det_params& p, int capacity, DbPending* pend);
     void db_post_collect(DbPending* pend, std::vector<int32_t>* boxes, std::vector<double>* scores, std::vector<int>* counts);
-    static constexpr int kDetLanes = 2;
     cudaStream_t det_st_[kDetLanes];
-    DbWork* db_lane_[kDetLanes] = {nullptr, nullptr};
+    DbWork* db_lane_[kDetLanes] = {};
     DevBuf d_lane_jobs_[kDetLanes];
     cudaEvent_t ev_det_done_[kDetLanes];
     void rec_batch(Model* rec, const struct ResizeJob* d_jobs, const int* d_slots, int b, int img_h, int W, int max_len,

@@ -1,0 +1,84 @@
+"""GPU: the streaming det entry points (b200ocr_det_submit / b200ocr_det_collect, two batches in flight on separate
+lane pairs) return exactly what the synchronous b200ocr_det_pages returns, interleave correctly with synchronous calls,
+and reject misuse (a third batch in flight, a stale ticket) with an error instead of corrupting a slot."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _batches():
+    from onnxocr_b200 import synth_pages
+    shapes = [(480, 640), (512, 704), (320, 480)]
+    out = []
+    for k in range(5):                       # 5 batches: every slot is reused, the last one drains alone
+        n = [16, 3, 9, 12, 1][k]             # 16 -> two sub-batches of 8 (both lanes), the others one lane / mixed groups
+        pages = []
+        for i in range(n):
+            h, w = shapes[(k + (i if k == 2 else 0)) % 3]
+            pages.append(synth_pages.render_page(h, w, 6, seed=1000 + 37 * k + i)[0])
+        out.append(pages)
+    return out
+
+
+def _same(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("which", ["engine_bf16", "engine_fp32"])
+def test_stream_equals_sync(which, request):
+    eng = request.getfixturevalue(which)
+    batches = _batches()
+    ref = [eng.det_pages(b) for b in batches]
+    assert sum(len(x) for r in ref for x in r) > 100
+    for rep in range(2):                     # second pass replays the CUDA graphs of the slot plans
+        got = list(eng.det_pages_stream(batches))
+        assert len(got) == len(ref)
+        for g, r in zip(got, ref):
+            _same(g, r)
+
+
+def test_stream_interleaved_with_sync_calls(engine_bf16):
+    eng = engine_bf16
+    batches = _batches()
+    ref = [eng.det_pages(b) for b in batches]
+    t0 = eng.det_submit(batches[0])
+    t1 = eng.det_submit(batches[1])
+    mid = eng.det_pages(batches[2])          # a synchronous call drains the batches in flight; their results are kept
+    _same(mid, ref[2])
+    _same(eng.det_collect(t1), ref[1])       # collecting out of order is allowed
+    _same(eng.det_collect(t0), ref[0])
+    # the fused Level-C entry uses the same lanes
+    t3 = eng.det_submit(batches[3])
+    lines = eng.ocr_pages(batches[4])
+    assert len(lines) == len(batches[4])
+    _same(eng.det_collect(t3), ref[3])
+
+
+def test_stream_misuse_is_an_error(engine_bf16):
+    eng = engine_bf16
+    batches = _batches()
+    t0 = eng.det_submit(batches[1])
+    t1 = eng.det_submit(batches[4])
+    with pytest.raises(RuntimeError, match="in flight"):
+        eng.det_submit(batches[1])
+    a = eng.det_collect(t0)
+    with pytest.raises(RuntimeError, match="ticket"):
+        eng.det_collect(t0)                  # already collected
+    with pytest.raises(RuntimeError, match="ticket"):
+        eng.det_collect((12345, t1[1]))
+    b = eng.det_collect(t1)
+    _same(a, eng.det_pages(batches[1]))
+    _same(b, eng.det_pages(batches[4]))
+
+
+def test_resident_stream_counts_the_same_boxes(engine_bf16):
+    from onnxocr_b200 import synth_pages
+    eng = engine_bf16
+    pages = synth_pages.det_pages_c2(8, 480, 12, seed=5)
+    eng.det_resident_upload(pages)
+    _, n_sync, _ = eng.det_resident_run(iters=1)
+    ms, n_stream = eng.det_resident_stream(iters=6, pages_per_step=4)     # 6 steps of 4 pages = the 8 pages three times
+    assert n_sync > 20 and n_stream == 3 * n_sync and ms > 0
