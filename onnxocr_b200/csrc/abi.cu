@@ -111,6 +111,14 @@ int b200ocr_load_onnx(b200ocr_engine* e, int kind, const char* path, int precisi
         if (kind < 0 || kind > 2 || !path) throw std::runtime_error("bad argument to load_onnx");
         std::lock_guard<std::mutex> lk(e->mu);
         e->models[kind].reset(new Model(path, precision));
+        if (kind == B200OCR_DET) {
+            // det plans read the u8 pages directly (pre-processing fused into the stem) unless B200OCR_FUSED_PRE=0
+            float nv[8];
+            Stages::det_norm_values(nv);
+            e->models[kind]->set_pre_norm(nv);
+            const char* f = getenv("B200OCR_FUSED_PRE");
+            e->models[kind]->fused_pre_default = !(f && f[0] == '0');
+        }
         return B200OCR_OK;
     });
 }
@@ -308,7 +316,7 @@ int b200ocr_plan_stats(b200ocr_engine* e, int kind, int n, int h, int w, double*
     return guarded(e, [&]() {
         Model* m = need(e, kind);
         std::lock_guard<std::mutex> lk(e->mu);
-        Plan* p = m->plan_for(n, h, w);
+        Plan* p = m->plan_for(n, h, w, false, 0, 0, m->fused_pre_default);
         if (flops) *flops = p->flops;
         if (launches) *launches = p->launches;
         if (arena_bytes) *arena_bytes = (double)p->arena_bytes;
@@ -323,7 +331,7 @@ int b200ocr_profile_plan(b200ocr_engine* e, int kind, int n, int h, int w, int i
         std::lock_guard<std::mutex> lk(e->mu);
         std::vector<float> ms;
         m->profile(n, h, w, iters < 1 ? 1 : iters, e->stream, &ms);
-        Plan* p = m->plan_for(n, h, w);
+        Plan* p = m->plan_for(n, h, w, false, 0, 0, m->fused_pre_default);
         int ns = (int)ms.size();
         if (ns > capacity) throw std::runtime_error("profile buffers too small: need " + std::to_string(ns));
         size_t off = 0;
@@ -349,7 +357,7 @@ int b200ocr_time_plan(b200ocr_engine* e, int kind, int n, int h, int w, int head
         Model* m = need(e, kind);
         if (!ms_avg || iters < 1) throw std::runtime_error("bad argument to time_plan");
         std::lock_guard<std::mutex> lk(e->mu);
-        Plan* p = m->plan_for(n, h, w, head != 0);
+        Plan* p = m->plan_for(n, h, w, head != 0, 0, 0, m->fused_pre_default);
         for (int i = 0; i < 3; ++i) p->launch(e->stream);          // warm: lazy init, graph capture
         cudaEvent_t a, b;
         B200_CUDA_CHECK(cudaEventCreate(&a));

@@ -445,8 +445,8 @@ struct Arena {
 };
 }  // namespace
 
-Plan* Model::plan_for(int n, int h, int w, bool head, int own_arena, int slot) {
-    std::vector<int> key{n, h, w, head ? 1 : 0, own_arena, slot};
+Plan* Model::plan_for(int n, int h, int w, bool head, int own_arena, int slot, bool fused_pre) {
+    std::vector<int> key{n, h, w, head ? 1 : 0, own_arena, slot, fused_pre ? 1 : 0};
     auto it = plans_.find(key);
     if (it != plans_.end()) return it->second.get();
     if (plans_.size() >= 768) {                         // bounded cache (dynamic rec widths x batch sizes)
@@ -458,15 +458,17 @@ Plan* Model::plan_for(int n, int h, int w, bool head, int own_arena, int slot) {
         plans_.clear();
         private_bytes_ = 0;
     }
-    std::unique_ptr<Plan> p = build_plan(n, h, w, head, own_arena);
+    std::unique_ptr<Plan> p = build_plan(n, h, w, head, own_arena, fused_pre);
     Plan* raw = p.get();
     plans_[key] = std::move(p);
     return raw;
 }
 
-std::unique_ptr<Plan> Model::build_plan(int n, int h, int w, bool head, int own_arena) {
+std::unique_ptr<Plan> Model::build_plan(int n, int h, int w, bool head, int own_arena, bool fused_pre) {
     std::unique_ptr<Plan> p(new Plan());
     p->head_mode = head;
+    p->fused_pre = fused_pre;
+    for (int k = 0; k < 8; ++k) p->pre_norm[k] = pre_norm_[k];
     p->model_arena = &arena_;
     p->n = n;
     p->h = h;
@@ -934,6 +936,48 @@ void Model::build_steps(Plan& p) {
                     break;
                 }
                 int w_ld = dw.ColsW;
+                // ---- pre-processing fused into the stem (plans built with fused_pre): u8 pages -> stem output
+                if (p.fused_pre && in == p.in_val && !convt && !c.is_linear && iv.c == 3 && iv.cp == 4 && c.cout == 16 &&
+                    cp.CoutP == 16 && c.kh == 3 && c.kw == 3 && c.sh == 2 && c.sw == 2 && c.pt == 1 && c.pl == 1 &&
+                    nuse[g.input_name] == 1) {
+                    std::vector<float> hw((size_t)36 * dw.ColsW), hb(16);
+                    B200_CUDA_CHECK(cudaMemcpy(hw.data(), dw.w, hw.size() * sizeof(float), cudaMemcpyDeviceToHost));
+                    B200_CUDA_CHECK(cudaMemcpy(hb.data(), dw.bias, 16 * sizeof(float), cudaMemcpyDeviceToHost));
+                    StemW sw;
+                    for (int tap = 0; tap < 9; ++tap)
+                        for (int ci = 0; ci < 3; ++ci)
+                            for (int co = 0; co < 16; ++co) sw.w[tap * 3 + ci][co] = hw[(size_t)(tap * 4 + ci) * dw.ColsW + co];
+                    for (int co = 0; co < 16; ++co) sw.b[co] = hb[co];
+                    // the job table the stages overwrite before every launch; until then every image reads a plan-owned
+                    // grey page at identity scale (profile_plan / time_plan replay the plan without a caller)
+                    uint8_t* dummy = nullptr;
+                    ResizeJob* jobs = nullptr;
+                    B200_CUDA_CHECK(cudaMalloc(&dummy, (size_t)iv.h * iv.w * 3));
+                    p.owned.emplace_back(dummy, [](void* q) { cudaFree(q); });
+                    B200_CUDA_CHECK(cudaMemset(dummy, 0x80, (size_t)iv.h * iv.w * 3));
+                    B200_CUDA_CHECK(cudaMalloc(&jobs, sizeof(ResizeJob) * iv.n));
+                    p.owned.emplace_back(jobs, [](void* q) { cudaFree(q); });
+                    std::vector<ResizeJob> hj(iv.n);
+                    for (auto& j : hj) {
+                        j.src.p = dummy; j.src.h = iv.h; j.src.w = iv.w; j.src.stride = iv.w * 3; j.src.ph = iv.h; j.src.pw = iv.w;
+                        j.src.rot180 = 0; j.dh = iv.h; j.dw = iv.w; j.scale_y = 1.0; j.scale_x = 1.0;
+                    }
+                    B200_CUDA_CHECK(cudaMemcpy(jobs, hj.data(), sizeof(ResizeJob) * iv.n, cudaMemcpyHostToDevice));
+                    p.pre_jobs = jobs;
+                    const int tiles_x = (int)ceil_div(Wo, kPsTW), tiles_y = (int)ceil_div(Ho, kPsTH), tiles = tiles_x * tiles_y * iv.n;
+                    cost_bytes = (double)iv.n * iv.h * iv.w * 3 + vbytes(out) + 27.0 * 16 * 4;
+                    const int ih = iv.h, iw = iv.w;
+                    emit("pre+stem " + c.name, [=](cudaStream_t st) {
+                        NormP nrm;
+                        nrm.mul = pp->pre_norm[0];
+                        for (int k = 0; k < 3; ++k) { nrm.sub[k] = pp->pre_norm[1 + k]; nrm.div[k] = pp->pre_norm[4 + k]; }
+                        nrm.rec_style = (int)pp->pre_norm[7];
+                        launch_pdl(pre_stem_kernel<T>, (unsigned)std::min(tiles, 148 * 8), 256, 0, st, (const ResizeJob*)pp->pre_jobs,
+                                   ih, iw, nrm, sw, (T*)pp->ptr(out), cp, tiles_x, tiles_y, tiles);
+                    });
+                    vid[c.out] = out;
+                    break;
+                }
                 emit(std::string(convt ? "convT " : c.is_linear ? "linear " : "conv ") + c.name, [=](cudaStream_t st) {
                     const T* x = (const T*)pp->ptr(in);
                     T* y = (T*)pp->ptr(out);
@@ -1649,7 +1693,7 @@ void Plan::launch(cudaStream_t st) {
 
 void Model::profile(int n, int h, int w, int iters, cudaStream_t st, std::vector<float>* ms) {
     std::lock_guard<std::mutex> lk(mu_);
-    Plan* p = plan_for(n, h, w);
+    Plan* p = plan_for(n, h, w, false, 0, 0, fused_pre_default);
     size_t ns = p->steps.size();
     std::vector<cudaEvent_t> ev(ns + 1);
     for (auto& e : ev) B200_CUDA_CHECK(cudaEventCreate(&e));

@@ -75,6 +75,12 @@ struct Plan {
     int head_rows = 0, head_T = 0, head_idx_buf = -1, head_prob_buf = -1;
     const int* head_idx() const { return (const int*)bufptr(head_idx_buf); }
     const float* head_prob() const { return (const float*)bufptr(head_prob_buf); }
+    // Pre-processing fused into the stem (plan_for(..., fused_pre)): the first step reads u8 pages through `pre_jobs`
+    // (device table of n ResizeJob, overwritten by the caller before every launch) instead of in_ptr(); pre_jobs stays
+    // null when the graph's first layer is not an eligible stem (the caller then runs resize_norm_kernel as before).
+    bool fused_pre = false;
+    void* pre_jobs = nullptr;
+    float pre_norm[8] = {0, 0, 0, 0, 1, 1, 1, 0};   // NormP: mul, sub[3], div[3], rec_style
     float* out_dense = nullptr;    // dense fp32 logical output (device)
     size_t out_dense_elems = 0;
     bool out_written_dense = false;
@@ -109,7 +115,10 @@ public:
     // overlap on several streams); falls back to the shared slab when the private budget is exhausted.
     //   own_arena: 0 shared slab, 1 private when small, 2 always private; slot distinguishes otherwise identical plans
     //   that must be able to run at the same time (the two det lanes).
-    Plan* plan_for(int n, int h, int w, bool head = false, int own_arena = 0, int slot = 0);
+    Plan* plan_for(int n, int h, int w, bool head = false, int own_arena = 0, int slot = 0, bool fused_pre = false);
+    // normalisation constants of the fused pre-processing (NormP layout: mul, sub[3], div[3], rec_style)
+    void set_pre_norm(const float v[8]) { for (int k = 0; k < 8; ++k) pre_norm_[k] = v[k]; }
+    bool fused_pre_default = false;    // profile / time_plan build the plan the stages actually run
     // Host NCHW fp32 in -> plan launched on `st` (no synchronisation); head selects the fused CTC head variant.
     Plan* launch_host_input(const float* nchw, int n, int c, int h, int w, cudaStream_t st, bool head);
     // Per-step device time (ms, averaged over iters) measured with CUDA events between launches.
@@ -121,7 +130,8 @@ public:
     std::string describe() const;
 
 private:
-    std::unique_ptr<Plan> build_plan(int n, int h, int w, bool head, int own_arena);
+    std::unique_ptr<Plan> build_plan(int n, int h, int w, bool head, int own_arena, bool fused_pre);
+    float pre_norm_[8] = {0, 0, 0, 0, 1, 1, 1, 0};
     size_t private_bytes_ = 0;
     template <typename T> void build_steps(Plan& p);
     std::unique_ptr<CGraph> g_;

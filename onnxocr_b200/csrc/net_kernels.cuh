@@ -4,6 +4,7 @@
 // accumulation is always fp32.
 #pragma once
 #include "common.cuh"
+#include "pre_kernels.cuh"
 
 namespace b200ocr {
 
@@ -1316,6 +1317,98 @@ __global__ void __launch_bounds__(128) conv_stem_kernel(const T* __restrict__ x,
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] = (j + e < p.Cout) ? epi_apply(acc[j + e], p.epi) : 0.f;
             if (j < p.CoutP) ST<T>::st4(dst + j, o);
+        }
+    }
+}
+
+// Pre-processing fused into the stem: u8 BGR page -> (cv2-exact resize) -> normalise -> 3x3 stride-2 pad-1 conv 3 -> 16 ->
+// epilogue -> NHWC activations, in one pass (operators.py:54-138,22-31,170-176 + the first Conv of the graph).  The
+// normalised fp32 / bf16 input tensor (H*W*4 elements per page, written and re-read by the separate kernels) never exists.
+//   * a block owns an 8 x 32 tile of stem outputs: its 17 x 65 input pixels are resized / normalised once into shared
+//     memory (planar fp32, even and odd columns in separate planes so the stride-2 reads of a warp are conflict free);
+//   * the three rounded fp32 operations of NormalizeImage depend only on (channel, u8 value): a 3 x 256 table per block
+//     (the true division is done 768 times per block instead of three times per pixel); in bf16 mode the table holds the
+//     value already rounded to bf16, exactly what resize_norm_kernel would have stored;
+//   * the 432 weights and 16 biases are kernel parameters (constant bank): every FFMA takes its weight as a constant
+//     operand, there is no weight load at all in the loop;
+//   * accumulation order (bias, then ky, kx, ci) is conv_stem_kernel's, so both paths give bit-identical results (taps in
+//     the zero padding add v = 0 here and are skipped there).
+struct StemW {
+    float w[27][16];              // [(ky*3 + kx)*3 + ci][co]
+    float b[16];
+};
+constexpr int kPsTH = 8, kPsTW = 32, kPsRH = 2 * kPsTH + 1, kPsRW = 2 * kPsTW + 1, kPsPitch = 48;
+
+template <typename T>
+__global__ void __launch_bounds__(256) pre_stem_kernel(const ResizeJob* __restrict__ jobs, int IH, int IW, const NormP nrm,
+                                                       const __grid_constant__ StemW W, T* __restrict__ y, const ConvP p,
+                                                       int tiles_x, int tiles_y, int tiles) {
+    pdl_start();
+    __shared__ float lut[3][256];
+    __shared__ float tile[3][kPsRH][2][kPsPitch];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 768; i += 256) {
+        const int c = i >> 8, v = i & 255;
+        float f = norm_px(v, c, nrm);
+        if (sizeof(T) == 2) f = __bfloat162float(__float2bfloat16_rn(f));
+        lut[c][v] = f;
+    }
+    const int lx = tid & 31, ly = tid >> 5;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int tx = t % tiles_x;
+        const int r = t / tiles_x;
+        const int ty = r % tiles_y, n = r / tiles_y;
+        const ResizeJob j = jobs[n];
+        const int iy0 = 2 * ty * kPsTH - 1, ix0 = 2 * tx * kPsTW - 1;
+        __syncthreads();                                    // table ready / previous tile consumed
+        for (int q = tid; q < kPsRH * kPsRW; q += 256) {
+            const int ry = q / kPsRW, rx = q - ry * kPsRW;
+            const int iy = iy0 + ry, ix = ix0 + rx;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+            if ((unsigned)iy < (unsigned)IH && (unsigned)ix < (unsigned)IW && ix < j.dw && iy < j.dh) {
+                int px[3];
+                resize_px(j.src, j.dh, j.dw, j.scale_y, j.scale_x, iy, ix, px);
+                v0 = lut[0][px[0]]; v1 = lut[1][px[1]]; v2 = lut[2][px[2]];
+            }
+            tile[0][ry][rx & 1][rx >> 1] = v0;
+            tile[1][ry][rx & 1][rx >> 1] = v1;
+            tile[2][ry][rx & 1][rx >> 1] = v2;
+        }
+        __syncthreads();
+        const int oy = ty * kPsTH + ly, ox = tx * kPsTW + lx;
+        float acc[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = W.b[c];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    const float v = tile[ci][2 * ly + ky][kx & 1][lx + (kx >> 1)];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) acc[c] = fmaf(v, W.w[(ky * 3 + kx) * 3 + ci][c], acc[c]);
+                }
+        if (oy < p.Ho && ox < p.Wo) {
+            T* dst = y + (((int64_t)n * p.Ho + oy) * p.Wo + ox) * p.CoutP;
+            float o[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) o[c] = c < p.Cout ? epi_apply(acc[c], p.epi) : 0.f;
+            if (sizeof(T) == 2 && p.CoutP == 16) {
+                uint32_t w[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * c], o[2 * c + 1]);
+                    w[c] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                uint4* d4 = reinterpret_cast<uint4*>(dst);
+                d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; c += 4)
+                    if (c < p.CoutP) ST<T>::st4(dst + c, o + c);
+            }
         }
     }
 }

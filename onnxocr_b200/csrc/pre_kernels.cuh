@@ -130,7 +130,7 @@ struct WarpJob {
     size_t out_off;          // byte offset of this crop in the pool
 };
 
-__global__ void __launch_bounds__(256) warp_cubic_kernel(const WarpJob* __restrict__ jobs, const short* __restrict__ tab,
+static __global__ void __launch_bounds__(256) warp_cubic_kernel(const WarpJob* __restrict__ jobs, const short* __restrict__ tab,
                                                           uint8_t* __restrict__ pool) {
     const WarpJob& j = jobs[blockIdx.z];
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) warp_cubic_kernel(const WarpJob* __restri
 }
 
 // ClsPostProcess (cls_postprocess.py:24-26): argmax over the class probabilities, first maximum wins.
-__global__ void cls_argmax_kernel(const float* __restrict__ probs, int b, int ncls, const int* __restrict__ slots,
+static __global__ void cls_argmax_kernel(const float* __restrict__ probs, int b, int ncls, const int* __restrict__ slots,
                                   int* __restrict__ labels, float* __restrict__ scores) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= b) return;
@@ -184,7 +184,7 @@ __global__ void cls_argmax_kernel(const float* __restrict__ probs, int b, int nc
 
 // predict_cls.py:85-88: crops whose label contains '180' with score > cls_thresh are rotated before recognition;
 // the rotation is folded into the rec sampler (SrcView::rot180) instead of rewriting the crop.
-__global__ void rot_patch_kernel(ResizeJob* __restrict__ jobs, const int* __restrict__ slots, int n,
+static __global__ void rot_patch_kernel(ResizeJob* __restrict__ jobs, const int* __restrict__ slots, int n,
                                  const int* __restrict__ labels, const float* __restrict__ scores, unsigned rot_mask,
                                  float thresh) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -197,7 +197,7 @@ __global__ void rot_patch_kernel(ResizeJob* __restrict__ jobs, const int* __rest
 // CTCLabelDecode: argmax/max over classes (first maximum wins, like numpy), then collapse.
 // ---------------------------------------------------------------------------------------------
 // probs: dense fp32 [rows][C]; one block per row.
-__global__ void __launch_bounds__(256) ctc_argmax_kernel(const float* __restrict__ probs, int C, int* __restrict__ idx,
+static __global__ void __launch_bounds__(256) ctc_argmax_kernel(const float* __restrict__ probs, int C, int* __restrict__ idx,
                                                           float* __restrict__ mx) {
     __shared__ float sv[8];
     __shared__ int si[8];
@@ -249,7 +249,7 @@ __device__ inline float np_pairwise_sum(const float* a, int n) {
 
 // One thread per sequence: keep t where idx[t] != idx[t-1] and idx[t] != 0 (rec_postprocess.py:63-69),
 // score = float32 mean of the kept probabilities (rec_postprocess.py:85), 0 when nothing is kept.
-__global__ void ctc_collapse_kernel(const int* __restrict__ idx, const float* __restrict__ mx, int B, int T,
+static __global__ void ctc_collapse_kernel(const int* __restrict__ idx, const float* __restrict__ mx, int B, int T,
                                     const int* __restrict__ dst_slot, int max_len, int* __restrict__ ids_out,
                                     int* __restrict__ lens_out, float* __restrict__ scores_out,
                                     float* __restrict__ scratch) {

@@ -78,6 +78,12 @@ static NormP det_norm() {
     n.rec_style = 0;
     return n;
 }
+void Stages::det_norm_values(float v[8]) {
+    const NormP n = det_norm();
+    v[0] = n.mul;
+    for (int c = 0; c < 3; ++c) { v[1 + c] = n.sub[c]; v[4 + c] = n.div[c]; }
+    v[7] = (float)n.rec_style;
+}
 static NormP rec_norm() {
     NormP n = det_norm();
     n.rec_style = 1;
@@ -737,9 +743,10 @@ void Stages::det_enqueue(DetTicket* t, Model* det, const PagePool& pool, const u
                 }
                 jobs[j] = make_job(pool.base + pool.off[i], h, w, pool.stride[i], g.pad_h, g.pad_w, g.dst_h, g.dst_w, 0);
             }
-            ResizeJob* d_jobs = (ResizeJob*)d_lane_jobs_[lane].get(sizeof(ResizeJob) * max_group);
+            Plan* pl = det->plan_for(b, g.dst_h, g.dst_w, false, /*own_arena=*/2, /*slot=*/lane, det->fused_pre_default);
+            // the lane's previous sub-batch was collected above, so the plan's job table / the lane's table is free
+            ResizeJob* d_jobs = pl->pre_jobs ? (ResizeJob*)pl->pre_jobs : (ResizeJob*)d_lane_jobs_[lane].get(sizeof(ResizeJob) * max_group);
             B200_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(ResizeJob) * b, cudaMemcpyHostToDevice, st));
-            Plan* pl = det->plan_for(b, g.dst_h, g.dst_w, false, /*own_arena=*/2, /*slot=*/lane);
             if (!pl->own_arena) {
                 // The private-slab budget is exhausted and this plan lives in the model's shared slab: it must not run
                 // while anything else may be using that slab (another lane's network, or the DBPostProcess tail of
@@ -753,13 +760,16 @@ void Stages::det_enqueue(DetTicket* t, Model* det, const PagePool& pool, const u
                 for (int l = 0; l < kDetLanes; ++l)
                     if (l != lane) B200_CUDA_CHECK(cudaStreamSynchronize(det_st_[l]));
             }
-            dim3 grid((unsigned)ceil_div(g.dst_w, 256), g.dst_h, b);
-            if (det->precision() == PREC_BF16)
-                resize_norm_kernel<bf16><<<grid, 256, 0, st>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
-            else
-                resize_norm_kernel<float><<<grid, 256, 0, st>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
+            if (!pl->pre_jobs) {
+                dim3 grid((unsigned)ceil_div(g.dst_w, 256), g.dst_h, b);
+                if (det->precision() == PREC_BF16)
+                    resize_norm_kernel<bf16><<<grid, 256, 0, st>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
+                else
+                    resize_norm_kernel<float><<<grid, 256, 0, st>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
+                launches += 1;
+            }
             pl->launch(st);
-            launches += pl->launches + 1;
+            launches += pl->launches;
             B200_CUDA_CHECK(cudaGetLastError());
             // the dense output is [b,1,H,W] fp32 == the probability maps
             if (probmap_out)

@@ -77,6 +77,7 @@ public:
                          int* n_boxes_total);
 
     void l2_flush();
+    static void det_norm_values(float v[8]);     // NormalizeImage constants of the det path (NormP layout)
 
     int64_t launches = 0;
     float stage_ms[4] = {0, 0, 0, 0};
