@@ -9,7 +9,7 @@ batch of 16 synthetic 960x960 pages per GPU.  Pages shard across GPUs as indepen
 of the device time only.
 
   value     pages/s with the page bytes already resident in HBM (CUDA events on the engine stream), through the
-            streaming entry points (b200ocr_det_submit / _collect: two batches in flight, so the DBPostProcess tail
+            streaming entry points (b200ocr_det_submit / _collect: four batches in flight, so the DBPostProcess tail
             and box read-back of step k overlap the network of step k+1).  Steps rotate through 4 resident page sets
             (177 MB > the 126 MB L2).
   e2e       pages/s through the public API (`Engine.det_pages_stream`) with HOST page buffers: H2D of the page
@@ -46,8 +46,8 @@ CONFIG = {"workload": "C2 det-only: 16 synthetic 960x960 pages per GPU per step 
           "pages_per_gpu": PAGES_PER_GPU,
           "l2": "inputs larger than L2: the steps rotate through %d page sets (%d pages, 177 MB > 126 MB L2) and every step "
                 "rewrites ~2 GB of activations" % (SETS, SETS * PAGES_PER_GPU),
-          "pipeline": "streaming det: two batches in flight (submit / collect), each as two 8-page sub-batches on its own "
-                      "pair of det lanes; uploads, network and DBPostProcess of neighbouring steps overlap"}
+          "pipeline": "streaming det: four batches in flight (submit / collect), each a 16-page plan on its own det lane; "
+                      "uploads, network and DBPostProcess of neighbouring steps overlap"}
 
 
 def load_peaks():
@@ -269,13 +269,13 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- the network alone: the two 8-page sub-batches of a step, replayed back to back as CUDA graphs
-    net_ms = 2 * eng.time_plan(_lib.DET, PAGES_PER_GPU // 2, SIDE, SIDE, iters=10)
+    # ---- the network alone: the 16-page plan of a step, replayed back to back as a CUDA graph
+    net_ms = eng.time_plan(_lib.DET, PAGES_PER_GPU, SIDE, SIDE, iters=10)
 
     # ---- roofline of the dominant kernel (live CUDA-event timing per launch of the plan a step actually runs:
-    #      two sub-batches of 8 pages, one per det lane)
+    #      one 16-page plan per streaming batch)
     peaks = load_peaks()
-    sub = PAGES_PER_GPU // 2
+    sub = PAGES_PER_GPU
     prof = eng.profile_plan(_lib.DET, sub, SIDE, SIDE, iters=5)
     classes = {}
     for s in prof:
@@ -303,11 +303,11 @@ def main():
                "eltwise": "eltwise_bf16x8_kernel"}.get(kernel_class(top["name"]), kernel_class(top["name"]))
     roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
             "traffic": traffic, "kernel": top["name"], "algorithmic_bytes_per_launch": top["bytes"],
-            "launch_ms": top["ms"], "launches_per_step": 2, "share_of_network_time": top["ms"] / total_ms,
+            "launch_ms": top["ms"], "launches_per_step": 1, "share_of_network_time": top["ms"] / total_ms,
             "peak_source": peaks["source"],
             "tensor_tflops": top["flops"] / (top["ms"] / 1e3) / 1e12,
             "tensor_frac_of_sustained": top["flops"] / (top["ms"] / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
-            "note": "kernel = %s for the named layer at 8 pages (%.0f FLOP per algorithmic byte, below the ridge of %.0f, so "
+            "note": "kernel = %s for the named layer at 16 pages (%.0f FLOP per algorithmic byte, below the ridge of %.0f, so "
                     "HBM-bound); traffic = dram read+write of one launch from profiles/r1_traffic.json (ncu --set full); output "
                     "lines still resident in the 126 MB L2 at kernel end are not in it" % (
                         kern_of, top["flops"] / max(top["bytes"], 1.0), peaks["bf16_tflops_sustained"] * 1e3 / peaks["hbm_gbs"])}
@@ -328,9 +328,9 @@ def main():
         "sync": sync,
         "gpu_launches": int(launches),
         "network_ms_per_step": net_ms,
-        "network_algorithmic": {"gbytes_per_step": 2 * net_bytes / 1e9, "gflop_per_step": 2 * net_flops / 1e9,
-                                "hbm_gbs": 2 * net_bytes / (net_ms / 1e3) / 1e9,
-                                "hbm_frac_of_measured": 2 * net_bytes / (net_ms / 1e3) / 1e9 / peaks["hbm_gbs"]},
+        "network_algorithmic": {"gbytes_per_step": net_bytes / 1e9, "gflop_per_step": net_flops / 1e9,
+                                "hbm_gbs": net_bytes / (net_ms / 1e3) / 1e9,
+                                "hbm_frac_of_measured": net_bytes / (net_ms / 1e3) / 1e9 / peaks["hbm_gbs"]},
         "roofline": roof,
         "kernel_classes": breakdown,
         "clocks": sampler.summary(),

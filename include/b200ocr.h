@@ -109,7 +109,7 @@ int b200ocr_det_pages(b200ocr_engine* e, const uint8_t* const* pages, const int*
  * here the overlap is explicit and single-threaded).  b200ocr_det_submit enqueues the uploads, the network and
  * DBPostProcess of one batch on a free slot (two det lanes of its own) and returns a ticket without waiting for the
  * GPU; b200ocr_det_collect blocks until that batch's boxes are on the host and writes them exactly as
- * b200ocr_det_pages would.  Up to two batches may be in flight (a third submit returns B200OCR_E_CAPACITY): the upload
+ * b200ocr_det_pages would.  Up to four batches may be in flight (a fifth submit returns B200OCR_E_CAPACITY): the upload
  * and network of batch k+1 then overlap the DBPostProcess tail and box read-back of batch k.  The page buffers of a
  * batch must stay valid and unchanged until it has been collected.  Results are identical to b200ocr_det_pages. */
 int b200ocr_det_submit(b200ocr_engine* e, const uint8_t* const* pages, const int* hs, const int* ws,
@@ -201,6 +201,11 @@ int b200ocr_stage_times(b200ocr_engine* e, float ms_out[4]);
  * host box sorting / crop planning, warp + cls enqueue, rec enqueue, final drain. */
 int b200ocr_ocr_stage_times(b200ocr_engine* e, float ms_out[6]);
 
+/* Diagnostics: with B200OCR_TRACE=<file> in the environment the stages record CUDA events around the work they enqueue
+ * (det network, DBPostProcess, crop warp, cls, every rec batch) on each stream; this appends one JSON line per scope
+ * (name, tag, stream, start / end ms relative to the first scope) to the file and clears the log.  No-op otherwise. */
+void b200ocr_trace_dump(void);
+
 /* ---- device-resident benchmarking hooks (bench.py `value`: inputs already in HBM) ------- */
 /* Uploads pages once; b200ocr_det_resident_run then repeats preprocess -> DBNet -> DBPostProcess
  * on the resident copies and returns the device time in ms (CUDA events on the engine stream). */
@@ -208,7 +213,7 @@ int b200ocr_det_resident_upload(b200ocr_engine* e, const uint8_t* const* pages, 
                                 const int* strides, int n);
 int b200ocr_det_resident_run(b200ocr_engine* e, const b200ocr_det_params* p, int iters, float* ms_total,
                              int* n_boxes_total, float* net_ms_total);
-/* The same through the streaming path (submit / collect, two batches in flight): step k processes resident pages
+/* The same through the streaming path (submit / collect, B200OCR_DET_DEPTH = 4 batches in flight by default): step k processes resident pages
  * [k*pages_per_step, (k+1)*pages_per_step) modulo the resident set, so uploading more page sets than the L2 holds
  * makes every step read its pages from HBM.  ms_total = device time of all `iters` steps (CUDA events). */
 int b200ocr_det_resident_stream(b200ocr_engine* e, const b200ocr_det_params* p, int iters, int pages_per_step,

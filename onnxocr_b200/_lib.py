@@ -100,6 +100,8 @@ def lib():
         L.b200ocr_ocr_stage_times.argtypes = [vp, pf]
         L.b200ocr_det_resident_upload.argtypes = [vp, C.POINTER(vp), pi, pi, pi, i]
         L.b200ocr_det_resident_run.argtypes = [vp, C.POINTER(DetParams), i, pf, pi, pf]
+        L.b200ocr_trace_dump.argtypes = []
+        L.b200ocr_trace_dump.restype = None
         L.b200ocr_det_resident_stream.argtypes = [vp, C.POINTER(DetParams), i, i, pf, pi]
         L.b200ocr_det_submit.argtypes = [vp, C.POINTER(vp), pi, pi, pi, i, C.POINTER(DetParams), pi]
         L.b200ocr_det_collect.argtypes = [vp, i, vp, i, pi]
@@ -316,12 +318,14 @@ class Engine(object):
         self._check(self._L.b200ocr_det_collect(self._h, tid, _ptr(boxes), max_boxes, counts))
         return [boxes[i, :counts[i]].copy() for i in range(n)]
 
-    def det_pages_stream(self, batches, params=None, max_boxes=1000, depth=2):
-        """Generator over an iterable of page batches: yields each batch's boxes in order while keeping `depth` (<= 2)
+    def det_pages_stream(self, batches, params=None, max_boxes=1000, depth=None):
+        """Generator over an iterable of page batches: yields each batch's boxes in order while keeping `depth` (<= 4)
         batches in flight, so uploads and the network of the next batch overlap the post-processing of this one."""
+        if depth is None:
+            depth = int(os.environ.get("B200OCR_DET_DEPTH", "4"))
         pending = []
         for b in batches:
-            if len(pending) >= max(1, min(depth, 2)):
+            if len(pending) >= max(1, min(depth, 4)):
                 yield self.det_collect(pending.pop(0), max_boxes)
             pending.append(self.det_submit(b, params))
         while pending:

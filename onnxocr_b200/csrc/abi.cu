@@ -410,6 +410,8 @@ int b200ocr_ocr_stage_times(b200ocr_engine* e, float ms_out[6]) {
     });
 }
 
+void b200ocr_trace_dump(void) { trace_dump(); }
+
 int b200ocr_det_resident_upload(b200ocr_engine* e, const uint8_t* const* pages, const int* hs, const int* ws,
                                 const int* strides, int n) {
     return guarded(e, [&]() {

@@ -489,6 +489,7 @@ void Stages::db_post_enqueue(int lane, const float* d_prob, int n, int h, int w,
     const int hw = h * w;
     const int maxc = std::max(1, std::min(capacity, p.max_candidates));
     cudaStream_t st = det_st_[lane];
+    TraceScope tr_post("db_post", st, n);
     uint8_t* bm = (uint8_t*)W.bitmap.get((size_t)total * (p.use_dilation ? 2 : 1));
     int* L = (int*)W.labels.get((size_t)total * sizeof(int));
     int* flags = (int*)W.flags.get((size_t)total * sizeof(int));

@@ -503,6 +503,15 @@ std::unique_ptr<Plan> Model::build_plan(int n, int h, int w, bool head, int own_
     return p;
 }
 
+static int ws_min_tiles() {
+    static const int v = [] {
+        const char* e = getenv("B200OCR_WS_MIN_TILES");
+        int k = e ? atoi(e) : 1;            // measured: 4 costs 35 % single-batch latency and buys nothing at 8 streams
+        return k >= 1 && k <= 64 ? k : 1;
+    }();
+    return v;
+}
+
 template <typename T>
 void Model::build_steps(Plan& p) {
     const CGraph& g = *g_;
@@ -900,7 +909,12 @@ void Model::build_steps(Plan& p) {
                                                    : tp.tiles_x * tp.tiles_y * tp.N;
                         if (ws_bn) {
                             int n_tiles = (int)ceil_div(tp.CoutP, ws_bn);
-                            int m_groups = std::max(1, std::min(m_tiles, 148 / n_tiles));
+                            // A CTA of this kernel owns a whole SM (its weight slab and the activation ring fill the shared
+                            // memory), so a small layer that spreads one tile to every SM locks out the kernels of every
+                            // other stream (rec batches on the auxiliary streams, the other det lanes) for its whole
+                            // latency-bound lifetime.  Give every CTA at least ws_min_tiles() tiles: the layer itself takes
+                            // barely longer (the slab load and pipeline fill dominate) and the other SMs stay free.
+                            int m_groups = std::max(1, std::min(std::max(1, m_tiles / ws_min_tiles()), 148 / n_tiles));
                             size_t smem = tc::ws_smem_bytes(ws_bn, nkb, tp.ws_stages, tp.ws_halo ? (size_t)tp.ws_stage_bytes : (size_t)tc::WS_A_BYTES);
                             cudaFuncSetAttribute(tc::conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::WS_SMEM_LIMIT);
                             launch_pdl(tc::conv_tc_ws_kernel, dim3((unsigned)(n_tiles * m_groups)), tc::kWsThreads, smem, st, 

@@ -4,6 +4,8 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <numeric>
 #include <thread>
 
@@ -38,6 +40,58 @@ PinBuf::~PinBuf() {
 
 // DetResizeForTest.resize_image_type0 (operators.py:91-138) — Python float/int semantics in C++:
 // int() truncates, round() is half-to-even (nearbyint under the default rounding mode).
+// ------------------------------------------------------------------------------- trace
+namespace {
+struct TraceRec { std::string name; int tag; uintptr_t stream; cudaEvent_t a, b; };
+struct TraceState {
+    const char* path = getenv("B200OCR_TRACE");
+    std::vector<TraceRec> recs;
+    std::mutex mu;
+};
+TraceState& trace_state() { static TraceState t; return t; }
+}  // namespace
+
+TraceScope::TraceScope(const char* name, cudaStream_t s, int tag) : st(s) {
+    TraceState& t = trace_state();
+    if (!t.path || !t.path[0]) return;
+    std::lock_guard<std::mutex> lk(t.mu);
+    if (t.recs.size() >= 200000) return;
+    TraceRec r{name, tag, (uintptr_t)s, nullptr, nullptr};
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    idx = (int)t.recs.size();
+    t.recs.push_back(r);
+}
+TraceScope::~TraceScope() {
+    if (idx < 0) return;
+    TraceState& t = trace_state();
+    std::lock_guard<std::mutex> lk(t.mu);
+    cudaEventRecord(t.recs[idx].b, st);
+}
+void trace_dump() {
+    TraceState& t = trace_state();
+    if (!t.path || !t.path[0] || t.recs.empty()) return;
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(t.mu);
+    FILE* f = fopen(t.path, "a");
+    if (!f) return;
+    std::map<uintptr_t, int> sid;
+    for (auto& r : t.recs) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, t.recs[0].a, r.a);
+        cudaEventElapsedTime(&b, t.recs[0].a, r.b);
+        if (!sid.count(r.stream)) { int k = (int)sid.size(); sid[r.stream] = k; }
+        fprintf(f, "{\"name\": \"%s\", \"tag\": %d, \"stream\": %d, \"t0\": %.4f, \"t1\": %.4f}\n", r.name.c_str(), r.tag, sid[r.stream], a, b);
+    }
+    for (auto& r : t.recs) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    fclose(f);
+    t.recs.clear();
+}
+
 DetGeom det_geometry(int h, int w, const b200ocr_det_params& p) {
     DetGeom g;
     g.src_h = h;
@@ -200,9 +254,11 @@ Stages::Stages(cudaStream_t st) : st_(st) {
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
     for (auto& e : ev_join_) B200_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     db_ = nullptr;
+    if (const char* e = getenv("B200OCR_AUX")) n_aux_ = std::max(1, std::min(kAux, atoi(e)));
 }
 
 Stages::~Stages() {
+    trace_dump();
     for (auto& a : aux_) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
     for (auto& a : det_st_) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
     for (auto& e : ev_det_done_) cudaEventDestroy(e);
@@ -408,6 +464,7 @@ void Stages::rec_batch(Model* rec, const ResizeJob* d_jobs, const int* d_slots, 
         lane = 0;
         st = st_;
     }
+    TraceScope tr_rec("rec_batch", st, b * 10000 + W);
     dim3 grid((unsigned)ceil_div(W, 256), img_h, b);
     if (rec->precision() == PREC_BF16)
         resize_norm_kernel<bf16><<<grid, 256, 0, st>>>(d_jobs, img_h, W, p->in_ptr(), 0, rec_norm());
@@ -450,25 +507,49 @@ void Stages::rec_batches(Model* rec, const ResizeJob* d_jobs, const int* d_slots
     }
     int n_small = 0;
     for (auto& be : batches) n_small += (be.second - be.first) <= small_batch;
-    const bool fan_out = n_small >= 2 && kAux > 0;
+    const bool fan_out = n_small >= 2 && n_aux_ > 0;
     if (fan_out) {
         B200_CUDA_CHECK(cudaEventRecord(ev_fork_, st_));
-        for (int a = 0; a < kAux; ++a) B200_CUDA_CHECK(cudaStreamWaitEvent(aux_[a], ev_fork_, 0));
+        for (int a = 0; a < n_aux_; ++a) B200_CUDA_CHECK(cudaStreamWaitEvent(aux_[a], ev_fork_, 0));
     }
-    std::vector<char> used(kAux, 0);
-    for (auto& be : batches) {
-        int b = be.second - be.first, W = imgw_sorted[be.first];
-        int lane = 0;
-        if (fan_out && b <= small_batch) {
-            // a plan (b, W) always runs on the same auxiliary stream: its private slab may still be in use by the
-            // previous wave's batch of the same shape, and stream order is what protects it
-            lane = 1 + (int)(((unsigned)b * 2654435761u + (unsigned)W * 40503u) % (unsigned)kAux);
-            used[lane - 1] = 1;
+    std::vector<char> used(n_aux_, 0);
+    // Small batches are spread over the auxiliary streams longest-first onto the least loaded stream (they are latency
+    // bound: a batch of 6 crops costs about as much as one of 24).  A plan (b, W) that already ran in this call stays
+    // on its stream: its private slab may still be in use by the previous wave's batch of the same shape, and stream
+    // order is what protects it (rec_lane_of_ is cleared when a call starts, i.e. after the previous call drained).
+    std::vector<int> lane_of(batches.size(), 0);
+    if (fan_out) {
+        std::vector<double> load(n_aux_, 0.0);
+        auto cost = [&](int i) { return 1.0 + (double)(batches[i].second - batches[i].first) * imgw_sorted[batches[i].first] / 8000.0; };
+        std::vector<int> order;
+        for (int i = 0; i < (int)batches.size(); ++i) {
+            int b = batches[i].second - batches[i].first, W = imgw_sorted[batches[i].first];
+            if (b > small_batch) continue;
+            auto it = rec_lane_of_.find({b, W});
+            if (it != rec_lane_of_.end()) {
+                lane_of[i] = it->second;
+                load[it->second - 1] += cost(i);
+            } else {
+                order.push_back(i);
+            }
         }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return cost(a) > cost(c); });
+        for (int i : order) {
+            int best = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            load[best] += cost(i);
+            lane_of[i] = best + 1;
+            rec_lane_of_[{batches[i].second - batches[i].first, imgw_sorted[batches[i].first]}] = best + 1;
+        }
+    }
+    for (int i = 0; i < (int)batches.size(); ++i) {
+        auto& be = batches[i];
+        int b = be.second - be.first, W = imgw_sorted[be.first];
+        int lane = lane_of[i];
+        if (lane > 0) used[lane - 1] = 1;
         rec_batch(rec, d_jobs + be.first, d_slots + be.first, b, img_h, W, max_len, d_ids, d_lens, d_scores, lane);
     }
     if (fan_out)
-        for (int a = 0; a < kAux; ++a)
+        for (int a = 0; a < n_aux_; ++a)
             if (used[a]) {
                 B200_CUDA_CHECK(cudaEventRecord(ev_join_[a], aux_[a]));
                 B200_CUDA_CHECK(cudaStreamWaitEvent(st_, ev_join_[a], 0));
@@ -512,6 +593,7 @@ void Stages::rec_crops(Model* rec, const uint8_t* const* crops, const int* hs, c
                        const uint8_t* rotate180, int32_t* ids_out, int max_len, int* lens_out, float* scores_out) {
     if (n == 0) return;
     if (batch_num <= 0) batch_num = 6;
+    rec_lane_of_.clear();                       // the previous call drained every stream
     const int img_h = 48, img_w0 = 320;         // rec_image_shape "3, 48, 320" (onnx_paddleocr.py:20)
     uint8_t* d_base = nullptr;
     std::vector<size_t> off = upload_crops(d_crops_, h_pin_, crops, hs, ws, n, st_, &d_base);
@@ -715,11 +797,15 @@ void Stages::det_enqueue(DetTicket* t, Model* det, const PagePool& pool, const u
         for (int l = 0; l < kLanesPerSlot; ++l) B200_CUDA_CHECK(cudaStreamWaitEvent(det_st_[lane0 + l], ev_fork_, 0));
     }
 
-    static const int sub = [] {
+    // A synchronous call splits 16 equal pages into 8 + 8 on its two lanes (DBPostProcess of one half overlaps the network
+    // of the other); a streaming batch keeps them together (one 16-page plan is 13 % cheaper than two 8-page plans, and
+    // the overlap comes from the other batches in flight).  B200OCR_DET_SUB overrides both.
+    static const int sub_env = [] {
         const char* e = getenv("B200OCR_DET_SUB");
-        int v = e ? atoi(e) : 8;
-        return v >= 1 && v <= 16 ? v : 8;
+        int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= 16 ? v : 0;
     }();
+    const int sub = sub_env ? sub_env : (t == &sync_ticket_ ? 8 : 16);
     const int max_group = 16;
     for (int g0 = 0; g0 < n;) {
         int g1 = g0;
@@ -760,6 +846,7 @@ void Stages::det_enqueue(DetTicket* t, Model* det, const PagePool& pool, const u
                 for (int l = 0; l < kDetLanes; ++l)
                     if (l != lane) B200_CUDA_CHECK(cudaStreamSynchronize(det_st_[l]));
             }
+            TraceScope tr_net("det_net", st, b);
             if (!pl->pre_jobs) {
                 dim3 grid((unsigned)ceil_div(g.dst_w, 256), g.dst_h, b);
                 if (det->precision() == PREC_BF16)
@@ -911,6 +998,7 @@ void Stages::ocr_pages(Model* det, Model* cls, Model* rec, const uint8_t* const*
     auto t0 = now();
     PagePool pool;
     drain_tickets();
+    rec_lane_of_.clear();                       // the previous call drained every stream
     plan_pool(hs, ws, strides, n, &pool, &sync_ticket_.store);
     ocr_ms[0] = ms_since(t0);
     const bool use_cls = op.use_angle_cls && cls != nullptr;
@@ -997,6 +1085,7 @@ void Stages::ocr_pages(Model* det, Model* cls, Model* rec, const uint8_t* const*
         uint8_t* d_pool = (uint8_t*)d_crops_.get(coff[total] + 16);
         B200_CUDA_CHECK(cudaMemcpyAsync(d_wj, wj.data(), sizeof(WarpJob) * total, cudaMemcpyHostToDevice, st_));
         {
+            TraceScope tr_warp("warp", st_, total);
             dim3 block(32, 8);
             dim3 grid((unsigned)ceil_div(max_w, 32), (unsigned)ceil_div(max_h, 8), total);
             warp_cubic_kernel<<<grid, block, 0, st_>>>(d_wj, cubic_tab_device(), d_pool);
@@ -1018,6 +1107,7 @@ void Stages::ocr_pages(Model* det, Model* cls, Model* rec, const uint8_t* const*
             const int chunk = 512;
             for (int beg = 0; beg < total; beg += chunk) {
                 int b = std::min(chunk, total - beg);
+                TraceScope tr_cls("cls", st_, b);
                 Plan* p = cls->plan_for(b, img_h, cimg_w);
                 dim3 grid((unsigned)ceil_div(cimg_w, 256), img_h, b);
                 if (cls->precision() == PREC_BF16)
@@ -1177,21 +1267,26 @@ void Stages::resident_stream(Model* det, const b200ocr_det_params& p, int iters,
         for (auto& b : t->boxes) boxes_total += (int)(b.size() / 8);
     };
     B200_CUDA_CHECK(cudaEventRecord(ev_[0], st_));
+    static const int depth = [] {
+        const char* e = getenv("B200OCR_DET_DEPTH");
+        int v = e ? atoi(e) : kDetSlots;
+        return v >= 1 && v <= kDetSlots ? v : kDetSlots;
+    }();
     for (int it = 0; it < iters; ++it) {
-        DetTicket* t = &tickets_[it % kDetSlots];
+        DetTicket* t = &tickets_[it % depth];
         if (t->busy) finish(t);
-        t->slot = it % kDetSlots;
+        t->slot = it % depth;
         const int first = (int)(((int64_t)it * pps) % n);
         PagePool pool;
         pool.base = (uint8_t*)d_res_.p;
         pool.off.assign(res_off_.begin() + first, res_off_.begin() + first + pps);
         pool.stride.assign(res_stride_.begin() + first, res_stride_.begin() + first + pps);
         det_enqueue(t, det, pool, nullptr, res_h_.data() + first, res_w_.data() + first, pps, p, nullptr, 0, nullptr,
-                    it < kDetSlots ? st_ : nullptr);
+                    it < depth ? st_ : nullptr);
         t->busy = true;
     }
-    for (int k = 0; k < kDetSlots; ++k) {
-        DetTicket* t = &tickets_[(iters + k) % kDetSlots];
+    for (int k = 0; k < depth; ++k) {
+        DetTicket* t = &tickets_[(iters + k) % depth];
         if (t->busy) finish(t);
     }
     for (int l = 0; l < kDetLanes; ++l) {

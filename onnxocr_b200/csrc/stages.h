@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <map>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200ocr.h"
@@ -32,6 +34,17 @@ struct PinBuf {
     void* get(size_t bytes);
     ~PinBuf();
 };
+
+// Coarse device timeline for diagnostics (B200OCR_TRACE=<file>): a scope records a CUDA event on its stream when it is
+// opened and when it is closed, i.e. around the work enqueued in between; trace_dump() (engine destruction) writes one JSON
+// line per scope with start / end in ms relative to the first event.  Off (no events, no cost) unless the variable is set.
+struct TraceScope {
+    TraceScope(const char* name, cudaStream_t st, int tag = 0);
+    ~TraceScope();
+    int idx = -1;
+    cudaStream_t st = nullptr;
+};
+void trace_dump();
 
 struct DbWork;
 struct ResizeJob;              // device scratch of DBPostProcess (dbpost.cu)
@@ -109,7 +122,7 @@ private:
         bool active = false;
     };
     static constexpr int kLanesPerSlot = 2;
-    static constexpr int kDetSlots = 2;                      // batches in flight through det_submit
+    static constexpr int kDetSlots = 4;                      // batches in flight through det_submit
     static constexpr int kDetLanes = kLanesPerSlot * kDetSlots;
     struct DetChunk { int g0, b, h, w; };
     struct DetTicket {                                       // the host-side state of one enqueued batch
@@ -145,7 +158,9 @@ private:
                    int* d_ids, int* d_lens, float* d_scores, int lane);
     void rec_batches(Model* rec, const struct ResizeJob* d_jobs, const int* d_slots, const std::vector<int>& imgw_sorted,
                      int img_h, int max_len, int* d_ids, int* d_lens, float* d_scores);
-    static constexpr int kAux = 8;              // auxiliary streams for independent small rec batches
+    static constexpr int kAux = 16;             // auxiliary streams for independent small rec batches (n_aux_ in use)
+    int n_aux_ = 8;
+    std::map<std::pair<int, int>, int> rec_lane_of_;   // (batch, width) -> auxiliary stream within the current call
     cudaStream_t aux_[kAux];
     cudaEvent_t ev_fork_, ev_join_[kAux];
     DevBuf d_lane_[kAux + 1];                   // per-stream CTC scratch

@@ -1,6 +1,6 @@
-"""GPU: the streaming det entry points (b200ocr_det_submit / b200ocr_det_collect, two batches in flight on separate
+"""GPU: the streaming det entry points (b200ocr_det_submit / b200ocr_det_collect, up to four batches in flight on separate
 lane pairs) return exactly what the synchronous b200ocr_det_pages returns, interleave correctly with synchronous calls,
-and reject misuse (a third batch in flight, a stale ticket) with an error instead of corrupting a slot."""
+and reject misuse (a fifth batch in flight, a stale ticket) with an error instead of corrupting a slot."""
 import numpy as np
 import pytest
 
@@ -62,8 +62,14 @@ def test_stream_misuse_is_an_error(engine_bf16):
     batches = _batches()
     t0 = eng.det_submit(batches[1])
     t1 = eng.det_submit(batches[4])
+    t2 = eng.det_submit(batches[4])
+    t3 = eng.det_submit(batches[1])
     with pytest.raises(RuntimeError, match="in flight"):
-        eng.det_submit(batches[1])
+        eng.det_submit(batches[1])            # four slots
+    _same(eng.det_collect(t3), eng.det_collect(t0))
+    t0 = eng.det_submit(batches[1])
+    _same(eng.det_collect(t2), eng.det_collect(t1))
+    t1 = eng.det_submit(batches[4])
     a = eng.det_collect(t0)
     with pytest.raises(RuntimeError, match="ticket"):
         eng.det_collect(t0)                  # already collected
