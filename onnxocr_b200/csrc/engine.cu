@@ -841,9 +841,10 @@ void Model::build_steps(Plan& p) {
                     // descriptors.  Correct (tests/test_gpu_tc.py passes with B200OCR_TC_HALO=1) and it cuts the L2->SM
                     // traffic 6x, but measured SLOWER than the per-tap re-load kernel on these layers (0.132 vs 0.096 ms
                     // for 3x3 96->24 @ 240^2 x 8): with N = 32 the 72 small UMMAs per tile are issue-bound on the single
-                    // MMA thread and the streaming kernel runs two CTAs per SM.  Off by default until the issue loop is
-                    // restructured.
-                    static const int halo_on = [] { const char* e = getenv("B200OCR_TC_HALO"); return e ? atoi(e) : 0; }();
+                    // MMA thread and the streaming kernel runs two CTAs per SM.  Mode 2 (default since round 2) interleaves the
+                    // MMAs of two tiles' accumulators and issues them with running descriptors: 0.067 vs 0.077 ms on the
+                    // same layer, det plan 2.18 vs 2.29 ms at 16 pages.  B200OCR_TC_HALO=0 selects the per-tap kernel.
+                    static const int halo_on = [] { const char* e = getenv("B200OCR_TC_HALO"); return e ? atoi(e) : 2; }();
                     const bool halo = tp.mode == 1 && halo_on && c.kh <= 5 && c.kw <= 5;
                     size_t stage_bytes = tc::WS_A_BYTES;
                     if (halo) {
@@ -873,7 +874,10 @@ void Model::build_steps(Plan& p) {
                         tp.gap_rows = tp.mode == 0 ? tp.M / iv.n : 0;
                         p.vals[out].sums = gap_buf;
                         const int gb = gap_buf;
+                        const double keep_f = cost_flops, keep_b = cost_bytes;     // the work belongs to the conv step below
+                        cost_flops = 0; cost_bytes = (double)bytes;
                         emit("zero_sums " + c.name, [=](cudaStream_t st) { cudaMemsetAsync(pp->bufptr(gb), 0, bytes, st); });
+                        cost_flops = keep_f; cost_bytes = keep_b;
                     }
                     std::shared_ptr<TcState> ts(new TcState());
                     {

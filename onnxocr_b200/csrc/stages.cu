@@ -249,8 +249,22 @@ static short* g_cubic_tab[16] = {nullptr};
 Stages::Stages(cudaStream_t st) : st_(st) {
     for (auto& e : ev_) B200_CUDA_CHECK(cudaEventCreate(&e));
     for (auto& a : aux_) B200_CUDA_CHECK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
-    for (auto& a : det_st_) B200_CUDA_CHECK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    {
+        // B200OCR_DET_PRIO=1 gives the lanes distinct stream priorities (experiment, off): the block scheduler then drains
+        // the networks one after the other at their solo speed (2.3 ms per 16 pages), which loses more than the overlap of
+        // their DBPostProcess tails gains (concurrent networks fill each other's gaps: 1.8 ms each).  The rolling window
+        // in det_enqueue is what de-phases the lanes instead.
+        int lo = 0, hi = 0;
+        B200_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least urgent (numerically larger)
+        const char* e = getenv("B200OCR_DET_PRIO");
+        const bool prio = e && e[0] == '1';
+        for (int l = 0; l < kDetLanes; ++l) {
+            int pr = prio ? std::max(hi, lo - 1 - (l % std::max(1, lo - hi))) : lo;
+            B200_CUDA_CHECK(cudaStreamCreateWithPriority(&det_st_[l], cudaStreamNonBlocking, pr));
+        }
+    }
     for (auto& e : ev_det_done_) B200_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ev_net_done_) B200_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
     for (auto& e : ev_join_) B200_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     db_ = nullptr;
@@ -262,6 +276,7 @@ Stages::~Stages() {
     for (auto& a : aux_) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
     for (auto& a : det_st_) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
     for (auto& e : ev_det_done_) cudaEventDestroy(e);
+    for (auto& e : ev_net_done_) cudaEventDestroy(e);
     for (auto& d : db_lane_) db_free(d);
     cudaEventDestroy(ev_fork_);
     for (auto& e : ev_join_) cudaEventDestroy(e);
@@ -855,7 +870,23 @@ void Stages::det_enqueue(DetTicket* t, Model* det, const PagePool& pool, const u
                     resize_norm_kernel<float><<<grid, 256, 0, st>>>(d_jobs, g.dst_h, g.dst_w, pl->in_ptr(), 0, det_norm());
                 launches += 1;
             }
+            // Rolling window: this network starts when the network enqueued `window` chunks earlier has finished, so at
+            // most `window` networks run at a time and the lanes can never fall into lock step (all networks together,
+            // then all the latency-bound DBPostProcess tails together on an idle GPU).  The uploads above are not held
+            // back.  A chunk that reuses the lane of chunk c - window is ordered by the stream anyway.
+            static const int window = [] {
+                const char* e = getenv("B200OCR_DET_WINDOW");
+                int v = e ? atoi(e) : 2;
+                return v >= 0 && v < kDetLanes ? v : 2;
+            }();
+            if (window > 0 && net_seq_ >= window) {
+                const int prev_lane = net_lane_ring_[(net_seq_ - window) % kDetLanes];
+                if (prev_lane != lane) B200_CUDA_CHECK(cudaStreamWaitEvent(st, ev_net_done_[prev_lane], 0));
+            }
             pl->launch(st);
+            B200_CUDA_CHECK(cudaEventRecord(ev_net_done_[lane], st));
+            net_lane_ring_[net_seq_ % kDetLanes] = lane;
+            ++net_seq_;
             launches += pl->launches;
             B200_CUDA_CHECK(cudaGetLastError());
             // the dense output is [b,1,H,W] fp32 == the probability maps

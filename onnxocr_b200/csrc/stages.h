@@ -154,6 +154,9 @@ private:
     DbWork* db_lane_[kDetLanes] = {};
     DevBuf d_lane_jobs_[kDetLanes];
     cudaEvent_t ev_det_done_[kDetLanes];
+    cudaEvent_t ev_net_done_[kDetLanes];        // recorded right after a lane's network (rolling window in det_enqueue)
+    int net_lane_ring_[kDetLanes] = {};
+    long long net_seq_ = 0;
     void rec_batch(Model* rec, const struct ResizeJob* d_jobs, const int* d_slots, int b, int img_h, int W, int max_len,
                    int* d_ids, int* d_lens, float* d_scores, int lane);
     void rec_batches(Model* rec, const struct ResizeJob* d_jobs, const int* d_slots, const std::vector<int>& imgw_sorted,
