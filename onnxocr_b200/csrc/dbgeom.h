@@ -180,6 +180,42 @@ B200_HDN int sklansky(const uint64_t* k, int start, int end, int* stack, int nsi
     return --stacksize;
 }
 
+// The tail of cv::convexHull: cyclic shift of the hull so that the original contour indices ascend / descend.
+B200_HDN int hull_index_shift(const uint64_t* keys, int* hull, int nout, int* stack) {
+    // cyclic shift so that the original indices ascend / descend
+    if (nout >= 3) {
+        int min_idx = 0, max_idx = 0, lt = 0;
+        int i;
+        for (i = 1; i < nout; ++i) {
+            int idx = key_i(keys[hull[i]]);
+            lt += key_i(keys[hull[i - 1]]) < idx;
+            if (lt > 1 && lt <= i - 2) break;
+            if (idx < key_i(keys[hull[min_idx]])) min_idx = i;
+            if (idx > key_i(keys[hull[max_idx]])) max_idx = i;
+        }
+        int mmdist = max_idx - min_idx;
+        if (mmdist < 0) mmdist = -mmdist;
+        if ((mmdist == 1 || mmdist == nout - 1) && (lt <= 1 || lt >= nout - 2)) {
+            int ascending = (max_idx + 1) % nout == min_idx;
+            int i0 = ascending ? min_idx : max_idx, j = i0;
+            if (i0 > 0) {
+                for (i = 0; i < nout; ++i) {
+                    int cur = hull[j];
+                    stack[i] = cur;
+                    int next_j = j + 1 < nout ? j + 1 : 0;
+                    int curr_idx = key_i(keys[cur]);
+                    int next_idx = key_i(keys[hull[next_j]]);
+                    if (i < nout - 1 && (ascending != (curr_idx < next_idx))) break;
+                    j = next_j;
+                }
+                if (i == nout)
+                    for (i = 0; i < nout; ++i) hull[i] = stack[i];
+            }
+        }
+    }
+    return nout;
+}
+
 // cv::convexHull(points, hull, clockwise, returnPoints=true) for int points (cv::minAreaRect passes clockwise=false).
 //   keys   : n contour points packed by pack_key, in contour order on entry (sorted in place)
 //   stack  : scratch, n + 2 ints
@@ -229,38 +265,7 @@ B200_HDN int convex_hull(uint64_t* keys, int n, int* stack, int* hull, bool cloc
     }
     for (int i = 0; i < bl_count - 1; ++i) hull[nout++] = bl_stack[i];
     for (int i = br_count - 1; i > 0; --i) hull[nout++] = br_stack[i];
-    // cyclic shift so that the original indices ascend / descend
-    if (nout >= 3) {
-        int min_idx = 0, max_idx = 0, lt = 0;
-        int i;
-        for (i = 1; i < nout; ++i) {
-            int idx = key_i(keys[hull[i]]);
-            lt += key_i(keys[hull[i - 1]]) < idx;
-            if (lt > 1 && lt <= i - 2) break;
-            if (idx < key_i(keys[hull[min_idx]])) min_idx = i;
-            if (idx > key_i(keys[hull[max_idx]])) max_idx = i;
-        }
-        int mmdist = max_idx - min_idx;
-        if (mmdist < 0) mmdist = -mmdist;
-        if ((mmdist == 1 || mmdist == nout - 1) && (lt <= 1 || lt >= nout - 2)) {
-            int ascending = (max_idx + 1) % nout == min_idx;
-            int i0 = ascending ? min_idx : max_idx, j = i0;
-            if (i0 > 0) {
-                for (i = 0; i < nout; ++i) {
-                    int cur = hull[j];
-                    stack[i] = cur;
-                    int next_j = j + 1 < nout ? j + 1 : 0;
-                    int curr_idx = key_i(keys[cur]);
-                    int next_idx = key_i(keys[hull[next_j]]);
-                    if (i < nout - 1 && (ascending != (curr_idx < next_idx))) break;
-                    j = next_j;
-                }
-                if (i == nout)
-                    for (i = 0; i < nout; ++i) hull[i] = stack[i];
-            }
-        }
-    }
-    return nout;
+    return hull_index_shift(keys, hull, nout, stack);
 }
 
 // ---------------------------------------------------------------------------------------------

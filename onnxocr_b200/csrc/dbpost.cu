@@ -35,9 +35,20 @@ namespace {
 constexpr int kHoleBit = 1 << 30;
 constexpr int kUnclipCap = 256;
 
+// All per-pixel kernels index with 32 bits (db_post_enqueue rejects batches of 2^30 pixels or more): 64-bit divisions
+// were the largest cost of the merge and compact kernels.
 __global__ void threshold_kernel(const float* __restrict__ prob, uint8_t* __restrict__ bm, int64_t total, float thresh) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    const unsigned quads = (unsigned)(total >> 2);
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(prob)[q];
+        uchar4 o;
+        o.x = v.x > thresh ? 1 : 0; o.y = v.y > thresh ? 1 : 0; o.z = v.z > thresh ? 1 : 0; o.w = v.w > thresh ? 1 : 0;
+        reinterpret_cast<uchar4*>(bm)[q] = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (unsigned)(total & 3)) {
+        const int64_t i = (total & ~(int64_t)3) + threadIdx.x;
         bm[i] = prob[i] > thresh ? 1 : 0;
+    }
 }
 
 // cv2.dilate(mask, ones((2, 2))): anchor (1, 1) -> out(y, x) = max over in(y-1..y, x-1..x)
@@ -63,10 +74,27 @@ __device__ __forceinline__ int find_root(const int* L, int i) {
     return i;
 }
 
+// find with path halving (ECL-CC style): every visited node is re-pointed at its grandparent.  Parents only ever move
+// to a smaller index inside the same tree, so the racing plain stores are benign (any value written is an ancestor) and
+// the final roots — the raster-first pixel of each component — are unchanged; the chains the later unions and the
+// flatten pass have to walk become short instead of O(rows).
+__device__ __forceinline__ int find_root_halving(int* L, int i) {
+    int curr = L[i];
+    if (curr != i) {
+        int prev = i, next;
+        while (curr > (next = L[curr])) {
+            L[prev] = next;
+            prev = curr;
+            curr = next;
+        }
+    }
+    return curr;
+}
+
 __device__ __forceinline__ void unite(int* L, int a, int b) {
     for (;;) {
-        a = find_root(L, a);
-        b = find_root(L, b);
+        a = find_root_halving(L, a);
+        b = find_root_halving(L, b);
         if (a == b) return;
         if (a < b) {
             int old = atomicMin(&L[b], a);
@@ -82,10 +110,10 @@ __device__ __forceinline__ void unite(int* L, int a, int b) {
 
 // label initialisation: every pixel points at the first pixel of its horizontal run inside its 32-pixel warp segment
 __global__ void ccl_init_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int64_t total, int w) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    bool in = i < total;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool in = i < (unsigned)total;
     int v = in ? bm[i] : 2;
-    int x = in ? (int)(i % w) : 0;
+    int x = in ? (int)(i % (unsigned)w) : 0;
     int lane = threadIdx.x & 31;
     // a run breaks where the class changes or a new image row starts
     int left = __shfl_up_sync(0xffffffffu, v, 1);
@@ -93,37 +121,36 @@ __global__ void ccl_init_kernel(const uint8_t* __restrict__ bm, int* __restrict_
     unsigned m = __ballot_sync(0xffffffffu, brk);
     unsigned upto = m & (0xffffffffu >> (31 - lane));
     int start_lane = 31 - __clz(upto);
-    if (in) L[i] = (int)(i - (lane - start_lane));
+    if (in) L[i] = (int)i - (lane - start_lane);
 }
 
-__global__ void ccl_merge_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int n, int h, int w) {
-    int64_t total = (int64_t)n * h * w;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int x = (int)(i % w);
-        int y = (int)((i / w) % h);
-        int v = bm[i];
-        bool hasN = y > 0, hasW = x > 0, hasE = x + 1 < w;
-        bool N = hasN && bm[i - w] == v;
-        bool W = hasW && bm[i - 1] == v;
+__global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int n, int h, int w) {
+    const int total = n * h * w;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned row = (unsigned)i / (unsigned)w;
+        const int x = i - (int)row * w, y = (int)(row % (unsigned)h);
+        const uint8_t* q = bm + i;
+        const int v = q[0];
+        const bool hasN = y > 0, hasW = x > 0, hasE = x + 1 < w;
+        const int vN = hasN ? q[-w] : -1, vW = hasW ? q[-1] : -1, vNW = hasN && hasW ? q[-w - 1] : -1;
+        const bool N = vN == v, W = vW == v;
         // The link to the pixel above is implied when the left neighbour (same class, same 32-pixel segment, hence already
         // in this pixel's run) has the same class above it: i ~ i-1 ~ i-1-w ~ i-w.  Only the first pixel of such a chain
         // performs the union, which removes most of the atomic traffic.
-        const bool implied = N && W && (i & 31) != 0 && bm[i - w - 1] == v;
+        const bool implied = N && W && (i & 31) != 0 && vNW == v;
         if (v) {                                  // foreground: 8-connectivity
-            bool NW = hasN && hasW && bm[i - w - 1];
-            bool NE = hasN && hasE && bm[i - w + 1];
             if (implied) {
             } else if (N) {
-                unite(L, (int)i, (int)(i - w));
+                unite(L, i, i - w);
             } else {
-                if (NW) unite(L, (int)i, (int)(i - w - 1));
-                if (NE) unite(L, (int)i, (int)(i - w + 1));
+                if (vNW > 0) unite(L, i, i - w - 1);
+                if (hasN && hasE && q[-w + 1]) unite(L, i, i - w + 1);
             }
             // ccl_init_kernel already joined W inside a 32-pixel segment; join across segment boundaries here
-            if (W && (i & 31) == 0) unite(L, (int)i, (int)(i - 1));
+            if (W && (i & 31) == 0) unite(L, i, i - 1);
         } else {                                  // background: 4-connectivity
-            if (N && !implied) unite(L, (int)i, (int)(i - w));
-            if (W && (i & 31) == 0) unite(L, (int)i, (int)(i - 1));
+            if (N && !implied) unite(L, i, i - w);
+            if (W && (i & 31) == 0) unite(L, i, i - 1);
         }
     }
 }
@@ -159,17 +186,21 @@ __global__ void cand_flag_kernel(const uint8_t* __restrict__ bm, const int* __re
 // cand[p][r]: r-th contour of page p in cv2 order (descending start pixel); counts[p] = min(total, maxc)
 __global__ void compact_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ flags, const int* __restrict__ pos,
                                int* __restrict__ cand, int* __restrict__ counts, int n, int hw, int maxc) {
-    int64_t total = (int64_t)n * hw;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int p = (int)(i / hw);
-        int64_t first = (int64_t)p * hw, last = first + hw - 1;
-        int page_total = pos[last] + flags[last] - pos[first];
-        if (i == first) counts[p] = page_total < maxc ? page_total : maxc;
-        if (!flags[i]) continue;
+    const unsigned total = (unsigned)n * (unsigned)hw;
+    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gtid < (unsigned)n) {                                        // one thread per page: its candidate count
+        const unsigned first = gtid * (unsigned)hw, last = first + hw - 1;
+        const int page_total = pos[last] + flags[last] - pos[first];
+        counts[gtid] = page_total < maxc ? page_total : maxc;
+    }
+    for (unsigned i = gtid; i < total; i += gridDim.x * blockDim.x) {
+        if (!flags[i]) continue;                                     // almost every pixel stops here
+        const unsigned p = i / (unsigned)hw, first = p * (unsigned)hw, last = first + hw - 1;
+        const int page_total = pos[last] + flags[last] - pos[first];
         int r = page_total - 1 - (pos[i] - pos[first]);
         if (r >= maxc) continue;
         int local = (int)(i - first);
-        cand[(int64_t)p * maxc + r] = bm[i] ? local : ((local - 1) | kHoleBit);
+        cand[(size_t)p * maxc + r] = bm[i] ? local : ((local - 1) | kHoleBit);
     }
 }
 
@@ -229,7 +260,8 @@ __global__ void contour_box_kernel(const uint8_t* __restrict__ bm, const int* __
 constexpr int kWarpCap = 1024;
 constexpr int kWarpHull = 256;
 constexpr int kWarpsPerBlock = 4;
-constexpr size_t kWarpSmem = (size_t)kWarpCap * 8 + (size_t)(kWarpCap + 2) * 4 + (size_t)kWarpCap * 4 + (size_t)kWarpHull * 20;
+constexpr size_t kWarpSmem = (size_t)kWarpCap * 8 + (size_t)(kWarpCap + 4) * 4 + (size_t)kWarpCap * 4 + (size_t)kWarpHull * 20;
+static_assert((size_t)kWarpHull * 20 >= (size_t)(kWarpCap + 4) * 4 + 16, "the lower Sklansky chains borrow the calipers' scratch");
 
 __device__ __forceinline__ unsigned neighbour_mask(const Bitmap& img, int x, int y, int lane) {
     int v = 0;
@@ -237,10 +269,58 @@ __device__ __forceinline__ unsigned neighbour_mask(const Bitmap& img, int x, int
     return __ballot_sync(0xffffffffu, v != 0) & 0xffu;
 }
 
+// A 32 x 32 pixel window of the bitmap held by the warp in registers, one 32-bit row mask per lane.  Border following is
+// serial and every step needs the 8 neighbours of the current pixel: out of the window that is three shuffles instead of
+// a dependent global-memory round trip (the longest contour of a batch IS the latency of DBPostProcess).  The window is
+// re-loaded (one round trip: eight 4-byte loads per lane) when the walk comes within one pixel of its edge, placed ahead
+// of the walk in its current direction.
+struct TraceWindow {
+    int x0 = 0, y0 = 0;        // origin; x0 is a multiple of 4
+    unsigned bits = 0;         // this lane's row: bit c = pixel (x0 + c, y0 + lane), 0 outside the image
+    bool valid = false, usable = false;
+};
+
+__device__ __forceinline__ void window_load(const Bitmap& img, TraceWindow& wd, int cx, int cy, int s, int lane) {
+    const int x0 = (cx - 16 + 10 * dir_dx(s)) & ~3, y0 = cy - 16 + 10 * dir_dy(s);
+    const int y = y0 + lane;
+    unsigned bits = 0;
+    if ((unsigned)y < (unsigned)img.h) {
+        const uint8_t* row = img.p + (size_t)y * img.w;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int x = x0 + 4 * k;
+            if (x >= 0 && x < img.w) {           // w % 4 == 0 and x % 4 == 0: the word is entirely inside the row
+                const unsigned wv = *reinterpret_cast<const unsigned*>(row + x) & 0x01010101u;
+                bits |= ((wv * 0x10204080u) >> 28) << (4 * k);
+            }
+        }
+    }
+    wd.x0 = x0; wd.y0 = y0; wd.bits = bits; wd.valid = true;
+}
+
+// bit d = pixel at direction d from (x, y) — the same value neighbour_mask returns
+__device__ __forceinline__ unsigned window_mask(const Bitmap& img, TraceWindow& wd, int x, int y, int s, int lane) {
+    if (!wd.usable) return neighbour_mask(img, x, y, lane);
+    int cx = x - wd.x0, cy = y - wd.y0;
+    if (!wd.valid || cx < 1 || cx > 30 || cy < 1 || cy > 30) {
+        window_load(img, wd, x, y, s, lane);
+        cx = x - wd.x0;
+        cy = y - wd.y0;
+    }
+    const unsigned u = (__shfl_sync(0xffffffffu, wd.bits, cy - 1) >> (cx - 1)) & 7u;
+    const unsigned m = (__shfl_sync(0xffffffffu, wd.bits, cy) >> (cx - 1)) & 7u;
+    const unsigned d = (__shfl_sync(0xffffffffu, wd.bits, cy + 1) >> (cx - 1)) & 7u;
+    // 0 E, 1 NE, 2 N, 3 NW, 4 W, 5 SW, 6 S, 7 SE (dir_dx / dir_dy)
+    return ((m >> 2) & 1u) | (((u >> 2) & 1u) << 1) | (((u >> 1) & 1u) << 2) | ((u & 1u) << 3) | ((m & 1u) << 4) |
+           ((d & 1u) << 5) | (((d >> 1) & 1u) << 6) | (((d >> 2) & 1u) << 7);
+}
+
 // Warp-cooperative twin of geom::trace_contour (identical point sequence); all lanes return the point count.
 __device__ int warp_trace_contour(const Bitmap& img, int sx, int sy, bool is_hole, uint64_t* keys, int cap, int lane) {
     int s_end = is_hole ? 0 : 4, s = s_end;
-    unsigned mask = neighbour_mask(img, sx, sy, lane);
+    TraceWindow wd;
+    wd.usable = (img.w & 3) == 0 && (reinterpret_cast<uintptr_t>(img.p) & 3) == 0;
+    unsigned mask = window_mask(img, wd, sx, sy, s, lane);
     do {
         s = (s - 1) & 7;
     } while (!((mask >> s) & 1u) && s != s_end);
@@ -291,8 +371,8 @@ __device__ int warp_trace_contour(const Bitmap& img, int sx, int sy, bool is_hol
                 ptx += dir * k;
             }
         }
+        mask = window_mask(img, wd, i3x, i3y, s, lane);
         s = (s + 4) & 7;
-        mask = neighbour_mask(img, i3x, i3y, lane);
     }
     return n;
 }
@@ -312,60 +392,135 @@ __device__ void warp_bitonic_sort(uint64_t* a, int npow2, int lane) {
         }
 }
 
+// cv::convexHull on the sorted keys with the four Sklansky chains (top-left, top-right, bottom-left, bottom-right) walked
+// by four lanes at once instead of one after the other on lane 0: the chains are independent, each is as serial as
+// border following, and together they were the longest phase of the kernel.  The chain stacks live where convex_hull puts
+// them (top-right right behind top-left, ...) once their lengths are known, so the assembly below is geom::convex_hull's
+// own code path: `stack` and `stack2` (n + 4 ints each) hold the upper and the lower pair.
+__device__ int warp_convex_hull(uint64_t* keys, int n, int* stack, int* stack2, int* hull, int lane) {
+    if (n == 0) return 0;
+    // first index of the minimum / maximum y (the serial scan keeps the first one: strict comparisons)
+    int miny = 0, maxy = 0;
+    {
+        int bmin = 0x7fffffff, imin = 0x7fffffff, bmax = -0x7fffffff, imax = 0x7fffffff;
+        for (int i = lane; i < n; i += 32) {
+            const int y = key_y(keys[i]);
+            if (y < bmin) { bmin = y; imin = i; }
+            if (y > bmax) { bmax = y; imax = i; }
+        }
+        for (int o = 16; o; o >>= 1) {
+            const int y1 = __shfl_xor_sync(0xffffffffu, bmin, o), i1 = __shfl_xor_sync(0xffffffffu, imin, o);
+            if (y1 < bmin || (y1 == bmin && i1 < imin)) { bmin = y1; imin = i1; }
+            const int y2 = __shfl_xor_sync(0xffffffffu, bmax, o), i2 = __shfl_xor_sync(0xffffffffu, imax, o);
+            if (y2 > bmax || (y2 == bmax && i2 < imax)) { bmax = y2; imax = i2; }
+        }
+        miny = imin;
+        maxy = imax;
+    }
+    if (key_x(keys[0]) == key_x(keys[n - 1]) && key_y(keys[0]) == key_y(keys[n - 1])) {
+        if (lane == 0) hull[0] = 0;
+        return 1;
+    }
+    // the four chains, each into its own region: tl at stack[0..], tr at stack[maxy + 3 ..], bl / br likewise in stack2
+    int cnt = 0;
+    if (lane == 0) cnt = sklansky(keys, 0, maxy, stack, -1, 1);
+    else if (lane == 1) cnt = sklansky(keys, n - 1, maxy, stack + maxy + 3, -1, -1);
+    else if (lane == 2) cnt = sklansky(keys, 0, miny, stack2, 1, -1);
+    else if (lane == 3) cnt = sklansky(keys, n - 1, miny, stack2 + miny + 3, 1, 1);
+    __syncwarp();
+    int tl_count = __shfl_sync(0xffffffffu, cnt, 0), tr_count = __shfl_sync(0xffffffffu, cnt, 1);
+    int bl_count = __shfl_sync(0xffffffffu, cnt, 2), br_count = __shfl_sync(0xffffffffu, cnt, 3);
+    int nout = 0;
+    if (lane == 0) {
+        // geom::convex_hull with clockwise = false from here on (the upper pair is swapped)
+        const int* tl_stack = stack + maxy + 3;            // <- tr
+        const int* tr_stack = stack;                       // <- tl
+        { int c = tl_count; tl_count = tr_count; tr_count = c; }
+        for (int i = 0; i < tl_count - 1; ++i) hull[nout++] = tl_stack[i];
+        for (int i = tr_count - 1; i > 0; --i) hull[nout++] = tr_stack[i];
+        const int stop_idx = tr_count > 2 ? tr_stack[1] : tl_count > 2 ? tl_stack[tl_count - 2] : -1;
+        const int* bl_stack = stack2;
+        const int* br_stack = stack2 + miny + 3;
+        if (stop_idx >= 0) {
+            // convex_hull reads br_stack[2 - bl_count] with br_stack == bl_stack + bl_count, i.e. entry 2 of the pair
+            const int check_idx = bl_count > 2 ? bl_stack[1] : bl_count + br_count > 2 ? br_stack[2 - bl_count] : -1;
+            if (check_idx == stop_idx ||
+                (check_idx >= 0 && key_x(keys[check_idx]) == key_x(keys[stop_idx]) && key_y(keys[check_idx]) == key_y(keys[stop_idx]))) {
+                bl_count = bl_count < 2 ? bl_count : 2;
+                br_count = br_count < 2 ? br_count : 2;
+            }
+        }
+        for (int i = 0; i < bl_count - 1; ++i) hull[nout++] = bl_stack[i];
+        for (int i = br_count - 1; i > 0; --i) hull[nout++] = br_stack[i];
+        nout = hull_index_shift(keys, hull, nout, stack);
+    }
+    return __shfl_sync(0xffffffffu, nout, 0);
+}
+
+// One warp per candidate contour; the grid is persistent (a few blocks per SM) and every warp walks the dense list of the
+// batch's candidates (page p contributes counts[p] of its maxc slots), so no block is launched for the empty slots.
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) contour_warp_kernel(
     const uint8_t* __restrict__ bm, const int* __restrict__ cand, const int* __restrict__ counts, float* __restrict__ box1,
-    uint8_t* __restrict__ valid, int* __restrict__ n_flagged, int n, int h, int w, int maxc, float min_size) {
+    uint8_t* __restrict__ valid, int* __restrict__ n_flagged, int n, int h, int w, int maxc, float min_size, int dbg_phase) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * kWarpsPerBlock + warp;
-    if (t >= n * maxc) return;
     uint8_t* base = smem + (size_t)warp * kWarpSmem;
     uint64_t* keys = (uint64_t*)base;
     int* stack = (int*)(base + (size_t)kWarpCap * 8);
-    int* hull = stack + kWarpCap + 2;
+    int* hull = stack + kWarpCap + 4;
     PtF* hp = (PtF*)(hull + kWarpCap);
     PtF* vect = hp + kWarpHull;
     float* inv = (float*)(vect + kWarpHull);
-    const int p = t / maxc, r = t % maxc;
-    if (r >= counts[p]) {
-        if (lane == 0) valid[t] = 0;
-        return;
-    }
-    const int c = cand[t];
-    const int local = c & (kHoleBit - 1);
-    Bitmap img{bm + (size_t)p * h * w, h, w};
-    int np = warp_trace_contour(img, local % w, local / w, (c & kHoleBit) != 0, keys, kWarpCap, lane);
-    if (np > kWarpCap) {
-        if (lane == 0) { valid[t] = 2; atomicAdd(n_flagged, 1); }
-        return;
-    }
-    __syncwarp();
-    int npow2 = 1;
-    while (npow2 < np) npow2 <<= 1;
-    for (int i = np + lane; i < npow2; i += 32) keys[i] = ~(uint64_t)0;
-    __syncwarp();
-    warp_bitonic_sort(keys, npow2, lane);
-    if (lane == 0) {
-        int nh = convex_hull(keys, np, stack, hull, false, true);
-        if (nh > kWarpHull) {
-            valid[t] = 2;
-            atomicAdd(n_flagged, 1);
-        } else {
-            for (int i = 0; i < nh; ++i) {
-                hp[i].x = (float)key_x(keys[hull[i]]);
-                hp[i].y = (float)key_y(keys[hull[i]]);
-            }
-            RotRect rr = min_area_rect(hp, nh, vect, inv);
-            PtF box[4];
-            float sside = mini_box(rr, box);
-            if (sside < min_size) {
-                valid[t] = 0;
+    int* stack2 = (int*)hp;                                // lower chains: the calipers' scratch is free until the hull exists
+    // slots beyond a page's count are simply invalid
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n * maxc; t += gridDim.x * blockDim.x)
+        if (t % maxc >= counts[t / maxc]) valid[t] = 0;
+    int total = 0;
+    for (int p = 0; p < n; ++p) total += counts[p];
+    for (int j = blockIdx.x * kWarpsPerBlock + warp; j < total; j += gridDim.x * kWarpsPerBlock) {
+        int p = 0, r = j;
+        while (r >= counts[p]) { r -= counts[p]; ++p; }
+        const int t = p * maxc + r;
+        const int c = cand[t];
+        const int local = c & (kHoleBit - 1);
+        Bitmap img{bm + (size_t)p * h * w, h, w};
+        __syncwarp();
+        int np = warp_trace_contour(img, local % w, local / w, (c & kHoleBit) != 0, keys, kWarpCap, lane);
+        if (np > kWarpCap) {
+            if (lane == 0) { valid[t] = 2; atomicAdd(n_flagged, 1); }
+            continue;
+        }
+        __syncwarp();
+        if (dbg_phase == 1) { if (lane == 0) valid[t] = 0; continue; }      // timing experiments only (B200OCR_DBG_CONTOUR)
+        int npow2 = 1;
+        while (npow2 < np) npow2 <<= 1;
+        for (int i = np + lane; i < npow2; i += 32) keys[i] = ~(uint64_t)0;
+        __syncwarp();
+        warp_bitonic_sort(keys, npow2, lane);
+        if (dbg_phase == 2) { if (lane == 0) valid[t] = 0; continue; }
+        const int nh = warp_convex_hull(keys, np, stack, stack2, hull, lane);
+        if (dbg_phase == 3) { if (lane == 0) valid[t] = 0; continue; }
+        if (lane == 0) {
+            if (nh > kWarpHull) {
+                valid[t] = 2;
+                atomicAdd(n_flagged, 1);
             } else {
-                for (int i = 0; i < 4; ++i) {
-                    box1[(size_t)t * 8 + 2 * i] = box[i].x;
-                    box1[(size_t)t * 8 + 2 * i + 1] = box[i].y;
+                for (int i = 0; i < nh; ++i) {
+                    hp[i].x = (float)key_x(keys[hull[i]]);
+                    hp[i].y = (float)key_y(keys[hull[i]]);
                 }
-                valid[t] = 1;
+                RotRect rr = min_area_rect(hp, nh, vect, inv);
+                PtF box[4];
+                float sside = mini_box(rr, box);
+                if (sside < min_size) {
+                    valid[t] = 0;
+                } else {
+                    for (int i = 0; i < 4; ++i) {
+                        box1[(size_t)t * 8 + 2 * i] = box[i].x;
+                        box1[(size_t)t * 8 + 2 * i + 1] = box[i].y;
+                    }
+                    valid[t] = 1;
+                }
             }
         }
     }
@@ -536,12 +691,13 @@ void Stages::db_post_enqueue(int lane, const float* d_prob, int n, int h, int w,
         int dev = 0;
         cudaGetDevice(&dev);
         size_t smem = kWarpSmem * kWarpsPerBlock;
+        static const int dbg_phase = [] { const char* e = getenv("B200OCR_DBG_CONTOUR"); return e ? atoi(e) : 0; }();
         if (!attr_set[dev & 15]) {
             B200_CUDA_CHECK(cudaFuncSetAttribute(contour_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set[dev & 15] = true;
         }
-        contour_warp_kernel<<<(unsigned)ceil_div(nt, kWarpsPerBlock), 32 * kWarpsPerBlock, smem, st>>>(
-            bm, cand, counts, box1, valid, d_flagged, n, h, w, maxc, (float)p.min_size);
+        contour_warp_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nt, kWarpsPerBlock), 148 * 2), 32 * kWarpsPerBlock, smem, st>>>(
+            bm, cand, counts, box1, valid, d_flagged, n, h, w, maxc, (float)p.min_size, dbg_phase);
     }
     B200_CUDA_CHECK(cudaMemcpyAsync(h_counts, counts, n * sizeof(int), cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaMemcpyAsync(h_counts + n, d_flagged, sizeof(int), cudaMemcpyDeviceToHost, st));
