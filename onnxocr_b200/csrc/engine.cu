@@ -985,6 +985,51 @@ void Model::build_steps(Plan& p) {
                     const int tiles_x = (int)ceil_div(Wo, kPsTW), tiles_y = (int)ceil_div(Ho, kPsTH), tiles = tiles_x * tiles_y * iv.n;
                     cost_bytes = (double)iv.n * iv.h * iv.w * 3 + vbytes(out) + 27.0 * 16 * 4;
                     const int ih = iv.h, iw = iv.w;
+                    // bf16 plans: the stem as a tensor-core GEMM (B200OCR_STEM_MMA=0 keeps the FFMA kernel, which is
+                    // bit-identical to conv_stem_kernel)
+                    static const bool stem_mma = [] { const char* e = getenv("B200OCR_STEM_MMA"); return !(e && e[0] == '0'); }();
+                    if (std::is_same<T, bf16>::value && stem_mma) {
+                        std::unique_ptr<StemMmaTab> ht(new StemMmaTab());
+                        auto wk = [&](int k, int n) -> float {          // K index = tap * 4 + channel (BGR0)
+                            return (k < 36 && (k & 3) < 3) ? sw.w[(k >> 2) * 3 + (k & 3)][n] : 0.f;
+                        };
+                        auto split = [&](float v, int part) -> uint32_t {
+                            const bf16 hi = __float2bfloat16(v);
+                            const bf16 out = part == 0 ? hi : __float2bfloat16(v - __bfloat162float(hi));
+                            uint16_t u;
+                            memcpy(&u, &out, 2);
+                            return u;
+                        };
+                        for (int part = 0; part < 2; ++part)
+                            for (int ks = 0; ks < 3; ++ks)
+                                for (int jn = 0; jn < 2; ++jn)
+                                    for (int ln = 0; ln < 32; ++ln)
+                                        for (int r = 0; r < 2; ++r) {
+                                            const int gq = ln >> 2, tq = ln & 3, n = 8 * jn + gq, k = 16 * ks + 8 * r + 2 * tq;
+                                            ht->b[part][ks][jn][ln][r] = split(wk(k, n), part) | (split(wk(k + 1, n), part) << 16);
+                                        }
+                        for (int co = 0; co < 16; ++co) ht->bias[co] = sw.b[co];
+                        StemMmaTab* dtab = nullptr;
+                        B200_CUDA_CHECK(cudaMalloc(&dtab, sizeof(StemMmaTab)));
+                        p.owned.emplace_back(dtab, [](void* q) { cudaFree(q); });
+                        B200_CUDA_CHECK(cudaMemcpy(dtab, ht.get(), sizeof(StemMmaTab), cudaMemcpyHostToDevice));
+                        const bool hsw = cp.epi.n > 0 && cp.epi.fast && cp.epi.act == EPI_HSWISH;
+                        emit("pre+stem " + c.name, [=](cudaStream_t st) {
+                            NormP nrm;
+                            nrm.mul = pp->pre_norm[0];
+                            for (int k = 0; k < 3; ++k) { nrm.sub[k] = pp->pre_norm[1 + k]; nrm.div[k] = pp->pre_norm[4 + k]; }
+                            nrm.rec_style = (int)pp->pre_norm[7];
+                            const unsigned grid = (unsigned)std::min(tiles, 148 * 8);
+                            if (hsw)
+                                launch_pdl(pre_stem_mma_kernel<EPI_HSWISH>, grid, 256, 0, st, (const ResizeJob*)pp->pre_jobs, ih, iw, nrm,
+                                           (const StemMmaTab*)dtab, (bf16*)pp->ptr(out), cp, tiles_x, tiles_y, tiles);
+                            else
+                                launch_pdl(pre_stem_mma_kernel<-1>, grid, 256, 0, st, (const ResizeJob*)pp->pre_jobs, ih, iw, nrm,
+                                           (const StemMmaTab*)dtab, (bf16*)pp->ptr(out), cp, tiles_x, tiles_y, tiles);
+                        });
+                        vid[c.out] = out;
+                        break;
+                    }
                     emit("pre+stem " + c.name, [=](cudaStream_t st) {
                         NormP nrm;
                         nrm.mul = pp->pre_norm[0];

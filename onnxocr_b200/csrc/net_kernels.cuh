@@ -1200,25 +1200,38 @@ __global__ void __launch_bounds__(256) concat_multi_bf16_kernel(bf16* __restrict
     pdl_start();
     // grid (row chunks, H, N): one division per thread (in-row index -> pixel, chunk); upsampling by shifts.  The input a
     // chunk comes from is looked up (kmap) and its parameters are read with a run-time index, so the lanes of a warp —
-    // which span several inputs — all execute the same instruction stream instead of one branch per input.
+    // which span several inputs — all execute the same instruction stream instead of one branch per input.  The tables
+    // are first copied to shared memory: indexed reads of kernel parameters go through the constant cache, which serves
+    // one address per cycle — a warp spanning 12 chunks of 4 inputs replayed every one of those loads 4 to 12 times.
+    __shared__ unsigned char s_kmap[kCatMaxChunks];
+    __shared__ const bf16* s_src[kCatMaxIn];
+    __shared__ const float* s_scale[kCatMaxIn];
+    __shared__ int s_fh[kCatMaxIn], s_fw[kCatMaxIn], s_csp[kCatMaxIn], s_g0[kCatMaxIn], s_res[kCatMaxIn];
+    if (threadIdx.x < kCatMaxChunks) s_kmap[threadIdx.x] = p.kmap[threadIdx.x];
+    if (threadIdx.x < kCatMaxIn) {
+        const int k = threadIdx.x;
+        s_src[k] = p.src[k]; s_scale[k] = p.scale[k]; s_fh[k] = p.fh[k]; s_fw[k] = p.fw[k];
+        s_csp[k] = p.CsP[k]; s_g0[k] = p.g0[k]; s_res[k] = p.res[k];
+    }
+    __syncthreads();
     const uint32_t cg = (uint32_t)p.CdP >> 3;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= (uint32_t)p.W * cg) return;
     const uint32_t xw = j / cg, g = j - xw * cg;
     const uint32_t yh = blockIdx.y, n = blockIdx.z;
-    const int k = p.kmap[g];
+    const int k = s_kmap[g];
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (k != 255) {
-        const int fh = p.fh[k], fw = p.fw[k], csp = p.CsP[k];
+        const int fh = s_fh[k], fw = s_fw[k], csp = s_csp[k];
         const uint32_t Hs = (uint32_t)p.H >> fh, Ws = (uint32_t)p.W >> fw;
-        const uint32_t c = (g - (uint32_t)p.g0[k]) * 8u;
-        v = *reinterpret_cast<const uint4*>(p.src[k] + ((size_t)(n * Hs + (yh >> fh)) * Ws + (xw >> fw)) * csp + c);
-        const float* sc = p.scale[k];
+        const uint32_t c = (g - (uint32_t)s_g0[k]) * 8u;
+        v = *reinterpret_cast<const uint4*>(s_src[k] + ((size_t)(n * Hs + (yh >> fh)) * Ws + (xw >> fw)) * csp + c);
+        const float* sc = s_scale[k];
         if (sc) {
             const float4 s0 = *reinterpret_cast<const float4*>(sc + (size_t)n * csp + c);
             const float4 s1 = *reinterpret_cast<const float4*>(sc + (size_t)n * csp + c + 4);
             const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            const float keep = p.res[k] ? 1.f : 0.f;      // x * s + x  ==  x * s + keep * x  (same two roundings)
+            const float keep = s_res[k] ? 1.f : 0.f;      // x * s + x  ==  x * s + keep * x  (same two roundings)
             uint32_t* u = &v.x;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -1408,6 +1421,138 @@ __global__ void __launch_bounds__(256) pre_stem_kernel(const ResizeJob* __restri
 #pragma unroll
                 for (int c = 0; c < 16; c += 4)
                     if (c < p.CoutP) ST<T>::st4(dst + c, o + c);
+            }
+        }
+    }
+}
+
+// The same fused pre-processing + stem on the tensor cores (bf16 plans).  On CUDA cores the 432 FMAs per output pixel
+// make the kernel issue-bound at 3x its memory time (ncu: 68 M warp instructions, FMA pipe 34 %, 0.165 ms for 16 pages);
+// as a GEMM the stem is M = pixels, N = 16, K = 9 taps x 4 channels (BGR0) = 36 -> 48: three k-steps of
+// mma.sync.m16n8k16 (bf16 x bf16 -> fp32), two n-tiles.  The normalised input is bf16 already (that is what the two-kernel
+// path stores), the fp32 weights are split into bf16 hi + lo parts (two MMAs), so the products carry 16 mantissa bits —
+// the result differs from the FFMA kernel only by fp32 summation order.  A warp owns one row of 32 output pixels (two
+// m16 tiles); the A fragments are gathered straight from the staged tile: pixel = (2*oy + ky, 2*ox + kx), one 8-byte
+// BGR0 group per pixel, the fragment's k pairs are the channel pairs of consecutive taps (conflict-free 4-byte loads).
+// B fragments (per lane: 3 k-steps x 2 n-tiles x 2 registers, hi and lo) come from a table built when the plan is built.
+struct StemMmaTab {
+    uint32_t b[2][3][2][32][2];       // [hi, lo][k-step][n-tile][lane][b0, b1]
+    float bias[16];
+};
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int kPmPitch = kPsRW * 2;   // 32-bit words per tile row (two per pixel)
+
+template <int ACT>
+__global__ void __launch_bounds__(256) pre_stem_mma_kernel(const ResizeJob* __restrict__ jobs, int IH, int IW, const NormP nrm,
+                                                           const StemMmaTab* __restrict__ tab, bf16* __restrict__ y,
+                                                           const ConvP p, int tiles_x, int tiles_y, int tiles) {
+    pdl_start();
+    __shared__ uint16_t lut[3][256];
+    __shared__ __align__(16) uint32_t tile[kPsRH][kPmPitch];
+    const int tid = threadIdx.x, lane = tid & 31, ly = tid >> 5, g = lane >> 2, tig = lane & 3;
+    for (int i = tid; i < 768; i += 256) {
+        const int c = i >> 8, v = i & 255;
+        lut[c][v] = __bfloat16_as_ushort(__float2bfloat16_rn(norm_px(v, c, nrm)));
+    }
+    uint32_t bh[3][2][2], bl[3][2][2];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                bh[s][j][r] = tab->b[0][s][j][lane][r];
+                bl[s][j][r] = tab->b[1][s][j][lane][r];
+            }
+    float bias[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        bias[j][0] = tab->bias[8 * j + 2 * tig];
+        bias[j][1] = tab->bias[8 * j + 2 * tig + 1];
+    }
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int tx = t % tiles_x;
+        const int r = t / tiles_x;
+        const int ty = r % tiles_y, n = r / tiles_y;
+        const ResizeJob j = jobs[n];
+        const int iy0 = 2 * ty * kPsTH - 1, ix0 = 2 * tx * kPsTW - 1;
+        __syncthreads();                                    // table ready / previous tile consumed
+        for (int q = tid; q < kPsRH * kPsRW; q += 256) {
+            const int ry = q / kPsRW, rx = q - ry * kPsRW;
+            const int iy = iy0 + ry, ix = ix0 + rx;
+            uint2 v = make_uint2(0u, 0u);
+            if ((unsigned)iy < (unsigned)IH && (unsigned)ix < (unsigned)IW && ix < j.dw && iy < j.dh) {
+                int px[3];
+                resize_px(j.src, j.dh, j.dw, j.scale_y, j.scale_x, iy, ix, px);
+                v.x = (uint32_t)lut[0][px[0]] | ((uint32_t)lut[1][px[1]] << 16);
+                v.y = (uint32_t)lut[2][px[2]];
+            }
+            *reinterpret_cast<uint2*>(&tile[ry][2 * rx]) = v;
+        }
+        __syncthreads();
+        const int oy = ty * kPsTH + ly;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            float acc[2][4];
+#pragma unroll
+            for (int jn = 0; jn < 2; ++jn) { acc[jn][0] = acc[jn][2] = bias[jn][0]; acc[jn][1] = acc[jn][3] = bias[jn][1]; }
+            // word index of (tap, pixel row `g` of this m-tile): ((2 ly + ky) * 65 + 2 x + kx) * 2 + (tig & 1)
+            const int xw = 2 * (mt * 16 + g);               // input column of kx = 0 for output pixel g
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                uint32_t a[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {      // k 0..7 (a0, a1) and k 8..15 (a2, a3) of this k-step
+                    const int tap = 4 * s + 2 * half + (tig >> 1);
+                    if (4 * s + 2 * half <= 8) {            // compile time: the last k-step has only tap 8
+                        const int ky = tap / 3, kx = tap - 3 * ky;
+                        if (tap <= 8) {
+                            const uint32_t* row = &tile[2 * ly + ky][0];
+                            const int w0 = (xw + kx) * 2 + (tig & 1);
+                            a[2 * half] = row[w0];
+                            a[2 * half + 1] = row[w0 + 32];   // output pixel g + 8: 16 input pixels = 32 words further
+                        }
+                    }
+                }
+#pragma unroll
+                for (int jn = 0; jn < 2; ++jn) {
+                    mma_bf16_16816(acc[jn], a[0], a[1], a[2], a[3], bh[s][jn][0], bh[s][jn][1]);
+                    mma_bf16_16816(acc[jn], a[0], a[1], a[2], a[3], bl[s][jn][0], bl[s][jn][1]);
+                }
+            }
+            // epilogue: acc[jn][0..1] = pixel g, channels 8 jn + 2 tig (+1); acc[jn][2..3] = pixel g + 8
+            uint32_t item[4];                                // [pixel g: words tig, 4 + tig] [pixel g + 8: words tig, 4 + tig]
+#pragma unroll
+            for (int jn = 0; jn < 2; ++jn)
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int c0 = 8 * jn + 2 * tig;
+                    const float v0 = c0 < p.Cout ? epi_fast<ACT>(acc[jn][2 * hrow], p.epi) : 0.f;
+                    const float v1 = c0 + 1 < p.Cout ? epi_fast<ACT>(acc[jn][2 * hrow + 1], p.epi) : 0.f;
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                    item[2 * hrow + jn] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+            // 4 x 4 transpose inside the quad: lane q ends up with words 4 (q & 1) .. 4 (q & 1) + 3 of pixel g + 8 (q >> 1)
+            uint32_t out[4];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int pub = (tig - rr) & 3;              // the item this lane publishes in round rr
+                const uint32_t v = pub == 0 ? item[0] : pub == 1 ? item[1] : pub == 2 ? item[2] : item[3];
+                const uint32_t got = __shfl_sync(0xffffffffu, v, (lane & ~3) | ((tig + rr) & 3));
+                const int slot = (tig + rr) & 3;             // it came from lane `slot` of the quad = word index within the group
+                if (slot == 0) out[0] = got; else if (slot == 1) out[1] = got; else if (slot == 2) out[2] = got; else out[3] = got;
+            }
+            const int ox = tx * kPsTW + mt * 16 + g + 8 * (tig >> 1);
+            if (oy < p.Ho && ox < p.Wo) {
+                bf16* dst = y + (((int64_t)n * p.Ho + oy) * p.Wo + ox) * 16 + 8 * (tig & 1);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
             }
         }
     }

@@ -1,6 +1,7 @@
-"""Summarise `ncu --page raw --csv` exports (one kernel each) into a markdown table + profiles/r1_traffic.json.
+"""Summarise `ncu --page raw --csv` exports (one kernel each) into a markdown table + profiles/<round>_traffic.json.
 
-    python tools/summarize_ncu_raw.py gpurun_out/ncu_raw_*.csv
+    python tools/summarize_ncu_raw.py gpurun_out/ncu_raw_*.csv             (round 1 names)
+    ROUND=r2 python tools/summarize_ncu_raw.py gpurun_out/r2_ncu_raw_*.csv
 """
 import csv
 import json
@@ -29,7 +30,7 @@ def main(paths):
         if len(rows) < 3:
             continue
         hdr, units, r = rows[0], rows[1], rows[2]
-        name = os.path.basename(p).replace("ncu_raw_", "").replace(".csv", "")
+        name = os.path.basename(p).replace("r2_ncu_raw_", "").replace("ncu_raw_", "").replace(".csv", "")
         kern = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("b200ocr::", "")
         vals = {}
         for k, label in KEYS:
@@ -54,7 +55,7 @@ def main(paths):
     print("|---|---|" + "---|" * len(labels))
     for name, kern, vals in out:
         print("| %s | `%s` | " % (name, kern[:48]) + " | ".join(vals.get(l, "") for l in labels) + " |")
-    json.dump(traffic, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r1_traffic.json"), "w"), indent=1)
+    json.dump(traffic, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", os.environ.get("ROUND", "r1") + "_traffic.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
