@@ -1014,6 +1014,7 @@ void Model::build_steps(Plan& p) {
                         p.owned.emplace_back(dtab, [](void* q) { cudaFree(q); });
                         B200_CUDA_CHECK(cudaMemcpy(dtab, ht.get(), sizeof(StemMmaTab), cudaMemcpyHostToDevice));
                         const bool hsw = cp.epi.n > 0 && cp.epi.fast && cp.epi.act == EPI_HSWISH;
+                        const bool affine_only = cp.epi.fast && cp.epi.act == 0;        // BN folded, no activation (LCNetV3 stem)
                         emit("pre+stem " + c.name, [=](cudaStream_t st) {
                             NormP nrm;
                             nrm.mul = pp->pre_norm[0];
@@ -1022,6 +1023,9 @@ void Model::build_steps(Plan& p) {
                             const unsigned grid = (unsigned)std::min(tiles, 148 * 8);
                             if (hsw)
                                 launch_pdl(pre_stem_mma_kernel<EPI_HSWISH>, grid, 256, 0, st, (const ResizeJob*)pp->pre_jobs, ih, iw, nrm,
+                                           (const StemMmaTab*)dtab, (bf16*)pp->ptr(out), cp, tiles_x, tiles_y, tiles);
+                            else if (affine_only)
+                                launch_pdl(pre_stem_mma_kernel<0>, grid, 256, 0, st, (const ResizeJob*)pp->pre_jobs, ih, iw, nrm,
                                            (const StemMmaTab*)dtab, (bf16*)pp->ptr(out), cp, tiles_x, tiles_y, tiles);
                             else
                                 launch_pdl(pre_stem_mma_kernel<-1>, grid, 256, 0, st, (const ResizeJob*)pp->pre_jobs, ih, iw, nrm,

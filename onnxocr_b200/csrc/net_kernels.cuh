@@ -1450,7 +1450,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
 constexpr int kPmPitch = kPsRW * 2;   // 32-bit words per tile row (two per pixel)
 
 template <int ACT>
-__global__ void __launch_bounds__(256) pre_stem_mma_kernel(const ResizeJob* __restrict__ jobs, int IH, int IW, const NormP nrm,
+__global__ void __launch_bounds__(256, 3) pre_stem_mma_kernel(const ResizeJob* __restrict__ jobs, int IH, int IW, const NormP nrm,
                                                            const StemMmaTab* __restrict__ tab, bf16* __restrict__ y,
                                                            const ConvP p, int tiles_x, int tiles_y, int tiles) {
     pdl_start();
@@ -1481,20 +1481,58 @@ __global__ void __launch_bounds__(256) pre_stem_mma_kernel(const ResizeJob* __re
         const int tx = t % tiles_x;
         const int r = t / tiles_x;
         const int ty = r % tiles_y, n = r / tiles_y;
-        const ResizeJob j = jobs[n];
+        const ResizeJob& j = jobs[n];
         const int iy0 = 2 * ty * kPsTH - 1, ix0 = 2 * tx * kPsTW - 1;
+        const int jdh = j.dh, jdw = j.dw;
+        // the common case (C2, every page that already has its network size): no resampling, no virtual padding
+        const bool ident = jdh == j.src.ph && jdw == j.src.pw && j.src.h == j.src.ph && j.src.w == j.src.pw && !j.src.rot180;
         __syncthreads();                                    // table ready / previous tile consumed
-        for (int q = tid; q < kPsRH * kPsRW; q += 256) {
-            const int ry = q / kPsRW, rx = q - ry * kPsRW;
-            const int iy = iy0 + ry, ix = ix0 + rx;
-            uint2 v = make_uint2(0u, 0u);
-            if ((unsigned)iy < (unsigned)IH && (unsigned)ix < (unsigned)IW && ix < j.dw && iy < j.dh) {
-                int px[3];
-                resize_px(j.src, j.dh, j.dw, j.scale_y, j.scale_x, iy, ix, px);
-                v.x = (uint32_t)lut[0][px[0]] | ((uint32_t)lut[1][px[1]] << 16);
-                v.y = (uint32_t)lut[2][px[2]];
+        if (ident) {
+            const uint8_t* __restrict__ sp = j.src.p;
+            const int stride = j.src.stride;
+            const int ylim = min(IH, jdh), xlim = min(IW, jdw);
+            // all byte loads of this thread's (up to 5) pixels are issued before any is used: the kernel is bound by the
+            // bytes it keeps in flight, not by instructions
+            constexpr int kIt = (kPsRH * kPsRW + 255) / 256;
+            uint32_t b0[kIt], b1[kIt], b2[kIt];
+#pragma unroll
+            for (int k = 0; k < kIt; ++k) {
+                const int q = tid + 256 * k;
+                const int ry = q / kPsRW, rx = q - ry * kPsRW;
+                const int iy = iy0 + ry, ix = ix0 + rx;
+                b0[k] = 0xffffffffu;
+                if (q < kPsRH * kPsRW && (unsigned)iy < (unsigned)ylim && (unsigned)ix < (unsigned)xlim) {
+                    const uint8_t* s = sp + (size_t)iy * stride + ix * 3;
+                    b0[k] = s[0]; b1[k] = s[1]; b2[k] = s[2];
+                }
             }
-            *reinterpret_cast<uint2*>(&tile[ry][2 * rx]) = v;
+#pragma unroll
+            for (int k = 0; k < kIt; ++k) {
+                const int q = tid + 256 * k;
+                if (q < kPsRH * kPsRW) {
+                    const int ry = q / kPsRW, rx = q - ry * kPsRW;
+                    uint2 v = make_uint2(0u, 0u);
+                    if (b0[k] != 0xffffffffu) {
+                        v.x = (uint32_t)lut[0][b0[k]] | ((uint32_t)lut[1][b1[k]] << 16);
+                        v.y = (uint32_t)lut[2][b2[k]];
+                    }
+                    *reinterpret_cast<uint2*>(&tile[ry][2 * rx]) = v;
+                }
+            }
+        } else {
+            const ResizeJob jj = j;
+            for (int q = tid; q < kPsRH * kPsRW; q += 256) {
+                const int ry = q / kPsRW, rx = q - ry * kPsRW;
+                const int iy = iy0 + ry, ix = ix0 + rx;
+                uint2 v = make_uint2(0u, 0u);
+                if ((unsigned)iy < (unsigned)IH && (unsigned)ix < (unsigned)IW && ix < jdw && iy < jdh) {
+                    int px[3];
+                    resize_px(jj.src, jdh, jdw, jj.scale_y, jj.scale_x, iy, ix, px);
+                    v.x = (uint32_t)lut[0][px[0]] | ((uint32_t)lut[1][px[1]] << 16);
+                    v.y = (uint32_t)lut[2][px[2]];
+                }
+                *reinterpret_cast<uint2*>(&tile[ry][2 * rx]) = v;
+            }
         }
         __syncthreads();
         const int oy = ty * kPsTH + ly;
