@@ -289,16 +289,18 @@ def main():
     # every layer of this network is far below the tensor ridge (<= 120 FLOP/B vs 1381e12 / 6543e9 = 211): HBM-bound
     ach = top["bytes"] / (top["ms"] / 1e3) / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")       # ncu --set full captures of the same 16-page launches
     if os.path.exists(tpath):
         with open(tpath) as fh:
             tj = json.load(fh)
-        key = {"tcconv conv2d.out_2.tmp": "tcconv_out2_packed", "tcconvT2 p2o.ConvTranspose_0.tmp": "tcconvT2",
-               "eltwise p2o.Add_82.tmp": "eltwise_add82", "conv conv2d.out_0.tmp": "stem", "tcconv conv2d.out_46.tmp": "tcconv_out46",
-               "tcconv conv2d.out_61.tmp": "tcconv3x3", "tcconv conv2d.out_58.tmp": "tcconv3x3"}.get(top["name"])
+        key = {"tcconv conv2d.out_2.tmp": "ws_out2_packed", "tcconvT2 p2o.ConvTranspose_0.tmp": "ws_convT2_tail",
+               "eltwise p2o.Add_82.tmp": "fpn_add82", "pre+stem conv2d.out_0.tmp": "pre_stem", "tcconv conv2d.out_46.tmp": "ws_out46_sums",
+               "tcconv conv2d.out_58.tmp": "ws_halo3x3_out58", "concat p2o.Concat_0.tmp": "concat",
+               "dwconv conv2d.out_1.tmp": "dw3x3_first"}.get(top["name"])
         if key in tj:
             traffic = (tj[key]["dram_read_mb"] + tj[key]["dram_write_mb"]) * 1e6
-    kern_of = {"tcconv": "tc::conv_tc_ws_kernel / tc::conv_tc_kernel<BN> (tcgen05 + TMA implicit GEMM)", "conv": "conv_stem_kernel",
+    kern_of = {"tcconv": "tc::conv_tc_ws_kernel (tcgen05 + TMA implicit GEMM, weight stationary)", "conv": "conv_stem_kernel",
+               "pre+stem": "pre_stem_mma_kernel (pre-processing fused into the stem)", "concat": "concat_multi_bf16_kernel",
                "dwconv": "dwconv_strip_kernel", "tcconvT2": "tc::conv_tc_ws_kernel with the fused DB-head tail epilogue",
                "eltwise": "eltwise_bf16x8_kernel"}.get(kernel_class(top["name"]), kernel_class(top["name"]))
     roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
@@ -308,7 +310,7 @@ def main():
             "tensor_tflops": top["flops"] / (top["ms"] / 1e3) / 1e12,
             "tensor_frac_of_sustained": top["flops"] / (top["ms"] / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
             "note": "kernel = %s for the named layer at 16 pages (%.0f FLOP per algorithmic byte, below the ridge of %.0f, so "
-                    "HBM-bound); traffic = dram read+write of one launch from profiles/r1_traffic.json (ncu --set full); output "
+                    "HBM-bound); traffic = dram read+write of one launch from profiles/r2_traffic.json (ncu --set full); output "
                     "lines still resident in the 126 MB L2 at kernel end are not in it" % (
                         kern_of, top["flops"] / max(top["bytes"], 1.0), peaks["bf16_tflops_sustained"] * 1e3 / peaks["hbm_gbs"])}
     breakdown = {k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4),
