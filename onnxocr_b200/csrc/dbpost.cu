@@ -155,6 +155,47 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restric
     }
 }
 
+// Four pixels per thread (w % 4 == 0): two aligned 4-byte loads (this row, the row above) and three single bytes
+// (left, up-left, up-right) instead of five byte loads per pixel; the links examined are exactly those of the scalar kernel.
+__global__ void __launch_bounds__(256) ccl_merge4_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int n, int h, int w) {
+    const int quads = (n * h * w) >> 2;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
+        const int i = q << 2;
+        const unsigned row = (unsigned)i / (unsigned)w;
+        const int x = i - (int)row * w, y = (int)(row % (unsigned)h);
+        const uint32_t c = *reinterpret_cast<const uint32_t*>(bm + i);
+        const bool hasN = y > 0;
+        const uint32_t u = hasN ? *reinterpret_cast<const uint32_t*>(bm + i - w) : 0xffffffffu;     // 0xff never equals a class
+        const int l = x > 0 ? bm[i - 1] : -1;
+        const int ul = hasN && x > 0 ? bm[i - w - 1] : -1;
+        const int ur = hasN && x + 4 < w ? bm[i - w + 4] : -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int v = (c >> (8 * k)) & 0xff;
+            const int vN = hasN ? (int)((u >> (8 * k)) & 0xff) : -1;
+            const int vW = k == 0 ? l : (int)((c >> (8 * (k - 1))) & 0xff);
+            const int vNW = k == 0 ? ul : (hasN ? (int)((u >> (8 * (k - 1))) & 0xff) : -1);
+            const int vNE = k == 3 ? ur : (hasN ? (int)((u >> (8 * (k + 1))) & 0xff) : -1);
+            const bool N = vN == v, W = vW == v;
+            const int p = i + k;
+            const bool implied = N && W && (p & 31) != 0 && vNW == v;
+            if (v) {                              // foreground: 8-connectivity
+                if (implied) {
+                } else if (N) {
+                    unite(L, p, p - w);
+                } else {
+                    if (vNW > 0) unite(L, p, p - w - 1);
+                    if (vNE > 0) unite(L, p, p - w + 1);
+                }
+                if (W && (p & 31) == 0) unite(L, p, p - 1);
+            } else {                              // background: 4-connectivity
+                if (N && !implied) unite(L, p, p - w);
+                if (W && (p & 31) == 0) unite(L, p, p - 1);
+            }
+        }
+    }
+}
+
 __global__ void ccl_flatten_kernel(int* __restrict__ L, int64_t total) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
         L[i] = find_root(L, (int)i);
@@ -530,10 +571,17 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) contour_warp_kernel(
 // partial sums are combined in a fixed order, so the result is deterministic)
 __global__ void __launch_bounds__(128) score_kernel(const float* __restrict__ prob, const float* __restrict__ box1,
                                                      uint8_t* __restrict__ valid, double* __restrict__ score, int h, int w,
-                                                     int maxc, double box_thresh) {
-    int t = blockIdx.x;
-    if (valid[t] != 1) return;
-    int p = t / maxc;
+                                                     int maxc, double box_thresh, const int* __restrict__ counts, int n) {
+    // persistent grid over the dense candidate list (page p contributes counts[p] of its maxc slots)
+    __shared__ double ssum[128];
+    __shared__ long long scnt[128];
+    int total = 0;
+    for (int q = 0; q < n; ++q) total += counts[q];
+    for (int j = blockIdx.x; j < total; j += gridDim.x) {
+    int p = 0, r = j;
+    while (r >= counts[p]) { r -= counts[p]; ++p; }
+    const int t = p * maxc + r;
+    if (valid[t] != 1) continue;
     const float* pred = prob + (size_t)p * h * w;
     PtF box[4];
     for (int i = 0; i < 4; ++i) {
@@ -566,8 +614,6 @@ __global__ void __launch_bounds__(128) score_kernel(const float* __restrict__ pr
                 ++cnt;
             }
     }
-    __shared__ double ssum[128];
-    __shared__ long long scnt[128];
     ssum[threadIdx.x] = sum;
     scnt[threadIdx.x] = cnt;
     __syncthreads();
@@ -582,6 +628,8 @@ __global__ void __launch_bounds__(128) score_kernel(const float* __restrict__ pr
         double sc = scnt[0] ? ssum[0] / (double)scnt[0] : 0.0;
         score[t] = sc;
         if (box_thresh > sc) valid[t] = 0;            // db_postprocess.py:134
+    }
+    __syncthreads();                                  // ssum / scnt are reused by the next candidate
     }
 }
 
@@ -657,7 +705,8 @@ void Stages::db_post_enqueue(int lane, const float* d_prob, int n, int h, int w,
         launches += 1;
     }
     ccl_init_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(bm, L, total, w);
-    ccl_merge_kernel<<<grid_for(total), 256, 0, st>>>(bm, L, n, h, w);
+    if ((w & 3) == 0) ccl_merge4_kernel<<<grid_for(total >> 2), 256, 0, st>>>(bm, L, n, h, w);
+    else ccl_merge_kernel<<<grid_for(total), 256, 0, st>>>(bm, L, n, h, w);
     ccl_flatten_kernel<<<grid_for(total), 256, 0, st>>>(L, total);
     B200_CUDA_CHECK(cudaMemsetAsync(border, 0, (size_t)total, st));
     border_kernel<<<grid_for((int64_t)n * 2 * (h + w)), 256, 0, st>>>(bm, L, border, n, h, w);
@@ -703,7 +752,7 @@ void Stages::db_post_enqueue(int lane, const float* d_prob, int n, int h, int w,
     B200_CUDA_CHECK(cudaMemcpyAsync(h_counts + n, d_flagged, sizeof(int), cudaMemcpyDeviceToHost, st));
     launches += 11;
     auto run_tail = [&]() {
-        score_kernel<<<nt, 128, 0, st>>>(d_prob, box1, valid, score, h, w, maxc, p.box_thresh);
+        score_kernel<<<(unsigned)std::min(nt, 148 * 8), 128, 0, st>>>(d_prob, box1, valid, score, h, w, maxc, p.box_thresh, counts, n);
         unclip_kernel<<<(unsigned)ceil_div(nt, 32), 32, 0, st>>>(box1, valid, res_box, d_src, n, h, w, maxc, p.unclip_ratio,
                                                                   (float)(p.min_size + 2));
         launches += 2;
@@ -751,7 +800,7 @@ void Stages::db_post_collect(DbPending* pend, std::vector<int32_t>* boxes, std::
     uint8_t* hv = (uint8_t*)(h_res + (size_t)nt * (8 * sizeof(int) + sizeof(double)));
     size_t tmp_bytes = 0;
     auto run_tail = [&]() {
-        score_kernel<<<nt, 128, 0, st>>>(d_prob, box1, valid, score, h, w, maxc, p.box_thresh);
+        score_kernel<<<(unsigned)std::min(nt, 148 * 8), 128, 0, st>>>(d_prob, box1, valid, score, h, w, maxc, p.box_thresh, counts, n);
         unclip_kernel<<<(unsigned)ceil_div(nt, 32), 32, 0, st>>>(box1, valid, res_box, d_src, n, h, w, maxc, p.unclip_ratio,
                                                                   (float)(p.min_size + 2));
         launches += 2;
