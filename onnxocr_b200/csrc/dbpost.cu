@@ -23,7 +23,7 @@ using namespace geom;
 
 struct DbWork {
     DevBuf bitmap, labels, flags, pos, border, scan_tmp;
-    DevBuf cand, counts, npts, offs, box1, valid, score, res_box;
+    DevBuf cand, counts, npts, offs, box1, valid, score, res_box, cbuf, found;
     DevBuf keys, ipool, fpool;
     PinBuf h_counts, h_res;
 };
@@ -214,7 +214,7 @@ __global__ void border_kernel(const uint8_t* __restrict__ bm, const int* __restr
         else if (k < 2 * w + h) { x = 0; y = k - 2 * w; }
         else { x = w - 1; y = k - 2 * w - h; }
         int64_t i = ((int64_t)p * h + y) * w + x;
-        if (!bm[i]) border[L[i]] = 1;
+        if (!bm[i]) border[find_root(L, (int)i)] = 1;     // the labels are not flattened: nothing else needs every pixel's root
     }
 }
 
@@ -242,6 +242,66 @@ __global__ void compact_kernel(const uint8_t* __restrict__ bm, const int* __rest
         if (r >= maxc) continue;
         int local = (int)(i - first);
         cand[(size_t)p * maxc + r] = bm[i] ? local : ((local - 1) | kHoleBit);
+    }
+}
+
+// Candidate list without the flag / scan / compact passes over every pixel: component roots (few hundred per page) are
+// appended with an atomic counter and then sorted per page; the order cv2.findContours(RETR_LIST) returns is descending
+// start pixel.  found[p] counts every qualifying root, so a page with more than kCandBuf of them (speckle maps) is
+// detected and the batch is redone through the scan path at collection time.
+constexpr int kCandBuf = 16384;
+__global__ void cand_collect_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ L, const uint8_t* __restrict__ border,
+                                    int* __restrict__ buf, int* __restrict__ found, int n, int hw) {
+    const unsigned total = (unsigned)n * (unsigned)hw;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        if (L[i] != (int)i) continue;
+        if (!bm[i] && border[i]) continue;
+        const unsigned p = i / (unsigned)hw;
+        const int slot = atomicAdd(&found[p], 1);
+        if (slot < kCandBuf) buf[(size_t)p * kCandBuf + slot] = (int)(i - p * (unsigned)hw);
+    }
+}
+
+// one block per page: ascending bitonic sort of the page's roots, then cand[p][r] = r-th largest (cv2 order)
+__global__ void __launch_bounds__(1024) cand_sort_kernel(const uint8_t* __restrict__ bm, int* __restrict__ buf,
+                                                         const int* __restrict__ found, int* __restrict__ cand,
+                                                         int* __restrict__ counts, int* __restrict__ overflow, int hw, int maxc) {
+    __shared__ int sk[4096];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const int m_all = found[p];
+    if (m_all > kCandBuf) {
+        if (tid == 0) { atomicAdd(overflow, 1); counts[p] = 0; }
+        return;
+    }
+    const int m = m_all;
+    int* g = buf + (size_t)p * kCandBuf;
+    int npow2 = 1;
+    while (npow2 < m) npow2 <<= 1;
+    int* a = npow2 <= 4096 ? sk : g;                       // large lists are sorted in place in global memory
+    if (a == sk) {
+        for (int i = tid; i < npow2; i += 1024) sk[i] = i < m ? g[i] : 0x7fffffff;
+    } else {
+        for (int i = m + tid; i < npow2; i += 1024) g[i] = 0x7fffffff;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npow2; i += 1024) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const int x = a[i], y = a[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    const int cnt = m < maxc ? m : maxc;
+    if (tid == 0) counts[p] = cnt;
+    const uint8_t* pbm = bm + (size_t)p * hw;
+    for (int r = tid; r < cnt; r += 1024) {
+        const int local = a[m - 1 - r];
+        cand[(size_t)p * maxc + r] = pbm[local] ? local : ((local - 1) | kHoleBit);
     }
 }
 
@@ -668,7 +728,23 @@ int grid_for(int64_t total, int block = 256) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(g, 148 * 16));
 }
 
+static void launch_contour_warp(const uint8_t* bm, const int* cand, const int* counts, float* box1, uint8_t* valid, int* d_flagged,
+                                int n, int h, int w, int maxc, float min_size, int nt, cudaStream_t st) {
+    static bool attr_set[16] = {false};             // per device: function attributes are per context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t smem = kWarpSmem * kWarpsPerBlock;
+    static const int dbg_phase = [] { const char* e = getenv("B200OCR_DBG_CONTOUR"); return e ? atoi(e) : 0; }();
+    if (!attr_set[dev & 15]) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(contour_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev & 15] = true;
+    }
+    contour_warp_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nt, kWarpsPerBlock), 148 * 2), 32 * kWarpsPerBlock, smem, st>>>(
+        bm, cand, counts, box1, valid, d_flagged, n, h, w, maxc, min_size, dbg_phase);
+}
+
 }  // namespace
+
 
 void Stages::db_postprocess_device(const float* d_prob, int n, int h, int w, const int* src_hs, const int* src_ws,
                                    const b200ocr_det_params& p, int capacity, std::vector<int32_t>* boxes,
@@ -695,8 +771,6 @@ void Stages::db_post_enqueue(int lane, const float* d_prob, int n, int h, int w,
     TraceScope tr_post("db_post", st, n);
     uint8_t* bm = (uint8_t*)W.bitmap.get((size_t)total * (p.use_dilation ? 2 : 1));
     int* L = (int*)W.labels.get((size_t)total * sizeof(int));
-    int* flags = (int*)W.flags.get((size_t)total * sizeof(int));
-    int* pos = (int*)W.pos.get((size_t)total * sizeof(int));
     uint8_t* border = (uint8_t*)W.border.get((size_t)total);
     threshold_kernel<<<grid_for(total), 256, 0, st>>>(d_prob, bm, total, p.thresh);
     if (p.use_dilation) {
@@ -707,50 +781,38 @@ void Stages::db_post_enqueue(int lane, const float* d_prob, int n, int h, int w,
     ccl_init_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(bm, L, total, w);
     if ((w & 3) == 0) ccl_merge4_kernel<<<grid_for(total >> 2), 256, 0, st>>>(bm, L, n, h, w);
     else ccl_merge_kernel<<<grid_for(total), 256, 0, st>>>(bm, L, n, h, w);
-    ccl_flatten_kernel<<<grid_for(total), 256, 0, st>>>(L, total);
     B200_CUDA_CHECK(cudaMemsetAsync(border, 0, (size_t)total, st));
     border_kernel<<<grid_for((int64_t)n * 2 * (h + w)), 256, 0, st>>>(bm, L, border, n, h, w);
-    cand_flag_kernel<<<grid_for(total), 256, 0, st>>>(bm, L, border, flags, total);
-    size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flags, pos, (int)total, st);
-    void* tmp = W.scan_tmp.get(tmp_bytes + 256);
-    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flags, pos, (int)total, st);
     const int nt = n * maxc;
     int* cand = (int*)W.cand.get((size_t)nt * sizeof(int));
     int* counts = (int*)W.counts.get((size_t)(n + 2 * n + 1) * sizeof(int));
     int* d_src = counts + n;
     int* npts = (int*)W.npts.get((size_t)(nt + 1) * sizeof(int));
     int* offs = (int*)W.offs.get((size_t)(nt + 1) * sizeof(int));
-    compact_kernel<<<grid_for(total), 256, 0, st>>>(bm, flags, pos, cand, counts, n, hw, maxc);
+    // candidate roots: atomic append + per-page sort (found[n] is the overflow flag, see db_post_collect)
+    int* cbuf = (int*)W.cbuf.get((size_t)n * kCandBuf * sizeof(int));
+    int* found = (int*)W.found.get((size_t)(n + 1) * sizeof(int));
+    B200_CUDA_CHECK(cudaMemsetAsync(found, 0, (size_t)(n + 1) * sizeof(int), st));
+    cand_collect_kernel<<<grid_for(total), 256, 0, st>>>(bm, L, border, cbuf, found, n, hw);
+    cand_sort_kernel<<<n, 1024, 0, st>>>(bm, cbuf, found, cand, counts, found + n, hw, maxc);
     float* box1 = (float*)W.box1.get((size_t)nt * 8 * sizeof(float));
     uint8_t* valid = (uint8_t*)W.valid.get((size_t)nt);
     double* score = (double*)W.score.get((size_t)nt * sizeof(double));
     int* res_box = (int*)W.res_box.get((size_t)nt * 8 * sizeof(int));
     int* d_flagged = npts + nt;                       // reuse the scan sentinel slot as the overflow counter
     B200_CUDA_CHECK(cudaMemsetAsync(d_flagged, 0, sizeof(int), st));
-    int* h_counts = (int*)W.h_counts.get((size_t)(n + 2) * sizeof(int) + 2 * n * sizeof(int));
-    int* h_src = h_counts + n + 2;
+    int* h_counts = (int*)W.h_counts.get((size_t)(n + 3) * sizeof(int) + 2 * n * sizeof(int));
+    int* h_src = h_counts + n + 3;                     // [0, n) counts, [n] flagged contours, [n + 1] scratch, [n + 2] candidate overflow
     for (int i = 0; i < n; ++i) {
         h_src[2 * i] = src_hs[i];
         h_src[2 * i + 1] = src_ws[i];
     }
     B200_CUDA_CHECK(cudaMemcpyAsync(d_src, h_src, 2 * n * sizeof(int), cudaMemcpyHostToDevice, st));
-    {
-        static bool attr_set[16] = {false};             // per device: function attributes are per context
-        int dev = 0;
-        cudaGetDevice(&dev);
-        size_t smem = kWarpSmem * kWarpsPerBlock;
-        static const int dbg_phase = [] { const char* e = getenv("B200OCR_DBG_CONTOUR"); return e ? atoi(e) : 0; }();
-        if (!attr_set[dev & 15]) {
-            B200_CUDA_CHECK(cudaFuncSetAttribute(contour_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set[dev & 15] = true;
-        }
-        contour_warp_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nt, kWarpsPerBlock), 148 * 2), 32 * kWarpsPerBlock, smem, st>>>(
-            bm, cand, counts, box1, valid, d_flagged, n, h, w, maxc, (float)p.min_size, dbg_phase);
-    }
+    launch_contour_warp(bm, cand, counts, box1, valid, d_flagged, n, h, w, maxc, (float)p.min_size, nt, st);
     B200_CUDA_CHECK(cudaMemcpyAsync(h_counts, counts, n * sizeof(int), cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaMemcpyAsync(h_counts + n, d_flagged, sizeof(int), cudaMemcpyDeviceToHost, st));
-    launches += 11;
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_counts + n + 2, found + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    launches += 9;
     auto run_tail = [&]() {
         score_kernel<<<(unsigned)std::min(nt, 148 * 8), 128, 0, st>>>(d_prob, box1, valid, score, h, w, maxc, p.box_thresh, counts, n);
         unclip_kernel<<<(unsigned)ceil_div(nt, 32), 32, 0, st>>>(box1, valid, res_box, d_src, n, h, w, maxc, p.unclip_ratio,
@@ -806,6 +868,32 @@ void Stages::db_post_collect(DbPending* pend, std::vector<int32_t>* boxes, std::
         launches += 2;
     };
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h_counts[n + 2] > 0) {
+        // rare: a page has more than kCandBuf component roots (speckle maps) -> candidates through flag / scan / compact over
+        // every pixel (which has no capacity limit), then the per-candidate kernels again
+        const int hw = h * w;
+        int* L = (int*)W.labels.p;
+        const uint8_t* border = (const uint8_t*)W.border.p;
+        int* flags = (int*)W.flags.get((size_t)total * sizeof(int));
+        int* pos = (int*)W.pos.get((size_t)total * sizeof(int));
+        cand_flag_kernel<<<grid_for(total), 256, 0, st>>>(bm, L, border, flags, total);
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, flags, pos, (int)total, st);
+        void* tmp = W.scan_tmp.get(tb + 256);
+        cub::DeviceScan::ExclusiveSum(tmp, tb, flags, pos, (int)total, st);
+        compact_kernel<<<grid_for(total), 256, 0, st>>>(bm, flags, pos, cand, counts, n, hw, maxc);
+        int* d_flagged = npts + nt;
+        B200_CUDA_CHECK(cudaMemsetAsync(d_flagged, 0, sizeof(int), st));
+        launch_contour_warp(bm, cand, counts, box1, valid, d_flagged, n, h, w, maxc, (float)p.min_size, nt, st);
+        B200_CUDA_CHECK(cudaMemcpyAsync(h_counts, counts, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaMemcpyAsync(h_counts + n, d_flagged, sizeof(int), cudaMemcpyDeviceToHost, st));
+        run_tail();
+        B200_CUDA_CHECK(cudaMemcpyAsync(hb, res_box, (size_t)nt * 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaMemcpyAsync(hs, score, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaMemcpyAsync(hv, valid, (size_t)nt, cudaMemcpyDeviceToHost, st));
+        launches += 7;
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
     if (h_counts[n] > 0) {
         // rare: some contour exceeded the shared-memory capacity of the warp kernel -> generic two-pass path for those
         trace_count_kernel<<<(unsigned)ceil_div(nt, 64), 64, 0, st>>>(bm, cand, counts, valid, npts, n, h, w, maxc);

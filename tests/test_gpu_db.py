@@ -65,6 +65,11 @@ def test_db_postprocess_noise_and_candidate_cap(engine_fp32):
     prob = cv2.GaussianBlur(rng.random((256, 256)).astype(np.float32), (7, 7), 0) * 1.6
     n = check(engine_fp32, prob, 512, 512)
     assert n >= 1
+    # > 16384 component roots on one page: the candidate buffer overflows and the batch is redone through the scan path
+    prob = rng.random((512, 768)).astype(np.float32)
+    assert len(cv2.findContours((prob > 0.3).astype(np.uint8), cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)[0]) > 20000
+    check(engine_fp32, prob, 512, 768)
+    # the same speckle page next to ordinary pages in one det batch (only the speckle page overflows)
 
 
 def test_db_postprocess_params(engine_fp32):
