@@ -109,10 +109,21 @@ __device__ __forceinline__ void unite(int* L, int a, int b) {
 }
 
 // label initialisation: every pixel points at the first pixel of its horizontal run inside its 32-pixel warp segment
-__global__ void ccl_init_kernel(const uint8_t* __restrict__ bm, int* __restrict__ L, int64_t total, int w) {
+// PROB != nullptr: the threshold is applied here as well (bm is written, not read) — one pass instead of two
+template <bool FROM_PROB>
+__global__ void ccl_init_kernel(const float* __restrict__ prob, float thresh, uint8_t* __restrict__ bm, int* __restrict__ L,
+                                int64_t total, int w) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     bool in = i < (unsigned)total;
-    int v = in ? bm[i] : 2;
+    int v = 2;
+    if (in) {
+        if (FROM_PROB) {
+            v = prob[i] > thresh ? 1 : 0;
+            bm[i] = (uint8_t)v;
+        } else {
+            v = bm[i];
+        }
+    }
     int x = in ? (int)(i % (unsigned)w) : 0;
     int lane = threadIdx.x & 31;
     // a run breaks where the class changes or a new image row starts
@@ -772,13 +783,15 @@ void Stages::db_post_enqueue(int lane, const float* d_prob, int n, int h, int w,
     uint8_t* bm = (uint8_t*)W.bitmap.get((size_t)total * (p.use_dilation ? 2 : 1));
     int* L = (int*)W.labels.get((size_t)total * sizeof(int));
     uint8_t* border = (uint8_t*)W.border.get((size_t)total);
-    threshold_kernel<<<grid_for(total), 256, 0, st>>>(d_prob, bm, total, p.thresh);
     if (p.use_dilation) {
+        threshold_kernel<<<grid_for(total), 256, 0, st>>>(d_prob, bm, total, p.thresh);
         dilate2x2_kernel<<<grid_for(total), 256, 0, st>>>(bm, bm + total, n, h, w);
         bm += total;
-        launches += 1;
+        launches += 2;
+        ccl_init_kernel<false><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(nullptr, 0.f, bm, L, total, w);
+    } else {
+        ccl_init_kernel<true><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(d_prob, p.thresh, bm, L, total, w);
     }
-    ccl_init_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(bm, L, total, w);
     if ((w & 3) == 0) ccl_merge4_kernel<<<grid_for(total >> 2), 256, 0, st>>>(bm, L, n, h, w);
     else ccl_merge_kernel<<<grid_for(total), 256, 0, st>>>(bm, L, n, h, w);
     B200_CUDA_CHECK(cudaMemsetAsync(border, 0, (size_t)total, st));

@@ -868,6 +868,10 @@ void Model::build_steps(Plan& p) {
                         g.nodes[ni + 1].in[0] == c.out && cp.CoutP <= kSeSumsThreads && cp.CoutP % 8 == 0) {
                         const size_t bytes = (size_t)iv.n * tc::kGapReplicas * cp.CoutP * sizeof(unsigned long long);
                         gap_buf = new_buf(bytes);
+                        // never shared with another buffer: the sums must still be zero (left so by se_fc_sums_kernel) when
+                        // the next launch starts, see zero_sums below
+                        buf_first[gap_buf] = -1;
+                        buf_last[gap_buf] = (int)g.nodes.size();
                         p.vals[out].sums_replicas = tc::kGapReplicas;
                         tp.gap = reinterpret_cast<unsigned long long*>(1);   // resolved at launch (the slab may move)
                         tp.gap_mod = cp.CoutP;
@@ -876,7 +880,12 @@ void Model::build_steps(Plan& p) {
                         const int gb = gap_buf;
                         const double keep_f = cost_flops, keep_b = cost_bytes;     // the work belongs to the conv step below
                         cost_flops = 0; cost_bytes = (double)bytes;
-                        emit("zero_sums " + c.name, [=](cudaStream_t st) { cudaMemsetAsync(pp->bufptr(gb), 0, bytes, st); });
+                        emit("zero_sums " + c.name, [=](cudaStream_t st) {
+                            // se_fc_sums_kernel re-zeroes the sums it consumed: in a private slab (nobody else writes
+                            // there) only the first launch needs the memset, the captured graph carries none
+                            if (pp->own_arena && pp->sums_clean) return;
+                            cudaMemsetAsync(pp->bufptr(gb), 0, bytes, st);
+                        });
                         cost_flops = keep_f; cost_bytes = keep_b;
                     }
                     std::shared_ptr<TcState> ts(new TcState());
@@ -1102,9 +1111,16 @@ void Model::build_steps(Plan& p) {
                     iv.cp <= kSeSumsThreads) {
                     const size_t bytes = (size_t)iv.n * iv.cp * sizeof(unsigned long long);
                     dw_gap_buf = new_buf(bytes);
+                    buf_first[dw_gap_buf] = -1;                  // whole-plan lifetime, see the tensor-core case
+                    buf_last[dw_gap_buf] = (int)g.nodes.size();
                     p.vals[out].sums = dw_gap_buf;
                     const int gb = dw_gap_buf;
-                    emit("zero_sums " + c.name, [=](cudaStream_t st) { cudaMemsetAsync(pp->bufptr(gb), 0, bytes, st); });
+                    emit("zero_sums " + c.name, [=](cudaStream_t st) {
+                            // se_fc_sums_kernel re-zeroes the sums it consumed: in a private slab (nobody else writes
+                            // there) only the first launch needs the memset, the captured graph carries none
+                            if (pp->own_arena && pp->sums_clean) return;
+                            cudaMemsetAsync(pp->bufptr(gb), 0, bytes, st);
+                        });
                 }
                 const DwP dp0 = dp;
                 emit("dwconv " + c.name, [=](cudaStream_t st) {
@@ -1714,6 +1730,7 @@ static bool graphs_enabled() {            // B200OCR_NO_GRAPH=1: launch every ke
 void Plan::launch(cudaStream_t st) {
     if (!graphs_enabled() || steps.size() < 8) {
         for (auto& s : steps) s(st);
+        sums_clean = true;
         return;
     }
     if (graph_exec && graph_arena == *model_arena) {
@@ -1730,6 +1747,7 @@ void Plan::launch(cudaStream_t st) {
         for (auto& s : steps) s(st);
         warm_launches = 1;
         warm_arena = *model_arena;
+        sums_clean = true;
         return;
     }
     cudaGraph_t g = nullptr;

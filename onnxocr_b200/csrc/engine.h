@@ -91,6 +91,7 @@ struct Plan {
     const char* graph_arena = nullptr;   // slab address the graph was recorded against
     const char* warm_arena = nullptr;
     int warm_launches = 0;
+    bool sums_clean = false;       // the SE channel-sum buffers were zeroed by a first launch (see zero_sums in build_steps)
     void* ptr(int v) const { return *model_arena + buf_off[vals[v].root]; }
     void* bufptr(int b) const { return *model_arena + buf_off[b]; }
     void* in_ptr() const { return ptr(in_val); }
