@@ -770,6 +770,18 @@ void Stages::det_finish(DetTicket* t) {
     for (int k = 0; k < kLanesPerSlot; ++k) det_collect_lane(t, (t->turn + k) % kLanesPerSlot);   // oldest first
 }
 
+// A batch failed while it was being enqueued (bad argument, CUDA error): wait for whatever it already put on its lanes and
+// drop the pending DBPostProcess state, so that the next user of the slot does not collect a stale sub-batch.
+void Stages::det_abort(DetTicket* t) {
+    for (int k = 0; k < kLanesPerSlot; ++k) {
+        if (!t->pend[k].active) continue;
+        t->pend[k].active = false;
+        cudaStreamSynchronize(det_st_[t->pend[k].lane]);
+    }
+    cudaGetLastError();
+    t->boxes.clear();
+}
+
 void Stages::drain_tickets() {
     for (auto& t : tickets_)
         if (t.busy) det_finish(&t);
@@ -910,7 +922,12 @@ void Stages::det_on_pool(Model* det, const PagePool& pool, const uint8_t* const*
     drain_tickets();                                   // streaming batches may own the lanes of slot 0
     DetTicket* t = &sync_ticket_;
     t->slot = 0;
-    det_enqueue(t, det, pool, pages, hs, ws, n, p, probmap_out, probmap_capacity, probmap_dims_out, st_);
+    try {
+        det_enqueue(t, det, pool, pages, hs, ws, n, p, probmap_out, probmap_capacity, probmap_dims_out, st_);
+    } catch (...) {
+        det_abort(t);
+        throw;
+    }
     det_finish(t);
     boxes_pp->swap(t->boxes);
     // later work on the engine stream (crops, cls, rec) reads the pages the lanes uploaded
@@ -951,7 +968,12 @@ int Stages::det_submit(Model* det, const uint8_t* const* pages, const int* hs, c
     t->id = ++ticket_seq_ * kDetSlots + t->slot;
     PagePool pool;
     plan_pool(hs, ws, strides, n, &pool, &t->store);
-    det_enqueue(t, det, pool, pages, hs, ws, n, p, nullptr, 0, nullptr, nullptr);
+    try {
+        det_enqueue(t, det, pool, pages, hs, ws, n, p, nullptr, 0, nullptr, nullptr);
+    } catch (...) {
+        det_abort(t);                              // the slot stays free; nothing of this batch is left on its lanes
+        throw;
+    }
     t->busy = true;
     return t->id;
 }
@@ -1312,8 +1334,15 @@ void Stages::resident_stream(Model* det, const b200ocr_det_params& p, int iters,
         pool.base = (uint8_t*)d_res_.p;
         pool.off.assign(res_off_.begin() + first, res_off_.begin() + first + pps);
         pool.stride.assign(res_stride_.begin() + first, res_stride_.begin() + first + pps);
-        det_enqueue(t, det, pool, nullptr, res_h_.data() + first, res_w_.data() + first, pps, p, nullptr, 0, nullptr,
-                    it < depth ? st_ : nullptr);
+        try {
+            det_enqueue(t, det, pool, nullptr, res_h_.data() + first, res_w_.data() + first, pps, p, nullptr, 0, nullptr,
+                        it < depth ? st_ : nullptr);
+        } catch (...) {
+            det_abort(t);
+            for (auto& o : tickets_)
+                if (o.busy) { det_abort(&o); o.busy = false; }
+            throw;
+        }
         t->busy = true;
     }
     for (int k = 0; k < depth; ++k) {

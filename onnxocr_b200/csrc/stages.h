@@ -143,6 +143,7 @@ private:
                      cudaStream_t resident_src);
     void det_collect_lane(DetTicket* t, int k);
     void det_finish(DetTicket* t);
+    void det_abort(DetTicket* t);                            // enqueue failed: leave the slot's lanes clean
     void drain_tickets();                                    // finish every streaming batch (results stay in its ticket)
     void det_on_pool(Model* det, const PagePool& pool, const uint8_t* const* pages, const int* hs, const int* ws, int n,
                      const b200ocr_det_params& p, std::vector<std::vector<float>>* boxes_pp, float* probmap_out,

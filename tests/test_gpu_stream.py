@@ -88,3 +88,34 @@ def test_resident_stream_counts_the_same_boxes(engine_bf16):
     _, n_sync, _ = eng.det_resident_run(iters=1)
     ms, n_stream = eng.det_resident_stream(iters=6, pages_per_step=4)     # 6 steps of 4 pages = the 8 pages three times
     assert n_sync > 20 and n_stream == 3 * n_sync and ms > 0
+
+
+def test_failed_submit_leaves_the_slot_clean(engine_bf16):
+    """A batch that fails while it is being enqueued (here: a null page in its second shape group, after the first group is
+    already on a lane) must not leave a pending sub-batch behind: the next batches on the same slot return correct boxes."""
+    import ctypes as C
+    from onnxocr_b200 import _lib, synth_pages
+    eng = engine_bf16
+    a = [synth_pages.render_page(320, 480, 6, seed=2000 + i)[0] for i in range(3)]
+    b = [synth_pages.render_page(480, 640, 6, seed=2100 + i)[0] for i in range(2)]
+    pages = a + b
+    ref = eng.det_pages(pages)
+    n = len(pages)
+    ptrs = (C.c_void_p * n)(*[p.ctypes.data for p in pages])
+    ptrs[n - 1] = None                                   # a page of the second (larger) shape group
+    hs, ws = _lib._int_arr([p.shape[0] for p in pages]), _lib._int_arr([p.shape[1] for p in pages])
+    st = _lib._int_arr([p.strides[0] for p in pages])
+    params = _lib.det_params()
+    t = C.c_int()
+    for _ in range(3):                                   # repeatedly: every slot sees a failed batch
+        rc = eng._L.b200ocr_det_submit(eng._h, ptrs, hs, ws, st, n, C.byref(params), C.byref(t))
+        assert rc != 0 and b"null page" in eng._L.b200ocr_last_error(eng._h)
+    boxes = np.zeros((n, 1000, 4, 2), np.float32)
+    counts = (C.c_int * n)()
+    rc = eng._L.b200ocr_det_pages(eng._h, ptrs, hs, ws, st, n, C.byref(params), _lib._ptr(boxes), 1000, counts, None, 0,
+                                  (C.c_int * (2 * n))())
+    assert rc != 0                                       # the synchronous entry point fails the same way ...
+    for _ in range(2):                                   # ... and both paths work afterwards
+        for got in eng.det_pages_stream([pages, pages, pages]):
+            _same(got, ref)
+        _same(eng.det_pages(pages), ref)
