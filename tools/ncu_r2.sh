@@ -23,7 +23,7 @@ cap dw5x5 dwconv_strip_kernel 6
 cap concat concat_multi_bf16_kernel 0
 cap fpn_add82 fpn_add_bf16_kernel 2
 cap se_fc_sums se_fc_sums_kernel 9
-cap ccl_merge ccl_merge_kernel 0
+cap ccl_merge ccl_merge4_kernel 0
 cap contour_warp contour_warp_kernel 0
 cap score score_kernel 0
 ls -la gpurun_out/ | tail -30
