@@ -982,10 +982,14 @@ void Stages::det_collect(int ticket, float* boxes_out, int max_boxes, int* n_box
     DetTicket* t = ticket >= 0 ? &tickets_[ticket % kDetSlots] : nullptr;
     if (!t || !t->busy || t->id != ticket) throw std::runtime_error("bad argument: unknown or already collected det ticket");
     det_finish(t);
-    t->busy = false;
+    // a too small box buffer leaves the ticket collectable (its results are complete): the caller retries with more room
     for (int i = 0; i < t->n; ++i) {
         int m = (int)(t->boxes[i].size() / 8);
         if (m > max_boxes) throw std::runtime_error("box capacity too small: page " + std::to_string(i) + " has " + std::to_string(m));
+    }
+    t->busy = false;
+    for (int i = 0; i < t->n; ++i) {
+        int m = (int)(t->boxes[i].size() / 8);
         n_boxes_out[i] = m;
         if (m) memcpy(boxes_out + (size_t)i * max_boxes * 8, t->boxes[i].data(), t->boxes[i].size() * sizeof(float));
     }

@@ -75,6 +75,8 @@ def test_stream_misuse_is_an_error(engine_bf16):
         eng.det_collect(t0)                  # already collected
     with pytest.raises(RuntimeError, match="ticket"):
         eng.det_collect((12345, t1[1]))
+    with pytest.raises(RuntimeError, match="capacity"):
+        eng.det_collect(t1, max_boxes=1)     # too small a box buffer: the ticket stays collectable
     b = eng.det_collect(t1)
     _same(a, eng.det_pages(batches[1]))
     _same(b, eng.det_pages(batches[4]))

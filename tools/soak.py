@@ -18,7 +18,7 @@ while time.time() - t0 < secs:
     k = int(rng.integers(1, 20))
     idx = rng.integers(0, len(pool), k)
     batch = [pool[i] for i in idx]
-    mode = int(rng.integers(0, 4))
+    mode = int(rng.integers(0, 5))
     if mode == 0:
         res = ocr.ocr_batch(batch)
         lines += sum(len(r) for r in res)
@@ -28,9 +28,24 @@ while time.time() - t0 < secs:
     elif mode == 2:
         res = ocr.ocr(batch[0])
         lines += len(res[0])
+    elif mode == 4:
+        # streaming det with random batch sizes / shapes, checked against the blocking call on a sample
+        batches = [[pool[i] for i in rng.integers(0, len(pool), int(rng.integers(1, 18)))] for _ in range(int(rng.integers(1, 7)))]
+        outs = list(ocr.engine.det_pages_stream(batches, ocr.text_detector.params))
+        lines += sum(len(b) for o in outs for b in o)
+        j = int(rng.integers(0, len(batches)))
+        ref = ocr.engine.det_pages(batches[j], ocr.text_detector.params)
+        assert all(np.array_equal(a, b) for a, b in zip(outs[j], ref)), "streaming det differs from the blocking call"
+        pages += sum(len(b) for b in batches)
     else:
         crops = synth_pages.rec_crops_c3(int(rng.integers(1, 40)), seed=int(rng.integers(0, 1000)), w=int(rng.integers(60, 900)))
         lines += len(ocr.text_recognizer(crops))
     calls += 1
     pages += k
+import subprocess  # noqa: E402
+try:
+    mem = subprocess.run(["nvidia-smi", "--query-gpu=memory.used", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
+except Exception:
+    mem = "?"
+print("device memory in use at the end: " + mem)
 print("soak ok: %d calls, %d pages, %d lines in %.1f s, %d launches" % (calls, pages, lines, time.time() - t0, ocr.engine.launch_count()))
