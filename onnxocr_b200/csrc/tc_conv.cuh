@@ -643,13 +643,23 @@ __device__ __noinline__ void gap_accumulate_tile(const uint8_t* stage, int row_b
             float s0 = 0.f, s1 = 0.f;
             const uint32_t a0 = sbase + (uint32_t)(rg * rows_pg) * (uint32_t)row_bytes + (uint32_t)(live ? cp : 0) * 4u;
             const uint32_t vm = vmask >> (rg * rows_pg);
+            if (vmask == 0xffffffffu) {                     // every row of the warp exists (all tiles but an image's last)
 #pragma unroll 8
-            for (int r = 0; r < rows_pg; ++r) {
-                uint32_t u;
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(a0 + (uint32_t)r * (uint32_t)row_bytes));
-                u &= 0u - ((vm >> r) & 1u);
-                s0 += __uint_as_float(u << 16);
-                s1 += __uint_as_float(u & 0xffff0000u);
+                for (int r = 0; r < rows_pg; ++r) {
+                    uint32_t u;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(a0 + (uint32_t)r * (uint32_t)row_bytes));
+                    s0 += __uint_as_float(u << 16);
+                    s1 += __uint_as_float(u & 0xffff0000u);
+                }
+            } else {
+#pragma unroll 8
+                for (int r = 0; r < rows_pg; ++r) {
+                    uint32_t u;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(a0 + (uint32_t)r * (uint32_t)row_bytes));
+                    u &= 0u - ((vm >> r) & 1u);
+                    s0 += __uint_as_float(u << 16);
+                    s1 += __uint_as_float(u & 0xffff0000u);
+                }
             }
             for (int d = lanes_pp; d < 32; d <<= 1) {
                 s0 += __shfl_xor_sync(0xffffffffu, s0, d);
