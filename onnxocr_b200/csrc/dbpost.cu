@@ -825,7 +825,7 @@ void Stages::db_post_enqueue(int lane, const float* d_prob, int n, int h, int w,
     B200_CUDA_CHECK(cudaMemcpyAsync(h_counts, counts, n * sizeof(int), cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaMemcpyAsync(h_counts + n, d_flagged, sizeof(int), cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaMemcpyAsync(h_counts + n + 2, found + n, sizeof(int), cudaMemcpyDeviceToHost, st));
-    launches += 9;
+    launches += 6;                                    // init, merge, border, collect, sort, contour (memsets and copies are not kernels)
     auto run_tail = [&]() {
         score_kernel<<<(unsigned)std::min(nt, 148 * 8), 128, 0, st>>>(d_prob, box1, valid, score, h, w, maxc, p.box_thresh, counts, n);
         unclip_kernel<<<(unsigned)ceil_div(nt, 32), 32, 0, st>>>(box1, valid, res_box, d_src, n, h, w, maxc, p.unclip_ratio,
