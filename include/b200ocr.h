@@ -76,6 +76,8 @@ typedef struct b200ocr_det_params {
     int use_dilation;         /* 0                                    utils.py:280 */
     double box_thresh;        /* det_db_box_thresh 0.6 (Python float, compared in float64)  utils.py:277 */
     double unclip_ratio;      /* det_db_unclip_ratio 1.5 (Python float)                      utils.py:278 */
+    int score_mode;           /* det_db_score_mode: 0 'fast' (box_score_fast), 1 'slow' (box_score_slow:
+                                 mean over cv2.fillPoly of the contour itself)  utils.py:283, db_postprocess.py:129-132,199-218 */
 } b200ocr_det_params;
 
 void b200ocr_det_params_default(b200ocr_det_params* p);

@@ -23,7 +23,7 @@ _lock = threading.Lock()
 class DetParams(C.Structure):
     _fields_ = [("limit_side_len", C.c_float), ("limit_type", C.c_int), ("thresh", C.c_float),
                 ("max_candidates", C.c_int), ("min_size", C.c_int), ("use_dilation", C.c_int),
-                ("box_thresh", C.c_double), ("unclip_ratio", C.c_double)]
+                ("box_thresh", C.c_double), ("unclip_ratio", C.c_double), ("score_mode", C.c_int)]
 
 
 class OcrParams(C.Structure):
@@ -32,12 +32,16 @@ class OcrParams(C.Structure):
 
 
 _LIMIT_TYPES = {"max": 0, "min": 1, "resize_long": 2}
+_SCORE_MODES = {"fast": 0, "slow": 1}      # det_db_score_mode, utils.py:283
 
 
 def det_params(limit_side_len=960, limit_type="max", thresh=0.3, box_thresh=0.6, unclip_ratio=1.5,
-               max_candidates=1000, min_size=3, use_dilation=False):
+               max_candidates=1000, min_size=3, use_dilation=False, score_mode="fast"):
+    if score_mode not in _SCORE_MODES:
+        raise ValueError("score_mode can only be one of %s" % list(_SCORE_MODES))
     return DetParams(float(limit_side_len), _LIMIT_TYPES[limit_type], float(thresh), int(max_candidates),
-                     int(min_size), int(bool(use_dilation)), float(box_thresh), float(unclip_ratio))
+                     int(min_size), int(bool(use_dilation)), float(box_thresh), float(unclip_ratio),
+                     _SCORE_MODES[score_mode])
 
 
 def ocr_params(det=None, use_angle_cls=False, cls_thresh=0.9, label_list=("0", "180"), rec_batch_num=6,

@@ -171,6 +171,7 @@ void b200ocr_det_params_default(b200ocr_det_params* p) {
     p->max_candidates = 1000;
     p->min_size = 3;
     p->use_dilation = 0;
+    p->score_mode = 0;
 }
 
 int b200ocr_det_preprocess(b200ocr_engine* e, const uint8_t* bgr, int h, int w, int row_stride,

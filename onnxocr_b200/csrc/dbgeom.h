@@ -699,6 +699,77 @@ B200_HDN double box_score_fast(const float* pred, int h, int w, const PtF box[4]
 }
 
 // ---------------------------------------------------------------------------------------------
+// box_score_slow (db_postprocess.py:199-218, det_db_score_mode='slow'): cv2.fillPoly of the CONTOUR itself + cv2.mean.
+// Every edge of a CHAIN_APPROX_SIMPLE contour is horizontal, vertical or diagonal (a run of one chain direction), so on
+// an integer row an edge is either a pixel range (horizontal) or exactly one pixel, and cv2's scan conversion reduces to:
+// mask = pixels on the closed chain  ∪  pixels with an odd number of edge crossings strictly to their right, an edge
+// counting on the rows [min y, max y) (even-odd rule; tests/test_geom_host.py: 0 mismatching pixels against cv2.fillPoly
+// over outer and hole contours of blob, blurred-noise and speckle bitmaps).
+// ---------------------------------------------------------------------------------------------
+// What edge (x0, y0) -> (x1, y1) contributes to row y: bit 0 = chain pixels [*xa, *xb], bit 1 = a crossing at *xa.
+B200_HD int edge_on_row(int x0, int y0, int x1, int y1, int y, int* xa, int* xb) {
+    if (y0 == y1) {
+        if (y != y0) return 0;
+        *xa = x0 < x1 ? x0 : x1;
+        *xb = x0 < x1 ? x1 : x0;
+        return 1;
+    }
+    const int lo = y0 < y1 ? y0 : y1, hi = y0 < y1 ? y1 : y0;
+    if (y < lo || y > hi) return 0;
+    const int x = x0 + (y - y0) * (x1 - x0) / (y1 - y0);      // exact: |x1 - x0| is 0 or |y1 - y0|
+    *xa = *xb = x;
+    return y < hi ? 3 : 1;
+}
+
+// p[b] = t[b] ^ t[b+1] ^ ... ^ t[31]
+B200_HD uint32_t suffix_xor(uint32_t t) {
+    t ^= t >> 1; t ^= t >> 2; t ^= t >> 4; t ^= t >> 8; t ^= t >> 16;
+    return t;
+}
+
+// Serial form (host fuzzing, and the specification of score_slow_kernel in dbpost.cu).  keys[0..nv) are the contour
+// points in trace order; chain / tog are scratch rows of ceil(bbox width / 32) words each.
+B200_HDN double box_score_slow(const float* pred, int h, int w, const uint64_t* keys, int nv, uint32_t* chain, uint32_t* tog) {
+    (void)h;
+    int xmin = key_x(keys[0]), xmax = xmin, ymin = key_y(keys[0]), ymax = ymin;
+    for (int i = 1; i < nv; ++i) {
+        const int x = key_x(keys[i]), y = key_y(keys[i]);
+        xmin = x < xmin ? x : xmin; xmax = x > xmax ? x : xmax;
+        ymin = y < ymin ? y : ymin; ymax = y > ymax ? y : ymax;
+    }
+    const int nw = (xmax - xmin) / 32 + 1;
+    double sum = 0;
+    long long cnt = 0;
+    for (int y = ymin; y <= ymax; ++y) {
+        for (int i = 0; i < nw; ++i) chain[i] = tog[i] = 0u;
+        for (int i = 0; i < nv; ++i) {
+            const uint64_t k0 = keys[i], k1 = keys[i + 1 == nv ? 0 : i + 1];
+            int xa, xb;
+            const int f = edge_on_row(key_x(k0), key_y(k0), key_x(k1), key_y(k1), y, &xa, &xb);
+            if (f & 1)
+                for (int x = xa - xmin; x <= xb - xmin; ++x) chain[x >> 5] |= 1u << (x & 31);
+            if (f & 2) tog[(xa - xmin) >> 5] ^= 1u << ((xa - xmin) & 31);
+        }
+        uint32_t carry = 0;
+        for (int wi = nw - 1; wi >= 0; --wi) {
+            const uint32_t t = tog[wi];
+            uint32_t m = suffix_xor(t) ^ t;                   // crossings strictly to the right, inside this word
+            if (carry) m = ~m;
+            uint32_t pc = t;
+            pc ^= pc >> 16; pc ^= pc >> 8; pc ^= pc >> 4; pc ^= pc >> 2; pc ^= pc >> 1;
+            carry ^= pc & 1u;
+            m |= chain[wi];
+            for (int b = 0; b < 32; ++b)
+                if ((m >> b) & 1u) {
+                    sum += (double)pred[(size_t)y * w + xmin + wi * 32 + b];
+                    ++cnt;
+                }
+        }
+    }
+    return cnt ? sum / (double)cnt : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // unclip (db_postprocess.py:151-157): shapely area/length + ClipperOffset(JT_ROUND, ET_CLOSEDPOLYGON)
 // ---------------------------------------------------------------------------------------------
 B200_HD long long clipper_round(double v) { return v < 0 ? (long long)(v - 0.5) : (long long)(v + 0.5); }

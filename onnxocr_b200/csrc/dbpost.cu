@@ -704,6 +704,139 @@ __global__ void __launch_bounds__(128) score_kernel(const float* __restrict__ pr
     }
 }
 
+// ---- det_db_score_mode = 'slow' (db_postprocess.py:129-132, 199-218): the score is the mean of pred over cv2.fillPoly of
+// the contour itself.  Two kernels, run from db_post_collect (the contour points of all candidates go to one pool whose
+// size the host must know): point counts, then trace + even-odd scan (geom::box_score_slow is the serial specification).
+__global__ void __launch_bounds__(32 * kWarpsPerBlock) slow_count_kernel(const uint8_t* __restrict__ bm, const int* __restrict__ cand,
+                                                                         const int* __restrict__ counts, const uint8_t* __restrict__ valid,
+                                                                         int* __restrict__ npts, int n, int h, int w, int maxc) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int total = 0;
+    for (int p = 0; p < n; ++p) total += counts[p];
+    for (int j = blockIdx.x * kWarpsPerBlock + warp; j < total; j += gridDim.x * kWarpsPerBlock) {
+        int p = 0, r = j;
+        while (r >= counts[p]) { r -= counts[p]; ++p; }
+        const int t = p * maxc + r;
+        if (valid[t] != 1) continue;                  // npts was zeroed by the host
+        const int c = cand[t];
+        const int local = c & (kHoleBit - 1);
+        Bitmap img{bm + (size_t)p * h * w, h, w};
+        const int np = warp_trace_contour(img, local % w, local / w, (c & kHoleBit) != 0, nullptr, 0, lane);
+        if (lane == 0) npts[t] = np;
+    }
+}
+
+constexpr int kSlowWarps = 4;
+// One block per candidate (persistent grid over the dense candidate list): warp 0 traces the contour into the pool, then
+// each warp takes every fourth row of the bounding box: all edges are tested against the row (chain pixels are OR-ed,
+// crossings XOR-ed into two bit rows in shared memory), a suffix parity over the crossing bits gives the interior, and
+// the masked pixels are summed with coalesced loads.  Partial sums meet in a fixed order (deterministic).
+__global__ void __launch_bounds__(32 * kSlowWarps) score_slow_kernel(
+    const float* __restrict__ prob, const uint8_t* __restrict__ bm, const int* __restrict__ cand, const int* __restrict__ counts,
+    const int* __restrict__ npts, const int* __restrict__ offs, uint64_t* __restrict__ pool, uint8_t* __restrict__ valid,
+    double* __restrict__ score, int n, int h, int w, int maxc, double box_thresh, int row_words) {
+    extern __shared__ uint32_t srows[];                // [kSlowWarps][2][row_words]
+    __shared__ double ssum[32 * kSlowWarps];
+    __shared__ long long scnt[32 * kSlowWarps];
+    __shared__ int sbox[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* chain = srows + (size_t)warp * 2 * row_words;
+    uint32_t* tog = chain + row_words;
+    int total = 0;
+    for (int q = 0; q < n; ++q) total += counts[q];
+    for (int j = blockIdx.x; j < total; j += gridDim.x) {
+        int p = 0, r = j;
+        while (r >= counts[p]) { r -= counts[p]; ++p; }
+        const int t = p * maxc + r;
+        if (valid[t] != 1) continue;                  // block-uniform
+        const int nv = npts[t];
+        uint64_t* keys = pool + offs[t];
+        if (warp == 0) {
+            const int c = cand[t];
+            const int local = c & (kHoleBit - 1);
+            Bitmap img{bm + (size_t)p * h * w, h, w};
+            warp_trace_contour(img, local % w, local / w, (c & kHoleBit) != 0, keys, nv, lane);
+        }
+        if (threadIdx.x == 0) { sbox[0] = 0x7fffffff; sbox[1] = -0x7fffffff; sbox[2] = 0x7fffffff; sbox[3] = -0x7fffffff; }
+        __threadfence_block();
+        __syncthreads();
+        {
+            int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
+            for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+                const uint64_t k = keys[i];
+                const int x = key_x(k), y = key_y(k);
+                xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
+            }
+            for (int o = 16; o; o >>= 1) {
+                xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+                ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+            }
+            if (lane == 0) { atomicMin(&sbox[0], xmin); atomicMax(&sbox[1], xmax); atomicMin(&sbox[2], ymin); atomicMax(&sbox[3], ymax); }
+        }
+        __syncthreads();
+        const int xmin = sbox[0], xmax = sbox[1], ymin = sbox[2], ymax = sbox[3];
+        const int nw = (xmax - xmin) / 32 + 1;
+        const float* pred = prob + (size_t)p * h * w;
+        double sum = 0;
+        long long cnt = 0;
+        for (int y = ymin + warp; y <= ymax; y += kSlowWarps) {
+            for (int i = lane; i < nw; i += 32) chain[i] = tog[i] = 0u;
+            __syncwarp();
+            for (int i = lane; i < nv; i += 32) {
+                const uint64_t k0 = keys[i], k1 = keys[i + 1 == nv ? 0 : i + 1];
+                int xa, xb;
+                const int f = edge_on_row(key_x(k0), key_y(k0), key_x(k1), key_y(k1), y, &xa, &xb);
+                if (f & 1) {
+                    xa -= xmin; xb -= xmin;
+                    for (int wi = xa >> 5; wi <= (xb >> 5); ++wi) {
+                        const int lo = max(xa - wi * 32, 0), hi = min(xb - wi * 32, 31);
+                        atomicOr(&chain[wi], (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo));
+                    }
+                    if (f & 2) atomicXor(&tog[xa >> 5], 1u << (xa & 31));
+                }
+            }
+            __syncwarp();
+            unsigned carry = 0;
+            for (int base = ((nw - 1) >> 5) << 5; base >= 0; base -= 32) {
+                const int wi = base + lane;
+                const uint32_t tg = wi < nw ? tog[wi] : 0u;
+                const unsigned odd = __ballot_sync(0xffffffffu, __popc(tg) & 1);
+                const unsigned above = lane == 31 ? 0u : (unsigned)__popc(odd >> (lane + 1)) & 1u;
+                uint32_t m = suffix_xor(tg) ^ tg;
+                if (carry ^ above) m = ~m;
+                m = wi < nw ? (m | chain[wi]) : 0u;
+                carry ^= (unsigned)__popc(odd) & 1u;
+                const unsigned any = __ballot_sync(0xffffffffu, m != 0u);
+                for (unsigned rest = any; rest; rest &= rest - 1) {
+                    const int jw = __ffs(rest) - 1;
+                    const uint32_t mj = __shfl_sync(0xffffffffu, m, jw);
+                    if ((mj >> lane) & 1u) {
+                        sum += (double)pred[(size_t)y * w + xmin + (base + jw) * 32 + lane];
+                        ++cnt;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        ssum[threadIdx.x] = sum;
+        scnt[threadIdx.x] = cnt;
+        __syncthreads();
+        for (int s = 16 * kSlowWarps; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                ssum[threadIdx.x] += ssum[threadIdx.x + s];
+                scnt[threadIdx.x] += scnt[threadIdx.x + s];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const double sc = scnt[0] ? ssum[0] / (double)scnt[0] : 0.0;
+            score[t] = sc;
+            if (box_thresh > sc) valid[t] = 0;        // db_postprocess.py:133
+        }
+        __syncthreads();
+    }
+}
+
 // phase C: unclip -> minAreaRect -> get_mini_boxes -> scale/round/clip
 __global__ void unclip_kernel(const float* __restrict__ box1, uint8_t* __restrict__ valid, int* __restrict__ res_box,
                               const int* __restrict__ src_hw, int n, int h, int w, int maxc, double unclip_ratio, float min_size2) {
@@ -827,6 +960,7 @@ void Stages::db_post_enqueue(int lane, const float* d_prob, int n, int h, int w,
     B200_CUDA_CHECK(cudaMemcpyAsync(h_counts + n + 2, found + n, sizeof(int), cudaMemcpyDeviceToHost, st));
     launches += 6;                                    // init, merge, border, collect, sort, contour (memsets and copies are not kernels)
     auto run_tail = [&]() {
+        if (p.score_mode) return;                     // 'slow' scores need a host-sized point pool: db_post_collect
         score_kernel<<<(unsigned)std::min(nt, 148 * 8), 128, 0, st>>>(d_prob, box1, valid, score, h, w, maxc, p.box_thresh, counts, n);
         unclip_kernel<<<(unsigned)ceil_div(nt, 32), 32, 0, st>>>(box1, valid, res_box, d_src, n, h, w, maxc, p.unclip_ratio,
                                                                   (float)(p.min_size + 2));
@@ -875,6 +1009,7 @@ void Stages::db_post_collect(DbPending* pend, std::vector<int32_t>* boxes, std::
     uint8_t* hv = (uint8_t*)(h_res + (size_t)nt * (8 * sizeof(int) + sizeof(double)));
     size_t tmp_bytes = 0;
     auto run_tail = [&]() {
+        if (p.score_mode) return;                     // 'slow' scores need a host-sized point pool: db_post_collect
         score_kernel<<<(unsigned)std::min(nt, 148 * 8), 128, 0, st>>>(d_prob, box1, valid, score, h, w, maxc, p.box_thresh, counts, n);
         unclip_kernel<<<(unsigned)ceil_div(nt, 32), 32, 0, st>>>(box1, valid, res_box, d_src, n, h, w, maxc, p.unclip_ratio,
                                                                   (float)(p.min_size + 2));
@@ -926,6 +1061,41 @@ void Stages::db_post_collect(DbPending* pend, std::vector<int32_t>* boxes, std::
                                                                        n, h, w, maxc, (float)p.min_size);
         launches += 4;
         run_tail();
+        B200_CUDA_CHECK(cudaMemcpyAsync(hb, res_box, (size_t)nt * 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaMemcpyAsync(hs, score, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaMemcpyAsync(hv, valid, (size_t)nt, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    if (p.score_mode) {
+        // det_db_score_mode 'slow': box1 / valid hold the mini boxes of every candidate that passed the size test; score
+        // them over the filled contour, then the common unclip tail.  Not the default, so it may cost a synchronisation.
+        B200_CUDA_CHECK(cudaMemsetAsync(npts, 0, (size_t)(nt + 1) * sizeof(int), st));
+        slow_count_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nt, kWarpsPerBlock), 148 * 4), 32 * kWarpsPerBlock, 0, st>>>(
+            bm, cand, counts, valid, npts, n, h, w, maxc);
+        size_t tmp3 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp3, npts, offs, nt + 1, st);
+        void* tmpc = W.scan_tmp.get(tmp3 + 256);
+        cub::DeviceScan::ExclusiveSum(tmpc, tmp3, npts, offs, nt + 1, st);
+        B200_CUDA_CHECK(cudaMemcpyAsync(h_counts + n + 1, offs + nt, sizeof(int), cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        const int64_t total_pts = h_counts[n + 1];
+        if (total_pts >= (1 << 20) * (int64_t)64) throw std::runtime_error("bad argument: contour point pool overflow");
+        uint64_t* pool = (uint64_t*)W.keys.get((size_t)(total_pts + 1) * sizeof(uint64_t));
+        const int row_words = w / 32 + 2;
+        const size_t smem = (size_t)kSlowWarps * 2 * row_words * sizeof(uint32_t);
+        static bool attr_set[16] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_set[dev & 15]) {                    // w < 60000: at most 60 KB
+            B200_CUDA_CHECK(cudaFuncSetAttribute(score_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            attr_set[dev & 15] = true;
+        }
+        score_slow_kernel<<<(unsigned)std::max(1, std::min(nt, 148 * 8)), 32 * kSlowWarps, smem, st>>>(
+            d_prob, bm, cand, counts, npts, offs, pool, valid, score, n, h, w, maxc, p.box_thresh, row_words);
+        unclip_kernel<<<(unsigned)ceil_div(nt, 32), 32, 0, st>>>(box1, valid, res_box, d_src, n, h, w, maxc, p.unclip_ratio,
+                                                                  (float)(p.min_size + 2));
+        launches += 4;
+        B200_CUDA_CHECK(cudaGetLastError());
         B200_CUDA_CHECK(cudaMemcpyAsync(hb, res_box, (size_t)nt * 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
         B200_CUDA_CHECK(cudaMemcpyAsync(hs, score, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, st));
         B200_CUDA_CHECK(cudaMemcpyAsync(hv, valid, (size_t)nt, cudaMemcpyDeviceToHost, st));

@@ -59,13 +59,14 @@ class TextDetector(object):
     """predict_det.py:6-120"""
 
     def __init__(self, args):
-        if args.det_algorithm != "DB" or args.det_box_type != "quad" or args.det_db_score_mode != "fast":
-            raise NotImplementedError("only DB / quad / score_mode 'fast' is on the B200 path (SURVEY.md §8f)")
+        if args.det_algorithm != "DB" or args.det_box_type != "quad":
+            raise NotImplementedError("only DB / quad boxes are on the B200 path (SURVEY.md §8f)")
         self.args = args
         self.engine = _engine_for(args)
         self.engine.load_onnx(_lib.DET, args.det_model_dir, _precision(args))
         self.params = _lib.det_params(args.det_limit_side_len, args.det_limit_type, args.det_db_thresh,
-                                      args.det_db_box_thresh, args.det_db_unclip_ratio, 1000, 3, args.use_dilation)
+                                      args.det_db_box_thresh, args.det_db_unclip_ratio, 1000, 3, args.use_dilation,
+                                      args.det_db_score_mode)
 
     def __call__(self, img):
         return self.engine.det_pages([img], self.params)[0]

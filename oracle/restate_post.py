@@ -43,6 +43,22 @@ def box_score_fast(bitmap, _box):
     return cv2.mean(bitmap[ymin:ymax + 1, xmin:xmax + 1], mask)[0]
 
 
+def box_score_slow(bitmap, contour):
+    """db_postprocess.py:199-218"""
+    h, w = bitmap.shape[:2]
+    contour = contour.copy()
+    contour = np.reshape(contour, (-1, 2))
+    xmin = np.clip(np.min(contour[:, 0]), 0, w - 1)
+    xmax = np.clip(np.max(contour[:, 0]), 0, w - 1)
+    ymin = np.clip(np.min(contour[:, 1]), 0, h - 1)
+    ymax = np.clip(np.max(contour[:, 1]), 0, h - 1)
+    mask = np.zeros((ymax - ymin + 1, xmax - xmin + 1), dtype=np.uint8)
+    contour[:, 0] = contour[:, 0] - xmin
+    contour[:, 1] = contour[:, 1] - ymin
+    cv2.fillPoly(mask, contour.reshape(1, -1, 2).astype("int32"), 1)
+    return cv2.mean(bitmap[ymin:ymax + 1, xmin:xmax + 1], mask)[0]
+
+
 def unclip(box, unclip_ratio):
     """db_postprocess.py:151-157"""
     poly = clipper_offset.Polygon(box)
@@ -53,8 +69,8 @@ def unclip(box, unclip_ratio):
 
 
 def boxes_from_bitmap(pred, bitmap, dest_width, dest_height, box_thresh=0.6, unclip_ratio=1.5, max_candidates=1000,
-                      min_size=3):
-    """db_postprocess.py:104-149 (score_mode 'fast', box_type 'quad')"""
+                      min_size=3, score_mode="fast"):
+    """db_postprocess.py:104-149 (box_type 'quad')"""
     height, width = bitmap.shape
     outs = cv2.findContours((bitmap * 255).astype(np.uint8), cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
     contours = outs[0] if len(outs) == 2 else outs[1]
@@ -66,7 +82,10 @@ def boxes_from_bitmap(pred, bitmap, dest_width, dest_height, box_thresh=0.6, unc
         if sside < min_size:
             continue
         points = np.array(points)
-        score = box_score_fast(pred, points.reshape(-1, 2))
+        if score_mode == "fast":
+            score = box_score_fast(pred, points.reshape(-1, 2))
+        else:
+            score = box_score_slow(pred, contour)
         if box_thresh > score:
             continue
         box = unclip(points, unclip_ratio).reshape(-1, 1, 2)
@@ -82,7 +101,7 @@ def boxes_from_bitmap(pred, bitmap, dest_width, dest_height, box_thresh=0.6, unc
 
 
 def db_postprocess(maps, shape_list, thresh=0.3, box_thresh=0.6, unclip_ratio=1.5, max_candidates=1000,
-                   use_dilation=False):
+                   use_dilation=False, score_mode="fast"):
     """DBPostProcess.__call__ db_postprocess.py:220-246.  maps: [N,1,H,W] float32; shape_list: [N,4] float64."""
     pred = maps[:, 0, :, :]
     segmentation = pred > thresh
@@ -93,7 +112,8 @@ def db_postprocess(maps, shape_list, thresh=0.3, box_thresh=0.6, unclip_ratio=1.
             mask = cv2.dilate(np.array(segmentation[b]).astype(np.uint8), np.array([[1, 1], [1, 1]]))
         else:
             mask = segmentation[b]
-        boxes, scores = boxes_from_bitmap(pred[b], mask, src_w, src_h, box_thresh, unclip_ratio, max_candidates)
+        boxes, scores = boxes_from_bitmap(pred[b], mask, src_w, src_h, box_thresh, unclip_ratio, max_candidates,
+                                          score_mode=score_mode)
         out.append((boxes, scores))
     return out
 

@@ -78,6 +78,16 @@ double geom_box_score(const float* pred, int h, int w, const float box[8]) {
     return box_score_fast(pred, h, w, b);
 }
 
+// box_score_slow on the contour that starts at (sx, sy): trace + fillPoly(contour) mean
+double geom_box_score_slow(const float* pred, const uint8_t* bitmap, int h, int w, int sx, int sy, int is_hole) {
+    Bitmap bm{bitmap, h, w};
+    int n = trace_contour(bm, sx, sy, is_hole != 0, nullptr, 0);
+    std::vector<uint64_t> keys(n);
+    trace_contour(bm, sx, sy, is_hole != 0, keys.data(), n);
+    std::vector<uint32_t> chain(w / 32 + 2), tog(w / 32 + 2);
+    return box_score_slow(pred, h, w, keys.data(), n, chain.data(), tog.data());
+}
+
 int geom_unclip(const float box[8], double ratio, int32_t* out_xy, int cap, double* dist) {
     PtF b[4];
     for (int i = 0; i < 4; ++i) { b[i].x = box[2 * i]; b[i].y = box[2 * i + 1]; }

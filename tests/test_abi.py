@@ -47,3 +47,7 @@ def test_det_params_struct_layout(lib_built):
     _lib.lib().b200ocr_det_params_default(ctypes.byref(p))
     assert (p.limit_side_len, p.limit_type, p.max_candidates, p.min_size, p.use_dilation) == (960.0, 0, 1000, 3, 0)
     assert abs(p.thresh - 0.3) < 1e-7 and p.box_thresh == 0.6 and p.unclip_ratio == 1.5
+    assert p.score_mode == 0 and ctypes.sizeof(p) == 48
+    assert _lib.det_params(score_mode="slow").score_mode == 1
+    with pytest.raises(ValueError):
+        _lib.det_params(score_mode="medium")

@@ -23,6 +23,7 @@ def G():
     L = C.CDLL(build_host.build())
     L.geom_min_area_rect.restype = C.c_float
     L.geom_box_score.restype = C.c_double
+    L.geom_box_score_slow.restype = C.c_double
     return L
 
 
@@ -218,6 +219,32 @@ def test_box_score_matches_cv2_mean(G):
         exp = restate_post.box_score_fast(pred, box)
         got = G.geom_box_score(P(pred), h, w, P(np.ascontiguousarray(box)))
         assert abs(got - exp) < 1e-9, (t, got, exp)
+
+
+@pytest.mark.parametrize("seed,noise", [(0, 0.0), (1, 0.02), (2, 0.2), (3, 0.5)])
+def test_box_score_slow_matches_cv2_fillpoly_of_the_contour(G, seed, noise):
+    """det_db_score_mode='slow' (db_postprocess.py:199-218): the mask is cv2.fillPoly of the contour itself, outer and
+    hole contours alike; the product's even-odd scan of the chain must give the same mean (same mask) as cv2."""
+    rng = np.random.default_rng(100 + seed)
+    n_checked = n_holes = 0
+    for it in range(8):
+        h, w = int(rng.integers(16, 120)), int(rng.integers(16, 200))
+        if it % 4 == 3:
+            bm = (cv2.GaussianBlur(rng.random((h, w)).astype(np.float32), (7, 7), 0) * 1.6 > 0.8).astype(np.uint8)
+        else:
+            bm = blob_bitmap(rng, h, w, int(rng.integers(1, 8)), noise=noise)
+        # scores that expose any single-pixel difference of the mask: distinct powers of two would overflow, random is enough
+        pred = rng.random((h, w)).astype(np.float32)
+        ref, _ = cv2.findContours((bm * 255).astype(np.uint8), cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+        starts = contour_starts(bm)
+        assert len(starts) == len(ref)
+        for k, ((sx, sy), hole) in enumerate(starts):
+            exp = restate_post.box_score_slow(pred, ref[k])
+            got = G.geom_box_score_slow(P(pred), P(bm), h, w, sx, sy, hole)
+            assert abs(got - exp) < 1e-12, (it, k, hole, got, exp)
+            n_checked += 1
+            n_holes += hole
+    assert n_checked > 20 and (noise == 0.0 or n_holes > 0)
 
 
 def test_scale_coord_matches_numpy(G):

@@ -81,6 +81,65 @@ def test_db_postprocess_params(engine_fp32):
     check(engine_fp32, prob, 640, 640, _lib.det_params(use_dilation=True), use_dilation=True)
 
 
+@pytest.mark.parametrize("seed,hw,src,holes", [(20, (320, 480), (700, 1000), True), (21, (160, 288), (170, 296), True),
+                                               (22, (960, 960), (960, 960), True), (23, (33, 47), (33, 47), True)])
+def test_db_postprocess_score_mode_slow(engine_fp32, seed, hw, src, holes):
+    """det_db_score_mode='slow' (db_postprocess.py:129-132, 199-218): mean over cv2.fillPoly of the contour itself."""
+    rng = np.random.default_rng(seed)
+    slow = _lib.det_params(score_mode="slow")
+    total = differs = 0
+    for _ in range(3):
+        prob = blob_prob(rng, hw[0], hw[1], int(rng.integers(1, 30)), holes)
+        total += check(engine_fp32, prob, src[0], src[1], slow, score_mode="slow")
+        _, s_fast = engine_fp32.db_postprocess(prob, src[0], src[1])
+        _, s_slow = engine_fp32.db_postprocess(prob, src[0], src[1], slow)
+        differs += len(s_fast) != len(s_slow) or not np.array_equal(s_fast, s_slow)
+    assert total > 0 or hw[0] < 64
+    assert differs > 0 or hw[0] < 64                                       # the option really selects another score
+
+
+def test_db_postprocess_score_mode_slow_hard_maps(engine_fp32):
+    rng = np.random.default_rng(24)
+    slow = _lib.det_params(score_mode="slow", box_thresh=0.3)
+    # blurred noise: ragged contours with holes and islands; a low box threshold keeps many of them
+    prob = cv2.GaussianBlur(rng.random((256, 256)).astype(np.float32), (7, 7), 0) * 1.6
+    assert check(engine_fp32, prob, 512, 512, slow, score_mode="slow", box_thresh=0.3) >= 1
+    # speckle: ~10^4 contours (first 1000 only), one percolating component with a contour far beyond the warp kernel's
+    # shared-memory capacity, more than 16384 roots on the page (candidate fallback) - all before the slow scores
+    prob = rng.random((200, 300)).astype(np.float32)
+    check(engine_fp32, prob, 200, 300, slow, score_mode="slow", box_thresh=0.3)
+    prob = rng.random((512, 768)).astype(np.float32)
+    check(engine_fp32, prob, 512, 768, slow, score_mode="slow", box_thresh=0.3)
+    check(engine_fp32, np.zeros((64, 64), np.float32), 64, 64, slow, score_mode="slow", box_thresh=0.3)
+    check(engine_fp32, np.ones((96, 128), np.float32), 300, 400, slow, score_mode="slow", box_thresh=0.3)
+    # dilation + slow scores, candidate cap
+    prob = blob_prob(rng, 320, 320, 14, True)
+    check(engine_fp32, prob, 640, 640, _lib.det_params(score_mode="slow", use_dilation=True), score_mode="slow", use_dilation=True)
+    check(engine_fp32, prob, 640, 640, _lib.det_params(score_mode="slow", max_candidates=5), score_mode="slow", max_candidates=5)
+
+
+def test_det_pages_score_mode_slow_through_text_detector(engine_fp32):
+    """The option as a user sets it (TextDetector(args) with det_db_score_mode='slow'), batch of pages, streaming path."""
+    pages = [synth_pages.render_page(640, 480, 14, seed=50)[0], synth_pages.render_page(640, 480, 10, seed=51)[0]]
+    slow = _lib.det_params(score_mode="slow")
+    boxes, maps = engine_fp32.det_pages(pages, slow, want_prob=True)
+    n_total = 0
+    for page, b, m in zip(pages, boxes, maps):
+        h, w = m.shape
+        exp, _ = restate_post.db_postprocess(m[None, None], np.array([[float(page.shape[0]), float(page.shape[1]), h / page.shape[0], w / page.shape[1]]]),
+                                             score_mode="slow")[0]
+        exp = restate_post.filter_tag_det_res(exp, page.shape)
+        assert b.shape[0] == len(exp)
+        if len(exp):
+            assert np.array_equal(b, exp)
+        n_total += len(exp)
+    assert n_total > 10
+    got = list(engine_fp32.det_pages_stream([pages, pages], slow))
+    for bb in got:
+        for b, e in zip(bb, boxes):
+            assert np.array_equal(b, e)
+
+
 def _oracle_det(prob, page_shape):
     h, w = prob.shape
     src_h, src_w = page_shape[:2]

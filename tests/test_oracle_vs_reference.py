@@ -64,11 +64,12 @@ def test_crop_and_rec_cls_preprocess_match_reference(ref, model_paths):
         assert np.array_equal(cls.resize_norm_img(got), restate_pre.resize_norm_img(got, 192))
 
 
-def test_db_postprocess_matches_reference(ref):
+@pytest.mark.parametrize("score_mode", ["fast", "slow"])
+def test_db_postprocess_matches_reference(ref, score_mode):
     from onnxocr.db_postprocess import DBPostProcess
     from onnxocr.predict_system import sorted_boxes
     rng = np.random.default_rng(0)
-    pp = DBPostProcess(thresh=0.3, box_thresh=0.6, max_candidates=1000, unclip_ratio=1.5)
+    pp = DBPostProcess(thresh=0.3, box_thresh=0.6, max_candidates=1000, unclip_ratio=1.5, score_mode=score_mode)
     n = 0
     for t in range(8):
         H, W = 320, 480
@@ -87,7 +88,7 @@ def test_db_postprocess_matches_reference(ref):
                 prob[y:y + 3, x:x + 4] = 0
         shape_list = np.array([[700.0, 1000.0, H / 700.0, W / 1000.0]])
         exp = pp({"maps": prob[None, None]}, shape_list)[0]["points"]
-        got, _ = restate_post.db_postprocess(prob[None, None], shape_list)[0]
+        got, _ = restate_post.db_postprocess(prob[None, None], shape_list, score_mode=score_mode)[0]
         assert exp.shape == got.shape and np.array_equal(exp, got)
         if len(exp):
             a = sorted_boxes(exp.astype(np.float32))
