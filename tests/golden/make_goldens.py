@@ -50,6 +50,12 @@ def main():
         h, w = prob.shape
         shape_list = np.array([[float(src[0]), float(src[1]), h / src[0], w / src[1]]])
         out["db_boxes_%d" % k] = pp({"maps": prob[None, None]}, shape_list)[0]["points"]
+    # 2b. the same maps with det_db_score_mode='slow' (box_score_slow, db_postprocess.py:199-218) and a lower box threshold
+    pp_slow = DBPostProcess(thresh=0.3, box_thresh=0.5, max_candidates=1000, unclip_ratio=1.5, score_mode="slow")
+    for k, (prob, src) in enumerate(gi.prob_maps()):
+        h, w = prob.shape
+        shape_list = np.array([[float(src[0]), float(src[1]), h / src[0], w / src[1]]])
+        out["db_boxes_slow_%d" % k] = pp_slow({"maps": prob[None, None]}, shape_list)[0]["points"]
     # 3. crops (utils.get_rotate_crop_image) and rec/cls pre-processing
     args = argparse.Namespace(**{a.dest: a.default for a in infer_args()._actions})
     args.rec_image_shape = "3, 48, 320"

@@ -17,6 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
 import golden_inputs as gi  # noqa: E402
 
+from onnxocr_b200 import _lib  # noqa: E402
 from oracle import restate_post, restate_pre  # noqa: E402
 
 
@@ -44,6 +45,8 @@ def test_oracle_db_postprocess_matches_reference(gold):
         shape = np.array([[float(src[0]), float(src[1]), h / src[0], w / src[1]]])
         boxes, _ = restate_post.db_postprocess(prob[None, None], shape)[0]
         assert np.array_equal(boxes, z["db_boxes_%d" % k])
+        boxes, _ = restate_post.db_postprocess(prob[None, None], shape, box_thresh=0.5, score_mode="slow")[0]
+        assert np.array_equal(boxes, z["db_boxes_slow_%d" % k])
 
 
 def test_oracle_crops_match_reference(gold):
@@ -88,6 +91,8 @@ def test_gpu_db_postprocess_matches_reference(gold, engine_fp32):
     for k, (prob, src) in enumerate(gi.prob_maps()):
         boxes, _ = engine_fp32.db_postprocess(prob, src[0], src[1])
         assert np.array_equal(boxes, z["db_boxes_%d" % k])
+        boxes, _ = engine_fp32.db_postprocess(prob, src[0], src[1], _lib.det_params(box_thresh=0.5, score_mode="slow"))
+        assert np.array_equal(boxes, z["db_boxes_slow_%d" % k])
 
 
 @pytest.mark.gpu
