@@ -6,7 +6,7 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from onnxocr_b200 import pipeline, synth_pages  # noqa: E402
+from onnxocr_b200 import _lib, pipeline, synth_pages  # noqa: E402
 
 secs = float(sys.argv[1]) if len(sys.argv) > 1 else 60
 ocr = pipeline.ONNXPaddleOcr(use_angle_cls=True, precision="bf16")
@@ -23,7 +23,10 @@ while time.time() - t0 < secs:
         res = ocr.ocr_batch(batch)
         lines += sum(len(r) for r in res)
     elif mode == 1:
-        res = ocr.text_detector.batch(batch)
+        if rng.random() < 0.5:
+            res = ocr.text_detector.batch(batch)
+        else:                                    # det_db_score_mode='slow' (runs its scores from db_post_collect)
+            res = ocr.engine.det_pages(batch, _lib.det_params(score_mode="slow", box_thresh=float(rng.uniform(0.3, 0.7))))
         lines += sum(len(r) for r in res)
     elif mode == 2:
         res = ocr.ocr(batch[0])
@@ -31,10 +34,11 @@ while time.time() - t0 < secs:
     elif mode == 4:
         # streaming det with random batch sizes / shapes, checked against the blocking call on a sample
         batches = [[pool[i] for i in rng.integers(0, len(pool), int(rng.integers(1, 18)))] for _ in range(int(rng.integers(1, 7)))]
-        outs = list(ocr.engine.det_pages_stream(batches, ocr.text_detector.params))
+        sp = ocr.text_detector.params if rng.random() < 0.7 else _lib.det_params(score_mode="slow")
+        outs = list(ocr.engine.det_pages_stream(batches, sp))
         lines += sum(len(b) for o in outs for b in o)
         j = int(rng.integers(0, len(batches)))
-        ref = ocr.engine.det_pages(batches[j], ocr.text_detector.params)
+        ref = ocr.engine.det_pages(batches[j], sp)
         assert all(np.array_equal(a, b) for a, b in zip(outs[j], ref)), "streaming det differs from the blocking call"
         pages += sum(len(b) for b in batches)
     else:
