@@ -76,6 +76,28 @@ static void make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t
     if (r != CUDA_SUCCESS) throw std::runtime_error("CUDA error: cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
 }
 
+// Depthwise strip kernel: NHWC activation as a 4-D map {CP, W, H, N}, box {box_c, box_w, box_h, 1}, no swizzle, zero fill.
+void dw_encode_tmap(DwTmap* m, const void* base, int N, int H, int W, int CP, int box_c, int box_w, int box_h) {
+    cuuint64_t gd[4] = {(cuuint64_t)CP, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t gs[3] = {(cuuint64_t)CP * 2, (cuuint64_t)W * CP * 2, (cuuint64_t)H * W * CP * 2};
+    cuuint32_t bx[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode_tiled_fn()(&m->map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gd, gs, bx, es,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("CUDA error: cuTensorMapEncodeTiled (depthwise tile) failed with code " + std::to_string((int)r));
+    m->base = base; m->box_c = box_c; m->box_w = box_w; m->box_h = box_h;
+}
+
+bool dw_tma_enabled() {                    // B200OCR_DW_TMA=0: cp.async tile load (A/B measurements)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200OCR_DW_TMA");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 static bool tc_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -1123,8 +1145,10 @@ void Model::build_steps(Plan& p) {
                         });
                 }
                 const DwP dp0 = dp;
+                std::shared_ptr<DwTmap> dtm(new DwTmap());
                 emit("dwconv " + c.name, [=](cudaStream_t st) {
                     DwP dp = dp0;
+                    DwTmap* tmq = dtm.get();
                     if (dw_gap_buf >= 0) dp.gap = (unsigned long long*)pp->bufptr(dw_gap_buf);
                     if (std::is_same<T, bf16>::value && wb16 && dp.CP % 8 == 0 && dp.kh == dp.kw && (dp.kw == 3 || dp.kw == 5) &&
                         (dp.sw == 1 || dp.sw == 2) && (dp.sh == 1 || dp.sh == 2)) {
@@ -1133,14 +1157,14 @@ void Model::build_steps(Plan& p) {
                         int key = dp.kw * 100 + dp.sh * 10 + dp.sw;
                         if (dw_strip_enabled()) {
                             switch (key) {
-                                case 311: launch_dwconv_strip<3, 1, 1>(xi, wptr, bptr, yo, dp, st); break;
-                                case 312: launch_dwconv_strip<3, 1, 2>(xi, wptr, bptr, yo, dp, st); break;
-                                case 321: launch_dwconv_strip<3, 2, 1>(xi, wptr, bptr, yo, dp, st); break;
-                                case 322: launch_dwconv_strip<3, 2, 2>(xi, wptr, bptr, yo, dp, st); break;
-                                case 511: launch_dwconv_strip<5, 1, 1>(xi, wptr, bptr, yo, dp, st); break;
-                                case 512: launch_dwconv_strip<5, 1, 2>(xi, wptr, bptr, yo, dp, st); break;
-                                case 521: launch_dwconv_strip<5, 2, 1>(xi, wptr, bptr, yo, dp, st); break;
-                                default: launch_dwconv_strip<5, 2, 2>(xi, wptr, bptr, yo, dp, st); break;
+                                case 311: launch_dwconv_strip<3, 1, 1>(xi, wptr, bptr, yo, dp, st, tmq); break;
+                                case 312: launch_dwconv_strip<3, 1, 2>(xi, wptr, bptr, yo, dp, st, tmq); break;
+                                case 321: launch_dwconv_strip<3, 2, 1>(xi, wptr, bptr, yo, dp, st, tmq); break;
+                                case 322: launch_dwconv_strip<3, 2, 2>(xi, wptr, bptr, yo, dp, st, tmq); break;
+                                case 511: launch_dwconv_strip<5, 1, 1>(xi, wptr, bptr, yo, dp, st, tmq); break;
+                                case 512: launch_dwconv_strip<5, 1, 2>(xi, wptr, bptr, yo, dp, st, tmq); break;
+                                case 521: launch_dwconv_strip<5, 2, 1>(xi, wptr, bptr, yo, dp, st, tmq); break;
+                                default: launch_dwconv_strip<5, 2, 2>(xi, wptr, bptr, yo, dp, st, tmq); break;
                             }
                             return;
                         }

@@ -3,6 +3,8 @@
 // T is the storage type (float for the exact fp32 mode, bf16 for the fast mode);
 // accumulation is always fp32.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 #include "pre_kernels.cuh"
 
@@ -226,7 +228,20 @@ struct DwP {
     int kh, kw, sh, sw, pt, pl;
     Epilogue epi;
     unsigned long long* gap = nullptr;   // strip kernel: per (image, channel) sums of the stored outputs for a following SE gate
+    int tma = 0;                         // strip kernel: the halo tile arrives as ONE 4-D TMA box (see dwconv_strip_kernel)
 };
+
+// Tensor map of an NHWC bf16 activation for the strip kernel's halo tile: box = {2 * WPP channels, IC columns, IR rows, 1},
+// no swizzle (the tile lands exactly as the cp.async path lays it out), zero fill outside the tensor.  Defined in engine.cu.
+struct DwTmap {
+    CUtensorMap map;
+    const void* base = nullptr;
+    int box_c = 0, box_w = 0, box_h = 0;
+};
+void dw_encode_tmap(DwTmap* m, const void* base, int N, int H, int W, int CP, int box_c, int box_w, int box_h);
+bool dw_tma_enabled();
+
+__device__ __forceinline__ uint32_t dw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ x, const float* __restrict__ w,
@@ -464,13 +479,14 @@ __device__ __forceinline__ void dw_strip_rows(const uint32_t* __restrict__ col, 
 template <int K, int SH, int SW, int WPP, int TY, bool GAP>
 __global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ bias, bf16* __restrict__ y, const DwP p,
-                                                            int tiles_x, int tiles_y) {
+                                                            int tiles_x, int tiles_y, const __grid_constant__ CUtensorMap tmap) {
     pdl_start();
     constexpr int TX = 256 / WPP;
     constexpr int IR = (TY - 1) * SH + K, IC = (TX - 1) * SW + K;
     constexpr int PS = (SW == 2 && WPP < 32) ? WPP * 3 / 2 : WPP;
     constexpr int G = WPP / 4;                    // 16-byte chunks per pixel
-    extern __shared__ uint32_t dw_tile[];         // [IR][IC][PS]
+    extern __shared__ __align__(128) uint32_t dw_tile[];         // [IR][IC][PS]
+    __shared__ __align__(8) unsigned long long dw_bar;
     int t = blockIdx.x;
     const int tx = t % tiles_x;
     t /= tiles_x;
@@ -481,7 +497,23 @@ __global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restric
     const int iy0 = y0 * SH - p.pt, ix0 = x0 * SW - p.pl;
     const int rows_out = min(TY, p.Ho - y0);
     const int rows_in = (rows_out - 1) * SH + K;
-    {
+    // Halo tile -> shared memory.  With a tensor map (PS == WPP: the tile is dense) ONE thread issues ONE 4-D TMA box
+    // {2 * WPP channels, IC, IR, 1} at (c0, ix0, iy0, n): padding and the ragged last tiles are the TMA unit's out-of-bounds
+    // zero fill, and the ~25 address / predicate instructions per 16-byte chunk of the cp.async loop below (a third of
+    // the warp-issue samples of these kernels in ncu) disappear.
+    const bool use_tma = PS == WPP && p.tma;
+    if (use_tma) {
+        const uint32_t bar = dw_smem_u32(&dw_bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(IR * IC * PS * 4)) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(dw_smem_u32(dw_tile)), "l"(&tmap), "r"(bar), "r"(c0), "r"(ix0), "r"(iy0), "r"(n)
+                : "memory");
+        }
+    } else {
         // thread -> (pixel column block, 16-byte chunk); rows advance by a fixed step so the index math is hoisted
         const int gi = threadIdx.x % G;
         const int ch = c0 + gi * 8;
@@ -510,8 +542,25 @@ __global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restric
         for (int k = 0; k < K * K; ++k) wf[k] = *reinterpret_cast<const f32x2_t*>(w + (int64_t)k * p.CP + c);
         bb = *reinterpret_cast<const f32x2_t*>(bias + c);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
+    if (use_tma) {
+        __syncthreads();                          // the barrier's initialisation is visible to every waiter
+        const uint32_t bar = dw_smem_u32(&dw_bar);
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n"
+                : "=r"(ok)
+                : "r"(bar)
+                : "memory");
+        }
+    } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
     if (!active && !GAP) return;
     float g0 = 0.f, g1 = 0.f;
     if (active) {
@@ -545,7 +594,7 @@ __global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restric
 }
 
 template <int K, int SH, int SW, int WPP>
-inline void launch_dwconv_strip_w(const bf16* x, const float* w, const float* bias, bf16* y, const DwP& p, cudaStream_t st) {
+inline void launch_dwconv_strip_w(const bf16* x, const float* w, const float* bias, bf16* y, const DwP& p, cudaStream_t st, DwTmap* tm) {
     constexpr int TY = SH == 2 ? 8 : 16;
     constexpr int TX = 256 / WPP;
     constexpr int IR = (TY - 1) * SH + K, IC = (TX - 1) * SW + K;
@@ -561,21 +610,30 @@ inline void launch_dwconv_strip_w(const bf16* x, const float* w, const float* bi
     }
     int tiles_x = (p.Wo + TX - 1) / TX, tiles_y = (p.Ho + TY - 1) / TY;
     dim3 grid((unsigned)(tiles_x * tiles_y * p.N), (unsigned)((p.CP + 2 * WPP - 1) / (2 * WPP)));
+    DwP pk = p;
+    static const DwTmap no_map{};
+    const DwTmap* tmu = &no_map;
+    if (PS == WPP && tm && IC <= 256 && IR <= 256 && dw_tma_enabled()) {
+        if (tm->base != (const void*)x || tm->box_c != 2 * WPP || tm->box_w != IC || tm->box_h != IR)
+            dw_encode_tmap(tm, x, p.N, p.H, p.W, p.CP, 2 * WPP, IC, IR);
+        pk.tma = 1;
+        tmu = tm;
+    }
     // the channel-sum variant is a separate instantiation: its extra registers would cost every other layer occupancy
-    if (p.gap) launch_pdl(dwconv_strip_kernel<K, SH, SW, WPP, TY, true>, grid, 256, smem, st, x, w, bias, y, p, tiles_x, tiles_y);
-    else launch_pdl(dwconv_strip_kernel<K, SH, SW, WPP, TY, false>, grid, 256, smem, st, x, w, bias, y, p, tiles_x, tiles_y);
+    if (p.gap) launch_pdl(dwconv_strip_kernel<K, SH, SW, WPP, TY, true>, grid, 256, smem, st, x, w, bias, y, pk, tiles_x, tiles_y, tmu->map);
+    else launch_pdl(dwconv_strip_kernel<K, SH, SW, WPP, TY, false>, grid, 256, smem, st, x, w, bias, y, pk, tiles_x, tiles_y, tmu->map);
 }
 
 template <int K, int SH, int SW>
-inline void launch_dwconv_strip(const bf16* x, const float* w, const float* bias, bf16* y, const DwP& p, cudaStream_t st) {
+inline void launch_dwconv_strip(const bf16* x, const float* w, const float* bias, bf16* y, const DwP& p, cudaStream_t st, DwTmap* tm = nullptr) {
     // channels per block: the candidate with the least channel padding, larger preferred
     auto padded = [&](int cc) { return (p.CP + cc - 1) / cc * cc; };
     int cc = 64;
     if (padded(32) < padded(cc)) cc = 32;
     if (padded(16) < padded(cc)) cc = 16;
-    if (cc == 64) launch_dwconv_strip_w<K, SH, SW, 32>(x, w, bias, y, p, st);
-    else if (cc == 32) launch_dwconv_strip_w<K, SH, SW, 16>(x, w, bias, y, p, st);
-    else launch_dwconv_strip_w<K, SH, SW, 8>(x, w, bias, y, p, st);
+    if (cc == 64) launch_dwconv_strip_w<K, SH, SW, 32>(x, w, bias, y, p, st, tm);
+    else if (cc == 32) launch_dwconv_strip_w<K, SH, SW, 16>(x, w, bias, y, p, st, tm);
+    else launch_dwconv_strip_w<K, SH, SW, 8>(x, w, bias, y, p, st, tm);
 }
 
 // ----------------------------------------------------------------------------------------
