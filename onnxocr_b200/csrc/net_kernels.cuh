@@ -4,6 +4,9 @@
 // accumulation is always fp32.
 #pragma once
 #include <cuda.h>
+#ifndef B200_DW_DENSE_S2
+#define B200_DW_DENSE_S2 1
+#endif
 
 #include "common.cuh"
 #include "pre_kernels.cuh"
@@ -444,7 +447,7 @@ __device__ __forceinline__ void dw_strip_rows(const uint32_t* __restrict__ col, 
                                               const Epilogue& epi, float& g0, float& g1) {
     constexpr int TX = 256 / WPP;
     constexpr int IR = (TY - 1) * SH + K, IC = (TX - 1) * SW + K;
-    constexpr int PS = (SW == 2 && WPP < 32) ? WPP * 3 / 2 : WPP;
+    constexpr int PS = (SW == 2 && WPP < 32 && !B200_DW_DENSE_S2) ? WPP * 3 / 2 : WPP;
     f32x2_t acc[TY];
 #pragma unroll
     for (int r = 0; r < IR; ++r) {
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(256) dwconv_strip_kernel(const bf16* __restric
     pdl_start();
     constexpr int TX = 256 / WPP;
     constexpr int IR = (TY - 1) * SH + K, IC = (TX - 1) * SW + K;
-    constexpr int PS = (SW == 2 && WPP < 32) ? WPP * 3 / 2 : WPP;
+    constexpr int PS = (SW == 2 && WPP < 32 && !B200_DW_DENSE_S2) ? WPP * 3 / 2 : WPP;
     constexpr int G = WPP / 4;                    // 16-byte chunks per pixel
     extern __shared__ __align__(128) uint32_t dw_tile[];         // [IR][IC][PS]
     __shared__ __align__(8) unsigned long long dw_bar;
@@ -598,7 +601,7 @@ inline void launch_dwconv_strip_w(const bf16* x, const float* w, const float* bi
     constexpr int TY = SH == 2 ? 8 : 16;
     constexpr int TX = 256 / WPP;
     constexpr int IR = (TY - 1) * SH + K, IC = (TX - 1) * SW + K;
-    constexpr int PS = (SW == 2 && WPP < 32) ? WPP * 3 / 2 : WPP;
+    constexpr int PS = (SW == 2 && WPP < 32 && !B200_DW_DENSE_S2) ? WPP * 3 / 2 : WPP;
     constexpr size_t smem = (size_t)IR * IC * PS * 4;
     static bool attr[16] = {false};                     // per device: function attributes are per context
     int dev = 0;
