@@ -829,6 +829,7 @@ void Model::build_steps(Plan& p) {
                         }
                     }
                     tp.TW = 128; tp.TH = 1;
+                    int64_t tap_cover = 0;                   // pixels the per-tap kernel's tiles cover (incl. the empty part)
                     if (tp.mode == 1) {
                         int64_t best = -1;
                         for (int tw = 128; tw >= 8; tw >>= 1) {
@@ -836,6 +837,7 @@ void Model::build_steps(Plan& p) {
                             int64_t cover = (int64_t)ceil_div(iv.w, tw) * tw * ceil_div(iv.h, th) * th;
                             if (best < 0 || cover < best) { best = cover; tp.TW = tw; tp.TH = th; }
                         }
+                        tap_cover = best;
                     }
                     tp.tiles_x = (int)ceil_div(iv.w, tp.TW);
                     tp.tiles_y = (int)ceil_div(iv.h, tp.TH);
@@ -867,7 +869,10 @@ void Model::build_steps(Plan& p) {
                     // MMAs of two tiles' accumulators and issues them with running descriptors: 0.067 vs 0.077 ms on the
                     // same layer, det plan 2.18 vs 2.29 ms at 16 pages.  B200OCR_TC_HALO=0 selects the per-tap kernel.
                     static const int halo_on = [] { const char* e = getenv("B200OCR_TC_HALO"); return e ? atoi(e) : 2; }();
-                    const bool halo = tp.mode == 1 && halo_on && c.kh <= 5 && c.kw <= 5;
+                    // The halo tile is a fixed 8 x 16 pixel block: on a flat map (the recogniser's [B, 1, 40] sequence feeds two 3x3
+                    // convolutions) 15 of its 16 rows are empty, five times the tiles of the per-tap kernel's 128 x 1 strip.
+                    const int64_t halo_cover = (int64_t)ceil_div(iv.w, tc::WS_HALO_TW) * tc::WS_HALO_TW * ceil_div(iv.h, tc::WS_HALO_TH) * tc::WS_HALO_TH;
+                    const bool halo = tp.mode == 1 && halo_on && c.kh <= 5 && c.kw <= 5 && halo_cover <= 2 * tap_cover;
                     size_t stage_bytes = tc::WS_A_BYTES;
                     if (halo) {
                         stage_bytes = tc::ws_halo_stage_bytes(c.kh, c.kw);
