@@ -1311,7 +1311,14 @@ void Model::build_steps(Plan& p) {
                 use(in);
                 int64_t total = (int64_t)iv.n * pl.Ho * pl.Wo * iv.cp;
                 cost_bytes = vbytes(in) + vbytes(out);
+                static const bool pool_x8_on = [] { const char* e = getenv("B200OCR_POOL_X8"); return !(e && e[0] == '0'); }();   // A/B switch
+                const bool pool_x8 = pool_x8_on && std::is_same<T, bf16>::value && iv.cp % 8 == 0 && total < ((int64_t)1 << 31) &&
+                                     (int64_t)iv.n * iv.h * iv.w * iv.cp < ((int64_t)1 << 31);
                 emit("pool " + c.name, [=](cudaStream_t st) {
+                    if (pool_x8) {
+                        launch_pdl(pool_bf16x8_kernel, grid_for(total / 8), 256, 0, st, (const bf16*)pp->ptr(in), (bf16*)pp->ptr(out), pl);
+                        return;
+                    }
                     launch_pdl(pool_kernel<T>, grid_for(total), 256, 0, st, (const T*)pp->ptr(in), (T*)pp->ptr(out), pl);
                 });
                 vid[c.out] = out;

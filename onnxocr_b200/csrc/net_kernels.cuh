@@ -993,6 +993,57 @@ __global__ void pool_kernel(const T* __restrict__ x, T* __restrict__ y, const Po
     }
 }
 
+// bf16 activations with CP % 8 == 0: eight channels per thread (16-byte accesses, 32-bit index arithmetic); per channel the
+// same operations in the same order as pool_kernel, so the results are bit-identical.
+__global__ void __launch_bounds__(256) pool_bf16x8_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const PoolP p) {
+    pdl_start();
+    const int cg = p.CP >> 3;
+    const int total = p.N * p.Ho * p.Wo * cg;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int g = i % cg;
+        int q = i / cg;
+        const int ox = q % p.Wo;
+        q /= p.Wo;
+        const int oy = q % p.Ho;
+        const int n = q / p.Ho;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = p.is_max ? -3.4e38f : 0.f;
+        int cnt = 0;
+        for (int ky = 0; ky < p.kh; ++ky) {
+            const int iy = oy * p.sh - p.pt + ky;
+            if ((unsigned)iy >= (unsigned)p.H) continue;
+            for (int kx = 0; kx < p.kw; ++kx) {
+                const int ix = ox * p.sw - p.pl + kx;
+                if ((unsigned)ix >= (unsigned)p.W) continue;
+                const uint4 t = *reinterpret_cast<const uint4*>(x + ((size_t)((n * p.H + iy) * p.W + ix) * p.CP + g * 8));
+                const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float v0 = __uint_as_float(u[j] << 16), v1 = __uint_as_float(u[j] & 0xffff0000u);
+                    acc[2 * j] = p.is_max ? fmaxf(acc[2 * j], v0) : acc[2 * j] + v0;
+                    acc[2 * j + 1] = p.is_max ? fmaxf(acc[2 * j + 1], v1) : acc[2 * j + 1] + v1;
+                }
+                ++cnt;
+            }
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a0 = acc[2 * j], a1 = acc[2 * j + 1];
+            if (!p.is_max) {
+                const float d = (float)(p.count_include_pad ? p.kh * p.kw : max(cnt, 1));
+                a0 = a0 / d;
+                a1 = a1 / d;
+            }
+            const int c = g * 8 + 2 * j;
+            __nv_bfloat162 r = __floats2bfloat162_rn(c < p.C ? a0 : 0.f, c + 1 < p.C ? a1 : 0.f);
+            o[j] = *reinterpret_cast<uint32_t*>(&r);
+        }
+        *reinterpret_cast<uint4*>(y + (size_t)i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // ----------------------------------------------------------------------------------------
 // element-wise: out = epi(a (op) b'), b' = b nearest-upsampled by (fh, fw) and/or broadcast over pixels
 // ----------------------------------------------------------------------------------------
