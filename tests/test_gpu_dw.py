@@ -57,3 +57,40 @@ def test_dwconv_vs_torch(lib_built, tmp_path, c, k, sh, sw, hw, n):
     bad = err > tol
     assert not bad.any(), "max err %g at %s, %d bad of %d" % (err.max(), np.unravel_index(err.argmax(), err.shape), bad.sum(), bad.size)
     eng.close()
+
+
+_AB_SCRIPT = r"""
+import sys, hashlib
+import numpy as np
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, %(tests)r)
+import test_gpu_dw as t
+from onnxocr_b200 import _lib
+h = hashlib.sha256()
+for c, k, sh, sw, hw, n in t.CASES:
+    path = %(tmp)r + "/dw_%%d_%%d_%%d_%%d.onnx" %% (c, k, sh, sw)
+    t.dw_model(path, c, k, sh, sw)
+    eng = _lib.Engine(0)
+    eng.load_onnx(_lib.DET, path, _lib.BF16)
+    x = t.bf16_round(np.random.default_rng(3).standard_normal((n, c, hw[0], hw[1])).astype(np.float32))
+    h.update(eng.session_run(_lib.DET, x).tobytes())
+    eng.close()
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_dwconv_tma_tile_equals_cpasync_tile(lib_built, tmp_path):
+    """The halo tile loaded as one TMA box (default) and by the cp.async loop (B200OCR_DW_TMA=0, read once per process)
+    must give bit-identical outputs on every variant, incl. the stride-2 ones whose tile layout lost its padding."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = _AB_SCRIPT % {"root": root, "tests": os.path.join(root, "tests"), "tmp": str(tmp_path)}
+    digests = []
+    for flag in ("1", "0"):
+        env = dict(os.environ, B200OCR_DW_TMA=flag)
+        r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append([l for l in r.stdout.splitlines() if l.startswith("DIGEST")][0])
+    assert digests[0] == digests[1]
